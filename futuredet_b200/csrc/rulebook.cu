@@ -1,0 +1,278 @@
+// Rulebook construction for SubMConv3d / SparseConv3d on sm_100a.
+//
+// spconv 1.x (external to the reference; call sites det3d/models/backbones/scn.py:98-146)
+// builds `indice_pairs` with a dense B*D*H*W int32 grid plus a thrust sort/unique per
+// strided layer.  Here:
+//   * coordinate -> row lookups go through a small open-addressing hash (L2 resident);
+//   * the active output set of a strided conv is a *bitmap* over the output grid
+//     (1 bit per cell, 1.4 MB for 21x720x720) + a popcount scan, which yields the
+//     ascending-linear-index order of spconv's sort+unique with no sort at all;
+//   * the rulebook is stored in gather form nbr[k][o] (input row or -1), which is what
+//     the output-stationary implicit-GEMM kernels consume -- no scatter atomics, so the
+//     convolution is deterministic.  fd_rulebook_to_pairs() exports spconv's layout.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace fd {
+
+struct Shape3 { int d, h, w; };
+struct Conv3Geom { int k[3], s[3], p[3]; };
+
+__device__ __forceinline__ long long lin_key(int b, int z, int y, int x, Shape3 sh) {
+  return (((long long)b * sh.d + z) * sh.h + y) * sh.w + x;
+}
+
+__global__ void __launch_bounds__(256)
+coord_index_insert(const int4* __restrict__ coords, const int32_t* __restrict__ d_n, int n_cap, Shape3 sh,
+                   long long* __restrict__ keys, int* __restrict__ vals, uint32_t mask) {
+  int n = d_n ? min(*d_n, n_cap) : n_cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    long long key = lin_key(c.x, c.y, c.z, c.w, sh);
+    uint32_t h = hash64((uint64_t)key) & mask;
+    while (true) {
+      long long prev = atomicCAS((unsigned long long*)&keys[h], (unsigned long long)kEmptyKey,
+                                 (unsigned long long)key);
+      if (prev == kEmptyKey || prev == key) break;
+      h = (h + 1) & mask;
+    }
+    vals[h] = i;
+  }
+}
+
+__device__ __forceinline__ int coord_index_find(const long long* __restrict__ keys, const int* __restrict__ vals,
+                                                uint32_t mask, long long key) {
+  uint32_t h = hash64((uint64_t)key) & mask;
+  while (true) {
+    long long k = keys[h];
+    if (k == key) return vals[h];
+    if (k == kEmptyKey) return -1;
+    h = (h + 1) & mask;
+  }
+}
+
+// mark every output cell reachable from an active input: out = (in + p - k) / s when divisible
+__global__ void __launch_bounds__(256)
+outset_mark(const int4* __restrict__ coords, const int32_t* __restrict__ d_n, int n_cap, Conv3Geom g,
+            Shape3 osh, uint32_t* __restrict__ bitmap) {
+  int n = min(*d_n, n_cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    for (int kz = 0; kz < g.k[0]; ++kz) {
+      int tz = c.y + g.p[0] - kz;
+      if (tz < 0 || tz % g.s[0]) continue;
+      int oz = tz / g.s[0];
+      if (oz >= osh.d) continue;
+      for (int ky = 0; ky < g.k[1]; ++ky) {
+        int ty = c.z + g.p[1] - ky;
+        if (ty < 0 || ty % g.s[1]) continue;
+        int oy = ty / g.s[1];
+        if (oy >= osh.h) continue;
+        for (int kx = 0; kx < g.k[2]; ++kx) {
+          int tx = c.w + g.p[2] - kx;
+          if (tx < 0 || tx % g.s[2]) continue;
+          int ox = tx / g.s[2];
+          if (ox >= osh.w) continue;
+          long long key = lin_key(c.x, oz, oy, ox, osh);
+          atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+        }
+      }
+    }
+  }
+}
+
+// enumerate set bits in ascending order -> out coords
+__global__ void __launch_bounds__(256)
+outset_emit(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ prefix, int64_t words, Shape3 osh,
+            int4* __restrict__ out_coords, int n_out_cap) {
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t bits = bitmap[w];
+    int row = prefix[w];
+    while (bits) {
+      int j = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (row < n_out_cap) {
+        long long key = w * 32 + j;
+        int x = (int)(key % osh.w); key /= osh.w;
+        int y = (int)(key % osh.h); key /= osh.h;
+        int z = (int)(key % osh.d); key /= osh.d;
+        out_coords[row] = make_int4((int)key, z, y, x);
+      }
+      ++row;
+    }
+  }
+}
+
+__global__ void clamp_count(int32_t* n, int cap) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && *n > cap) *n = cap;
+}
+
+// nbr[k][o]: one thread per output row, loop over kernel offsets (warp-uniform k -> ballot count)
+__global__ void __launch_bounds__(256)
+neighbors_kernel(const int4* __restrict__ out_coords, const int32_t* __restrict__ d_n, int n_cap,
+                 const long long* __restrict__ keys, const int* __restrict__ vals, uint32_t mask,
+                 Shape3 ish, Conv3Geom g, int* __restrict__ nbr, int nbr_stride, int* __restrict__ pair_num) {
+  const int n = d_n ? min(*d_n, n_cap) : n_cap;
+  const int K = g.k[0] * g.k[1] * g.k[2];
+  const int lane = threadIdx.x & 31;
+  const int n_round = (n + 31) & ~31;  // keep warps converged for the ballots
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_round; o += gridDim.x * blockDim.x) {
+    const bool live = o < n;
+    int4 c = live ? out_coords[o] : make_int4(0, 0, 0, 0);
+    const int z0 = c.y * g.s[0] - g.p[0], y0 = c.z * g.s[1] - g.p[1], x0 = c.w * g.s[2] - g.p[2];
+    int k = 0;
+    for (int kz = 0; kz < g.k[0]; ++kz)
+      for (int ky = 0; ky < g.k[1]; ++ky)
+        for (int kx = 0; kx < g.k[2]; ++kx, ++k) {
+          int z = z0 + kz, y = y0 + ky, x = x0 + kx;
+          int r = -1;
+          if (live && z >= 0 && z < ish.d && y >= 0 && y < ish.h && x >= 0 && x < ish.w)
+            r = coord_index_find(keys, vals, mask, lin_key(c.x, z, y, x, ish));
+          if (live) nbr[(size_t)k * nbr_stride + o] = r;
+          unsigned m = __ballot_sync(0xffffffffu, r >= 0);
+          if (lane == 0 && m) atomicAdd(&pair_num[k], __popc(m));
+        }
+  }
+  (void)K;
+}
+
+// ---- export to spconv layout ----------------------------------------------------
+struct LoadValid {
+  const int* nbr;
+  int nbr_stride;
+  const int32_t* d_n;
+  int n_cap;
+  __device__ __forceinline__ int operator()(int64_t i) const {
+    int n = d_n ? min(*d_n, n_cap) : n_cap;
+    return (int)(i % nbr_stride) < n && nbr[i] >= 0;
+  }
+};
+
+__global__ void __launch_bounds__(256)
+pairs_emit(const int* __restrict__ nbr, int nbr_stride, const int32_t* __restrict__ d_n, int n_cap,
+           const int32_t* __restrict__ pos, int32_t* __restrict__ pairs, int pair_cap, int k) {
+  int n = d_n ? min(*d_n, n_cap) : n_cap;
+  const int* row = nbr + (size_t)k * nbr_stride;
+  const int32_t* prow = pos + (size_t)k * nbr_stride;
+  int base = prow[0];
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+    int i = row[o];
+    if (i >= 0) {
+      int q = prow[o] - base;
+      if (q < pair_cap) {
+        pairs[((size_t)k * 2 + 0) * pair_cap + q] = i;
+        pairs[((size_t)k * 2 + 1) * pair_cap + q] = o;
+      }
+    }
+  }
+}
+
+static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace fd
+
+extern "C" {
+
+int fd_coord_index_build(const int32_t* d_coords4, const int32_t* d_n, int n_cap, const int32_t* shape3,
+                         int64_t* d_keys, int32_t* d_vals, int64_t cap, void* stream_) {
+  using namespace fd;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FD_REQUIRE(d_coords4 && shape3 && d_keys && d_vals, "fd_coord_index_build: null argument");
+  FD_REQUIRE(is_pow2(cap) && cap >= 2 * (int64_t)n_cap && cap <= (1LL << 31),
+             "fd_coord_index_build: cap %lld must be a power of two >= 2*n_cap (%d)", (long long)cap, n_cap);
+  FD_REQUIRE(((uintptr_t)d_coords4 & 15) == 0, "fd_coord_index_build: coords must be 16-byte aligned");
+  FD_CUDA(cudaMemsetAsync(d_keys, 0xff, sizeof(int64_t) * cap, stream));
+  if (n_cap <= 0) return 0;
+  Shape3 sh{shape3[0], shape3[1], shape3[2]};
+  coord_index_insert<<<persistent_grid(ceil_div(n_cap, 256), 8), 256, 0, stream>>>(
+      (const int4*)d_coords4, d_n, n_cap, sh, (long long*)d_keys, d_vals, (uint32_t)(cap - 1));
+  FD_LAUNCHED();
+  return 0;
+}
+
+int fd_rulebook_out_coords(const int32_t* d_in_coords4, const int32_t* d_n_in, int n_in_cap, int B,
+                           const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
+                           const int32_t* pad3, const int32_t* out_shape3, uint32_t* d_bitmap,
+                           int32_t* d_wordprefix, void* d_scan_tmp, int32_t* d_out_coords4, int n_out_cap,
+                           int32_t* d_n_out, void* stream_) {
+  using namespace fd;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FD_REQUIRE(d_in_coords4 && d_n_in && in_shape3 && ksize3 && stride3 && pad3 && out_shape3 && d_bitmap &&
+                 d_wordprefix && d_scan_tmp && d_out_coords4 && d_n_out,
+             "fd_rulebook_out_coords: null argument");
+  Conv3Geom g;
+  for (int j = 0; j < 3; ++j) {
+    g.k[j] = ksize3[j]; g.s[j] = stride3[j]; g.p[j] = pad3[j];
+    FD_REQUIRE(g.k[j] >= 1 && g.s[j] >= 1 && g.p[j] >= 0, "fd_rulebook_out_coords: bad conv geometry");
+    int expect = (in_shape3[j] + 2 * g.p[j] - g.k[j]) / g.s[j] + 1;
+    FD_REQUIRE(out_shape3[j] == expect, "fd_rulebook_out_coords: out_shape[%d]=%d, expected %d", j,
+               out_shape3[j], expect);
+  }
+  Shape3 osh{out_shape3[0], out_shape3[1], out_shape3[2]};
+  int64_t cells = (int64_t)B * osh.d * osh.h * osh.w;
+  FD_REQUIRE(cells > 0 && cells < (1LL << 36), "fd_rulebook_out_coords: output grid too large");
+  int64_t words = (cells + 31) / 32;
+  FD_CUDA(cudaMemsetAsync(d_bitmap, 0, sizeof(uint32_t) * words, stream));
+  if (n_in_cap > 0) {
+    outset_mark<<<persistent_grid(ceil_div(n_in_cap, 256), 8), 256, 0, stream>>>(
+        (const int4*)d_in_coords4, d_n_in, n_in_cap, g, osh, d_bitmap);
+    FD_LAUNCHED();
+  }
+  int rc = exclusive_scan_popc(d_bitmap, d_wordprefix, words, d_n_out, d_scan_tmp, stream);
+  if (rc) return rc;
+  outset_emit<<<persistent_grid(ceil_div(words, 256), 8), 256, 0, stream>>>(
+      d_bitmap, d_wordprefix, words, osh, (int4*)d_out_coords4, n_out_cap);
+  FD_LAUNCHED();
+  clamp_count<<<1, 32, 0, stream>>>(d_n_out, n_out_cap);
+  FD_LAUNCHED();
+  return 0;
+}
+
+int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, int n_out_cap,
+                          const int64_t* d_in_keys, const int32_t* d_in_vals, int64_t in_cap,
+                          const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
+                          const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
+                          void* stream_) {
+  using namespace fd;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FD_REQUIRE(d_out_coords4 && d_in_keys && d_in_vals && in_shape3 && ksize3 && stride3 && pad3 && d_nbr &&
+                 d_pair_num,
+             "fd_rulebook_neighbors: null argument");
+  FD_REQUIRE(is_pow2(in_cap), "fd_rulebook_neighbors: in_cap must be a power of two");
+  FD_REQUIRE(nbr_stride >= n_out_cap, "fd_rulebook_neighbors: nbr_stride < n_out_cap");
+  Conv3Geom g;
+  for (int j = 0; j < 3; ++j) { g.k[j] = ksize3[j]; g.s[j] = stride3[j]; g.p[j] = pad3[j]; }
+  const int K = g.k[0] * g.k[1] * g.k[2];
+  FD_REQUIRE(K >= 1 && K <= 343, "fd_rulebook_neighbors: kernel volume %d unsupported", K);
+  FD_CUDA(cudaMemsetAsync(d_pair_num, 0, sizeof(int32_t) * K, stream));
+  if (n_out_cap <= 0) return 0;
+  Shape3 ish{in_shape3[0], in_shape3[1], in_shape3[2]};
+  neighbors_kernel<<<persistent_grid(ceil_div(n_out_cap, 256), 8), 256, 0, stream>>>(
+      (const int4*)d_out_coords4, d_n_out, n_out_cap, (const long long*)d_in_keys, d_in_vals,
+      (uint32_t)(in_cap - 1), ish, g, d_nbr, nbr_stride, d_pair_num);
+  FD_LAUNCHED();
+  return 0;
+}
+
+int fd_rulebook_to_pairs(const int32_t* d_nbr, int nbr_stride, const int32_t* d_n_out, int n_out_cap, int K,
+                         int32_t* d_pairs, int pair_cap, void* d_scan_tmp, void* stream_) {
+  // d_scan_tmp: fd_scan_tmp_bytes(K*nbr_stride) + K*nbr_stride*4 bytes (positions)
+  using namespace fd;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FD_REQUIRE(d_nbr && d_pairs && d_scan_tmp && K >= 1, "fd_rulebook_to_pairs: null argument");
+  int64_t total = (int64_t)K * nbr_stride;
+  int32_t* pos = (int32_t*)d_scan_tmp;
+  void* tmp = (char*)d_scan_tmp + ((sizeof(int32_t) * total + 255) & ~(size_t)255);
+  FD_CUDA(cudaMemsetAsync(d_pairs, 0xff, sizeof(int32_t) * 2 * (size_t)K * pair_cap, stream));
+  int rc = scan_impl(LoadValid{d_nbr, nbr_stride, d_n_out, n_out_cap}, pos, total, nullptr, tmp, stream);
+  if (rc) return rc;
+  for (int k = 0; k < K; ++k) {
+    pairs_emit<<<persistent_grid(ceil_div(n_out_cap, 256), 4), 256, 0, stream>>>(
+        d_nbr, nbr_stride, d_n_out, n_out_cap, pos, d_pairs, pair_cap, k);
+    FD_LAUNCHED();
+  }
+  return 0;
+}
+
+}  // extern "C"

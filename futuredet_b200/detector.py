@@ -1,0 +1,122 @@
+"""VoxelNet single-stage detector: reader -> sparse backbone -> BEV neck -> CenterHead.
+
+Keeps det3d's detector API (det3d/models/detectors/base.py:10-70, single_stage.py:11-61, voxelnet.py:8-56):
+`VoxelNet(reader, backbone, neck, bbox_head, train_cfg, test_cfg, pretrained)`, `extract_feat(data)`,
+`forward(example, return_loss=True)` over the collated `example` dict of
+det3d/torchie/parallel/collate.py:163-245.
+
+Additive GPU-resident entry: `forward_points(points, batch_offsets)` takes the raw concatenated
+multi-sweep points [sum N, 5] and runs the fused voxelize+VFE kernel in place of the reference's CPU
+voxelizer + H2D copy of padded voxels + VFE.
+"""
+import logging
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .registry import DETECTORS, build_backbone, build_head, build_neck, build_reader
+
+
+class BaseDetector(nn.Module):
+    """Detector base (base.py:10-70): feature flags + train/test dispatch."""
+
+    def __init__(self):
+        super().__init__()
+        self.fp16_enabled = False
+
+    @property
+    def with_reader(self):
+        return getattr(self, "reader", None) is not None
+
+    @property
+    def with_neck(self):
+        return getattr(self, "neck", None) is not None
+
+    @property
+    def with_bbox(self):
+        return getattr(self, "bbox_head", None) is not None
+
+    def init_weights(self, pretrained=None):
+        if pretrained is not None:
+            logging.getLogger().info("load model from: %s", pretrained)
+
+
+class SingleStageDetector(BaseDetector):
+    def __init__(self, reader, backbone, neck=None, bbox_head=None, train_cfg=None, test_cfg=None, pretrained=None):
+        super().__init__()
+        self.reader = build_reader(reader)
+        self.backbone = build_backbone(backbone)
+        if neck is not None:
+            self.neck = build_neck(neck)
+        self.bbox_head = build_head(bbox_head)
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+        self.init_weights(pretrained=pretrained)
+
+    def init_weights(self, pretrained=None):
+        if pretrained is None:
+            return
+        sd = torch.load(pretrained, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+        self.load_state_dict(sd, strict=False)
+
+
+@DETECTORS.register_module
+class VoxelNet(SingleStageDetector):
+    def __init__(self, reader, backbone, neck, bbox_head, train_cfg=None, test_cfg=None, pretrained=None):
+        super().__init__(reader, backbone, neck, bbox_head, train_cfg, test_cfg, pretrained)
+        self.voxel_cfg = None      # set by configure_voxelizer() for forward_points()
+
+    def extract_feat(self, data):
+        if "mean_features" in data:          # fused path: VFE already done by the voxelizer
+            feats = data["mean_features"]
+        else:
+            feats = self.reader(data["features"], data["num_voxels"])
+        x, voxel_feature = self.backbone(feats, data["coors"], data["batch_size"], data["input_shape"],
+                                         n_dev=data.get("n_dev"), n_cap=data.get("n_cap"))
+        if self.with_neck:
+            x = self.neck(x)
+        return x, voxel_feature
+
+    def forward(self, example, return_loss=True, **kwargs):
+        num_voxels = example["num_voxels"]
+        data = dict(features=example["voxels"], num_voxels=example["num_points"], coors=example["coordinates"],
+                    batch_size=len(num_voxels), input_shape=example["shape"][0])
+        x, _ = self.extract_feat(data)
+        preds = self.bbox_head(x, None)
+        if return_loss:
+            return self.bbox_head.loss(example, preds)
+        return self.bbox_head.predict(example, preds, self.test_cfg)
+
+    # ---- fused GPU-resident path ----------------------------------------------------------------------
+    def configure_voxelizer(self, voxel_generator_cfg, training=False):
+        """voxel_generator_cfg: the config's `voxel_generator` dict (range, voxel_size, max_points_in_voxel,
+        max_voxel_num=[train, test]); picks the cap as preprocess.py:249-258 does."""
+        mv = voxel_generator_cfg["max_voxel_num"]
+        max_voxels = (mv[0] if training else mv[1]) if isinstance(mv, (list, tuple)) else mv
+        self.voxel_cfg = dict(range=[float(v) for v in voxel_generator_cfg["range"]],
+                              voxel_size=[float(v) for v in voxel_generator_cfg["voxel_size"]],
+                              max_points=int(voxel_generator_cfg["max_points_in_voxel"]), max_voxels=int(max_voxels))
+        return self
+
+    def voxelize(self, points, batch_offsets):
+        c = self.voxel_cfg
+        if c is None:
+            raise RuntimeError("call configure_voxelizer(cfg.voxel_generator) before forward_points()")
+        return ops.voxelize_vfe(points, batch_offsets, c["voxel_size"], c["range"], c["max_points"], c["max_voxels"],
+                                num_feat=self.reader.num_input_features)
+
+    def forward_points(self, points, batch_offsets, return_voxels=False):
+        """points [sum N, >=5] fp32 CUDA, batch_offsets [B+1] int32 CUDA -> CenterHead predictions."""
+        c = self.voxel_cfg
+        vox = self.voxelize(points, batch_offsets)
+        B = batch_offsets.numel() - 1
+        grid = ops.grid_size_of(c["range"], c["voxel_size"])
+        data = dict(mean_features=vox["features"], coors=vox["coords"], batch_size=B, input_shape=grid,
+                    n_dev=vox["total"], n_cap=vox["coords"].shape[0])
+        x, _ = self.extract_feat(data)
+        preds = self.bbox_head(x, None)
+        return (preds, vox) if return_voxels else preds

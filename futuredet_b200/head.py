@@ -1,0 +1,189 @@
+"""CenterHead / SepHead (multi-timestep CenterPoint heatmap + regression heads) on the native kernels.
+
+Constructor arguments, module tree and state_dict keys follow det3d/models/bbox_heads/center_head.py:81-152
+(SepHead) and :231-390 (CenterHead): `shared_conv.{0,1}`, `tasks.{t}.{reg,height,dim,rot,vel,hm}.{0,1,3}`.
+`vel` carries 2*timesteps channels (:354-356) -- this is the multi-timestep head of the forecast_n3 configs.
+
+forward() in the standard mode (all variant flags False, as in every BASELINE config) runs
+  1 kernel : shared 3x3 conv 512->64 + bias + BN + ReLU
+  1 kernel : the first 3x3 conv of all heads of a task fused into one 64 -> 64*n_heads GEMM (+bias+BN+ReLU)
+  n kernels: per head 3x3 conv 64 -> c (+bias), each reading its channel slice of the fused activation and
+             writing its channel slice of one [B,H,W,sum c] output tensor.
+The torch modules are parameter containers; no torch arithmetic runs in forward().
+"""
+import copy
+import logging
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .neck import conv_weight_kio, run_conv, to_nhwc
+from .registry import HEADS
+from .sparse import folded_epilogue
+
+
+class SepHead(nn.Module):
+    def __init__(self, in_channels, heads, head_conv=64, final_kernel=1, bn=False, init_bias=-2.19,
+                 two_stage=False, forecast_feature=False, wide_head=False, **kwargs):
+        super().__init__(**kwargs)
+        if two_stage or forecast_feature or wide_head:
+            raise NotImplementedError("SepHead: two_stage / forecast_feature / wide_head variants are outside the "
+                                      "hot-path scope (SURVEY.md section 8f-4)")
+        self.heads = heads
+        self.two_stage, self.forecast_feature, self.wide_head = two_stage, forecast_feature, wide_head
+        for head in self.heads:
+            classes, num_conv = self.heads[head]
+            layers = []
+            for _ in range(num_conv - 1):
+                layers.append(nn.Conv2d(head_conv, head_conv, kernel_size=final_kernel, stride=1,
+                                        padding=final_kernel // 2, bias=True))
+                if bn:
+                    layers.append(nn.BatchNorm2d(head_conv))
+                layers.append(nn.ReLU())
+            layers.append(nn.Conv2d(head_conv, classes, kernel_size=final_kernel, stride=1,
+                                    padding=final_kernel // 2, bias=True))
+            fc = nn.Sequential(*layers)
+            if "hm" in head:
+                fc[-1].bias.data.fill_(init_bias)
+            else:
+                for m in fc.modules():
+                    if isinstance(m, nn.Conv2d):
+                        nn.init.kaiming_normal_(m.weight, a=0, mode="fan_out", nonlinearity="relu")
+                        nn.init.constant_(m.bias, 0)
+            self.__setattr__(head, fc)
+
+    # ---- fused execution plan -------------------------------------------------------------------------
+    def _stage_groups(self):
+        """[(conv, bn|None, relu)] per head, split into layers."""
+        per_head = {}
+        for head in self.heads:
+            mods = list(getattr(self, head))
+            steps, i = [], 0
+            while i < len(mods):
+                conv = mods[i]
+                bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d) else None
+                j = i + 1 + (bn is not None)
+                relu = j < len(mods) and isinstance(mods[j], nn.ReLU)
+                steps.append((conv, bn, relu))
+                i = j + int(relu)
+            per_head[head] = steps
+        return per_head
+
+    def _fused_first(self, groups):
+        """Concatenate the first conv (+folded BN) of every head along Cout; cached on parameter versions."""
+        firsts = [groups[h][0] for h in self.heads]
+        key = tuple((c.weight.data_ptr(), c.weight._version, c.bias._version,
+                     None if b is None else (b.weight._version, b.bias._version, b.running_mean._version,
+                                             b.running_var._version, b.training)) for c, b, _ in firsts)
+        cache = self.__dict__.setdefault("_fused_cache", {})
+        if cache.get("k") != key:
+            ws, scs, shs = [], [], []
+            for conv, bnm, _ in firsts:
+                ws.append(conv_weight_kio(conv))
+                sc, sh = folded_epilogue(conv, bnm)
+                scs.append(sc if sc is not None else torch.ones_like(sh))
+                shs.append(sh)
+            cache["v"] = (torch.cat(ws, dim=2).contiguous(), torch.cat(scs).contiguous(), torch.cat(shs).contiguous())
+            cache["k"] = key
+        return cache["v"]
+
+    def forward(self, x, precision=None):
+        """x: channels-last [B,H,W,C] view (or logical NCHW).  Returns {head: logical [B,c,H,W]}."""
+        if x.dim() == 4 and x.stride(3) != 1:
+            x = to_nhwc(x)
+        from . import neck as _neck
+        prec = precision or _neck.DEFAULT_PRECISION
+        groups = self._stage_groups()
+        names = list(self.heads)
+        B, H, W, _ = x.shape
+        total_c = sum(self.heads[h][0] for h in names)
+        out = torch.empty((B, H, W, total_c), dtype=torch.float32, device=x.device)
+        fuse = all(len(groups[h]) == 2 for h in names) and len({groups[h][0][0].kernel_size for h in names}) == 1
+        ret, col = {}, 0
+        if fuse:
+            w, sc, sh = self._fused_first(groups)
+            c0 = groups[names[0]][0][0]
+            mid = ops.conv2d_nhwc(x, w, c0.kernel_size, c0.stride, c0.padding, sc, sh, True, precision=prec)
+            hc = c0.out_channels
+            for i, h in enumerate(names):
+                conv, bnm, relu = groups[h][1]
+                c = conv.out_channels
+                run_conv(mid[..., i * hc:(i + 1) * hc], conv, bnm, relu, out=out[..., col:col + c], precision=prec)
+                ret[h] = out[..., col:col + c].permute(0, 3, 1, 2)
+                col += c
+        else:
+            for h in names:
+                y = x
+                steps = groups[h]
+                for si, (conv, bnm, relu) in enumerate(steps):
+                    last = si == len(steps) - 1
+                    c = conv.out_channels
+                    y = run_conv(y, conv, bnm, relu, out=out[..., col:col + c] if last else None, precision=prec)
+                ret[h] = out[..., col:col + c].permute(0, 3, 1, 2)
+                col += c
+        return ret
+
+
+@HEADS.register_module
+class CenterHead(nn.Module):
+    def __init__(self, in_channels=[128, ], tasks=[], dataset="nuscenes", weight=0.25, code_weights=[],
+                 common_heads=dict(), logger=None, init_bias=-2.19, share_conv_channel=64, num_hm_conv=2,
+                 dcn_head=False, timesteps=1, two_stage=False, reverse=False, sparse=False, dense=False,
+                 bev_map=False, forecast_feature=False, classify=True, wide_head=False):
+        super().__init__()
+        self.two_stage, self.reverse, self.sparse, self.dense = two_stage, reverse, sparse, dense
+        self.bev_map, self.forecast_feature, self.classify, self.wide_head = bev_map, forecast_feature, classify, wide_head
+        self.target_timesteps = 7
+        self.standard = not (reverse or sparse or dense or classify or wide_head)
+        if not self.standard or two_stage or bev_map or forecast_feature or dcn_head:
+            raise NotImplementedError(
+                "CenterHead: only the standard mode (reverse/sparse/dense/classify/wide_head/two_stage/bev_map/"
+                "forecast_feature/dcn_head all False, as in the n0/n3 configs) is on the hot path; other variants "
+                "are listed as 'next' in SURVEY.md section 8f-4")
+        num_classes = [len(t["class_names"]) for t in tasks]
+        self.class_names = [t["class_names"] for t in tasks]
+        self.code_weights = code_weights
+        self.box_n_dim = 7
+        if all(k in common_heads for k in ("vel", "rvel", "rot", "rrot")):
+            self.box_n_dim = 13
+            self.code_weights_forecast = list(np.array(code_weights) * np.array([0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0]))
+        elif "vel" in common_heads and "rot" in common_heads:
+            self.box_n_dim = 9
+            self.code_weights_forecast = list(np.array(code_weights) * np.array([0, 0, 0, 0, 0, 0, 1, 1, 0, 0]))
+        self.weight = weight
+        self.dataset = dataset
+        self.in_channels = in_channels
+        self.num_classes = num_classes
+        self.use_direction_classifier = False
+        self.timesteps = timesteps
+        self.logger = logger or logging.getLogger("CenterHead")
+        self.logger.info("num_classes: %s", num_classes)
+
+        self.shared_conv = nn.Sequential(
+            nn.Conv2d(in_channels, share_conv_channel, kernel_size=3, padding=1, bias=True),
+            nn.BatchNorm2d(share_conv_channel), nn.ReLU(inplace=True))
+        self.tasks = nn.ModuleList()
+        for num_cls in self.num_classes:
+            heads = copy.deepcopy(dict(common_heads))
+            for head in heads:
+                if head in ("vel", "rvel"):
+                    heads[head] = (self.timesteps * heads[head][0], heads[head][1])      # center_head.py:354-356
+            heads.update(dict(hm=(num_cls, num_hm_conv)))
+            self.tasks.append(SepHead(share_conv_channel, heads, bn=True, init_bias=init_bias, final_kernel=3))
+        self.logger.info("Finish CenterHead Initialization")
+
+    def forward(self, x, bev_map=None, *kwargs):
+        """x logical [B,512,H,W] -> list over tasks of {head: logical [B,c,H,W]} (center_head.py:375-390)."""
+        x = to_nhwc(x)
+        x = run_conv(x, self.shared_conv[0], self.shared_conv[1], True)
+        return [task(x) for task in self.tasks]
+
+    def loss(self, example, preds_dicts, **kwargs):
+        from .loss import center_head_loss
+        return center_head_loss(self, example, preds_dicts)
+
+    def predict(self, example, preds_dicts, test_cfg, **kwargs):
+        raise NotImplementedError("CenterHead.predict (decode + rotated NMS) is the first 'next' row of "
+                                  "SURVEY.md section 8f; not built in this round")

@@ -1,0 +1,283 @@
+"""Thin torch-tensor wrappers over the C ABI (include/futuredet_b200.h).
+
+PyTorch is used here for device memory and streams only; every byte of arithmetic happens
+inside libfuturedet_b200.so.  All functions raise RuntimeError when the library is missing or a
+call fails -- there is no fallback path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _req(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise RuntimeError("%s must be a contiguous CUDA %s tensor" % (name, dtype))
+    return t
+
+
+def _pow2_at_least(n):
+    c = 1024
+    while c < n:
+        c <<= 1
+    return c
+
+
+def grid_size_of(point_cloud_range, voxel_size):
+    """grid = round((hi - lo) / vs) in float32 (det3d/core/input/voxel_generator.py:10-11)."""
+    r = np.asarray(point_cloud_range, dtype=np.float32)
+    v = np.asarray(voxel_size, dtype=np.float32)
+    return np.round((r[3:] - r[:3]) / v).astype(np.int64)
+
+
+# --------------------------------------------------------------------------- voxelize
+def voxelize_vfe(points, batch_offsets, voxel_size, point_cloud_range, max_points, max_voxels,
+                 num_feat=None, feat_stride=None, want_voxels=False):
+    """Fused voxelize + mean VFE + batch-index column.
+
+    points [total, P] fp32 CUDA (scenes concatenated), batch_offsets [B+1] int32 CUDA.
+    Returns dict(features [cap, feat_stride], coords [cap,4] (b,z,y,x), num_points [cap],
+    num_voxels [B], total [1]) with cap = B*max_voxels; rows >= total are undefined.
+    want_voxels adds voxels [cap, max_points, num_feat] (the padded array of the legacy API).
+    """
+    lib = L.load()
+    _req(points, torch.float32, "points")
+    _req(batch_offsets, torch.int32, "batch_offsets")
+    if points.dim() != 2:
+        raise RuntimeError("points must be [N, P]")
+    total, pstride = points.shape
+    B = batch_offsets.numel() - 1
+    num_feat = pstride if num_feat is None else num_feat
+    feat_stride = num_feat if feat_stride is None else feat_stride
+    dev = points.device
+    cap = B * max_voxels
+    feat = torch.empty((cap, feat_stride), dtype=torch.float32, device=dev)
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    npts = torch.empty((cap,), dtype=torch.int32, device=dev)
+    nvox = torch.empty((B,), dtype=torch.int32, device=dev)
+    tot = torch.empty((1,), dtype=torch.int32, device=dev)
+    voxels = torch.empty((cap, max_points, num_feat), dtype=torch.float32, device=dev) if want_voxels else None
+    ws_bytes = lib.fd_voxelize_workspace_bytes(total, B, max_voxels, max_points)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    grid = grid_size_of(point_cloud_range, voxel_size)
+    rc = lib.fd_voxelize_vfe(_ptr(points), total, pstride, num_feat, _ptr(batch_offsets), B,
+                             L.f32(point_cloud_range), L.f32(voxel_size), L.i32x3(grid),
+                             max_points, max_voxels, _ptr(feat), feat_stride, _ptr(coords), _ptr(npts),
+                             _ptr(nvox), _ptr(tot), _ptr(voxels), _ptr(ws), ws_bytes, _stream())
+    L.check(rc, "fd_voxelize_vfe")
+    return dict(features=feat, coords=coords, num_points=npts, num_voxels=nvox, total=tot, voxels=voxels)
+
+
+def vfe_mean(voxels, num_points, num_feat=None):
+    """VoxelFeatureExtractorV3.forward: [M,S,F] padded voxels, [M] counts -> [M,num_feat] means."""
+    lib = L.load()
+    _req(voxels, torch.float32, "voxels")
+    if num_points.dtype != torch.int32:
+        num_points = num_points.int()
+    _req(num_points, torch.int32, "num_points")
+    M, S, F = voxels.shape
+    num_feat = F if num_feat is None else num_feat
+    mean = torch.empty((M, num_feat), dtype=torch.float32, device=voxels.device)
+    L.check(lib.fd_vfe_mean(_ptr(voxels), _ptr(num_points), M, S, F, num_feat, _ptr(mean), _stream()), "fd_vfe_mean")
+    return mean
+
+
+# --------------------------------------------------------------------------- rulebook
+class CoordIndex:
+    """Hash (b,z,y,x) -> row for one set of active sites."""
+
+    def __init__(self, coords, n_dev, n_cap, shape):
+        lib = L.load()
+        _req(coords, torch.int32, "coords")
+        self.cap = _pow2_at_least(2 * max(n_cap, 1))
+        self.keys = torch.empty((self.cap,), dtype=torch.int64, device=coords.device)
+        self.vals = torch.empty((self.cap,), dtype=torch.int32, device=coords.device)
+        self.shape = [int(s) for s in shape]
+        rc = lib.fd_coord_index_build(_ptr(coords), _ptr(n_dev), n_cap, L.i32x3(self.shape), _ptr(self.keys),
+                                      _ptr(self.vals), self.cap, _stream())
+        L.check(rc, "fd_coord_index_build")
+
+
+class Rulebook:
+    """Gather-form rulebook: nbr [K, n_out_cap] int32 (input row or -1), pair_num [K]."""
+
+    def __init__(self, nbr, pair_num, K, out_coords, n_out_dev, n_out_cap, out_shape, ksize, stride, padding):
+        self.nbr, self.pair_num, self.K = nbr, pair_num, K
+        self.out_coords, self.n_out_dev, self.n_out_cap = out_coords, n_out_dev, n_out_cap
+        self.out_shape, self.ksize, self.stride, self.padding = out_shape, ksize, stride, padding
+
+    def to_pairs(self):
+        """spconv-1.x layout: (indice_pairs [K,2,P] int32 padded with -1, indice_pair_num [K])."""
+        lib = L.load()
+        n = self.n_out_cap
+        dev = self.nbr.device
+        pairs = torch.empty((self.K, 2, max(n, 1)), dtype=torch.int32, device=dev)
+        total = self.K * n
+        tmp_bytes = ((4 * total + 255) // 256) * 256 + lib.fd_scan_tmp_bytes(total) + 256
+        tmp = torch.empty((tmp_bytes,), dtype=torch.uint8, device=dev)
+        rc = lib.fd_rulebook_to_pairs(_ptr(self.nbr), n, _ptr(self.n_out_dev), n, self.K, _ptr(pairs), max(n, 1),
+                                      _ptr(tmp), _stream())
+        L.check(rc, "fd_rulebook_to_pairs")
+        return pairs, self.pair_num
+
+
+def _neighbors(out_coords, n_out_dev, n_out_cap, index, ksize, stride, padding):
+    lib = L.load()
+    K = int(ksize[0] * ksize[1] * ksize[2])
+    dev = out_coords.device
+    nbr = torch.empty((K, max(n_out_cap, 1)), dtype=torch.int32, device=dev)
+    pair_num = torch.empty((K,), dtype=torch.int32, device=dev)
+    rc = lib.fd_rulebook_neighbors(_ptr(out_coords), _ptr(n_out_dev), n_out_cap, _ptr(index.keys), _ptr(index.vals),
+                                   index.cap, L.i32x3(index.shape), L.i32x3(ksize), L.i32x3(stride),
+                                   L.i32x3(padding), _ptr(nbr), max(n_out_cap, 1), _ptr(pair_num), _stream())
+    L.check(rc, "fd_rulebook_neighbors")
+    return nbr, pair_num, K
+
+
+def rulebook_subm(coords, n_dev, n_cap, shape, ksize, index=None):
+    """SubMConv3d rulebook: outputs == inputs (same order), centred window."""
+    index = index or CoordIndex(coords, n_dev, n_cap, shape)
+    pad = [k // 2 for k in ksize]
+    nbr, pair_num, K = _neighbors(coords, n_dev, n_cap, index, ksize, [1, 1, 1], pad)
+    return Rulebook(nbr, pair_num, K, coords, n_dev, n_cap, list(shape), list(ksize), [1, 1, 1], pad), index
+
+
+def conv_out_shape(shape, ksize, stride, padding):
+    return [(int(s) + 2 * p - k) // st + 1 for s, k, st, p in zip(shape, ksize, stride, padding)]
+
+
+def rulebook_conv(coords, n_dev, n_cap, batch_size, shape, ksize, stride, padding, n_out_cap=None, index=None):
+    """Regular SparseConv3d rulebook: active output set (ascending linear order) + neighbour table."""
+    lib = L.load()
+    dev = coords.device
+    out_shape = conv_out_shape(shape, ksize, stride, padding)
+    cells = batch_size * out_shape[0] * out_shape[1] * out_shape[2]
+    fan = 1
+    for k, s in zip(ksize, stride):
+        fan *= -(-k // s)  # outputs one input can reach along this axis
+    bound = min(cells, n_cap * fan)
+    n_out_cap = bound if n_out_cap is None else min(n_out_cap, bound)
+    words = (cells + 31) // 32
+    bitmap = torch.empty((words + 1,), dtype=torch.int32, device=dev)
+    prefix = torch.empty((words + 1,), dtype=torch.int32, device=dev)
+    tmp = torch.empty((lib.fd_scan_tmp_bytes(words) + 256,), dtype=torch.uint8, device=dev)
+    out_coords = torch.empty((max(n_out_cap, 1), 4), dtype=torch.int32, device=dev)
+    n_out = torch.empty((1,), dtype=torch.int32, device=dev)
+    rc = lib.fd_rulebook_out_coords(_ptr(coords), _ptr(n_dev), n_cap, batch_size, L.i32x3(shape), L.i32x3(ksize),
+                                    L.i32x3(stride), L.i32x3(padding), L.i32x3(out_shape), _ptr(bitmap),
+                                    _ptr(prefix), _ptr(tmp), _ptr(out_coords), n_out_cap, _ptr(n_out), _stream())
+    L.check(rc, "fd_rulebook_out_coords")
+    index = index or CoordIndex(coords, n_dev, n_cap, shape)
+    nbr, pair_num, K = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
+    return Rulebook(nbr, pair_num, K, out_coords, n_out, n_out_cap, out_shape, list(ksize), list(stride),
+                    list(padding)), index
+
+
+# --------------------------------------------------------------------------- convolution
+def _conv_desc(x, in_stride, cin, w, scale, shift, residual, relu, out, out_stride, precision):
+    d = L.ConvDesc()
+    d.d_in = x.data_ptr(); d.in_stride = in_stride; d.cin = cin
+    d.d_w = w.data_ptr(); d.K, _, d.cout = w.shape
+    d.d_scale = scale.data_ptr() if scale is not None else None
+    d.d_shift = shift.data_ptr() if shift is not None else None
+    if residual is not None:
+        d.d_residual = residual.data_ptr(); d.res_stride = residual.stride(0)
+    d.relu = int(bool(relu))
+    d.d_out = out.data_ptr(); d.out_stride = out_stride
+    d.precision = L.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+    return d
+
+
+def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out=None, precision="fp32",
+                bev=None):
+    """out[o] = act((sum_k x[nbr[k,o]] @ w[k]) * scale + shift (+ residual[o])).
+
+    x [n_in_cap, >=Cin] fp32 rows, w [K, Cin, Cout] fp32, rb: Rulebook.  With bev=(B,D,H,W) the result
+    is written straight into a zero-initialised channels-last BEV tensor [B,H,W,Cout*D]
+    (SparseConvTensor.dense().view(N, C*D, H, W) of scn.py:165-168) which is returned.
+    """
+    lib = L.load()
+    _req(w, torch.float32, "w")
+    K, cin, cout = w.shape
+    if K != rb.K:
+        raise RuntimeError("weight has %d kernel offsets, rulebook has %d" % (K, rb.K))
+    if x.dtype != torch.float32 or not x.is_cuda or x.stride(1) != 1:
+        raise RuntimeError("x must be CUDA fp32 with unit channel stride")
+    n_cap = rb.n_out_cap
+    if bev is not None:
+        B, D, H, Wd = bev
+        if out is None:
+            out = torch.zeros((B, H, Wd, cout * D), dtype=torch.float32, device=x.device)
+        d = _conv_desc(x, x.stride(0), cin, w, scale, shift, None, relu, out, cout * D, precision)
+        d.out_map = L.OUTMAP_BEV
+        d.d_out_coords4 = rb.out_coords.data_ptr(); d.bevD, d.bevH, d.bevW = D, H, Wd
+    else:
+        if out is None:
+            out = torch.empty((max(n_cap, 1), cout), dtype=torch.float32, device=x.device)
+        d = _conv_desc(x, x.stride(0), cin, w, scale, shift, residual, relu, out, out.stride(0), precision)
+        d.out_map = L.OUTMAP_IDENTITY
+    d.mode = L.GATHER_TABLE
+    d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
+    d.d_n_out = rb.n_out_dev.data_ptr() if rb.n_out_dev is not None else None
+    d.n_out_cap = n_cap
+    L.check(lib.fd_conv_forward(C.byref(d), _stream()), "fd_conv_forward(sparse)")
+    return out
+
+
+def conv2d_nhwc(x, w, ksize, stride, padding, scale=None, shift=None, relu=False, out=None, residual=None,
+                precision="fp32", transposed=False):
+    """Dense 2-D convolution on channels-last activations.
+
+    x: [B,H,W,Cs] fp32 CUDA view with unit channel stride (a channel slice of a wider buffer is fine),
+    w: [kh*kw, Cin, Cout].  `out` may likewise be a channel slice [B,Ho,Wo,Cout] of a wider buffer (this is
+    how torch.cat(ups, dim=1) of rpn.py:156-157 is fused away).  transposed=True: ConvTranspose2d, kernel==stride.
+    """
+    lib = L.load()
+    _req(w, torch.float32, "w")
+    K, cin, cout = w.shape
+    B, H, Wd, _ = x.shape
+    kh, kw = ksize
+    sh, sw = stride
+    ph, pw = padding
+    if x.stride(3) != 1 or x.stride(2) * Wd != x.stride(1) or x.stride(1) * H != x.stride(0):
+        raise RuntimeError("x must be a channels-last [B,H,W,C] view with dense pixels")
+    if transposed:
+        Ho, Wo = H * sh, Wd * sw
+    else:
+        Ho, Wo = (H + 2 * ph - kh) // sh + 1, (Wd + 2 * pw - kw) // sw + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x.device)
+    if out.stride(3) != 1 or out.stride(2) * Wo != out.stride(1) or out.stride(1) * Ho != out.stride(0):
+        raise RuntimeError("out must be a channels-last [B,H,W,C] view with dense pixels")
+    res2 = residual.reshape(-1, residual.shape[-1]) if residual is not None else None
+    d = _conv_desc(x, x.stride(2), cin, w, scale, shift, res2, relu, out, out.stride(2), precision)
+    d.mode = L.GATHER_CONVT2D if transposed else L.GATHER_CONV2D
+    d.B, d.Hin, d.Win, d.Hout, d.Wout = B, H, Wd, Ho, Wo
+    d.kh, d.kw, d.sh, d.sw, d.ph, d.pw = kh, kw, sh, sw, ph, pw
+    d.out_map = L.OUTMAP_IDENTITY
+    d.d_n_out = None
+    d.n_out_cap = B * H * Wd if transposed else B * Ho * Wo
+    L.check(lib.fd_conv_forward(C.byref(d), _stream()), "fd_conv_forward(conv2d)")
+    return out
+
+
+def sparse_to_dense(features, coords, n_dev, n_cap, batch_size, shape):
+    """SparseConvTensor.dense(): [N,C] rows -> zero-filled NCDHW tensor."""
+    lib = L.load()
+    Cc = features.shape[1]
+    D, H, Wd = [int(s) for s in shape]
+    dense = torch.empty((batch_size, Cc, D, H, Wd), dtype=torch.float32, device=features.device)
+    rc = lib.fd_sparse_to_dense_ncdhw(_ptr(features), features.stride(0), Cc, _ptr(coords), _ptr(n_dev), n_cap,
+                                      batch_size, D, H, Wd, _ptr(dense), _stream())
+    L.check(rc, "fd_sparse_to_dense_ncdhw")
+    return dense

@@ -1,0 +1,224 @@
+"""spconv-1.x-shaped API over the native rulebook + implicit-GEMM kernels.
+
+Replaces the external `spconv` package the reference backbone imports (det3d/models/backbones/scn.py:2-3):
+`SparseConvTensor`, `SubMConv3d`, `SparseConv3d`, `SparseSequential`, `SparseModule`, with the semantics
+summarised in SURVEY.md appendix B.  Parameters keep spconv 1.x's layout (`weight [kD,kH,kW,Cin,Cout]`,
+`bias [Cout]`) so reference checkpoints load unchanged.
+
+Differences that matter to callers:
+  * row counts live on the device (`n_dev`), buffers are allocated at a static capacity (`n_cap`) and rows
+    >= n are undefined -- nothing in a forward pass synchronises with the host;
+  * `SparseSequential` fuses conv -> BatchNorm1d(eval) -> ReLU triples into the conv epilogue;
+  * only inference (module.eval()) is implemented natively in this round; train-mode BatchNorm raises.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+
+DEFAULT_PRECISION = "fp32"
+
+
+def _triple(v):
+    return [int(v)] * 3 if isinstance(v, int) else [int(x) for x in v]
+
+
+class SparseConvTensor:
+    def __init__(self, features, indices, spatial_shape, batch_size, n_dev=None, n_cap=None):
+        if indices.dtype != torch.int32:
+            indices = indices.int()
+        self.features = features
+        self.indices = indices.contiguous()
+        self.spatial_shape = [int(s) for s in spatial_shape]
+        self.batch_size = int(batch_size)
+        self.n_cap = int(indices.shape[0] if n_cap is None else n_cap)
+        if n_dev is None:
+            n_dev = torch.full((1,), self.n_cap, dtype=torch.int32, device=indices.device)
+        self.n_dev = n_dev
+        self.indice_dict = {}     # indice_key -> (Rulebook, out spatial shape)
+        self._index = None        # CoordIndex of self.indices
+
+    def coord_index(self):
+        if self._index is None:
+            self._index = ops.CoordIndex(self.indices, self.n_dev, self.n_cap, self.spatial_shape)
+        return self._index
+
+    def find_indice_pair(self, key):
+        return self.indice_dict.get(key) if key is not None else None
+
+    def num_active(self):
+        """Host-side row count (synchronises)."""
+        return int(self.n_dev.item())
+
+    def trimmed(self):
+        n = self.num_active()
+        return self.features[:n], self.indices[:n]
+
+    def dense(self, channels_first=True):
+        """[B, C, D, H, W] (zeros at inactive sites), as spconv's `.dense()` (scn.py:165)."""
+        d = ops.sparse_to_dense(self.features, self.indices, self.n_dev, self.n_cap, self.batch_size,
+                                self.spatial_shape)
+        return d if channels_first else d.permute(0, 2, 3, 4, 1).contiguous()
+
+    def _like(self, features, indices=None, spatial_shape=None, n_dev=None, n_cap=None):
+        same_sites = indices is None
+        t = SparseConvTensor(features, self.indices if same_sites else indices,
+                             self.spatial_shape if spatial_shape is None else spatial_shape, self.batch_size,
+                             self.n_dev if same_sites else n_dev, self.n_cap if same_sites else n_cap)
+        t.indice_dict = self.indice_dict
+        if same_sites:
+            t._index = self._index
+        return t
+
+
+class SparseModule(nn.Module):
+    """Marker: SparseSequential passes the SparseConvTensor itself to these (scn.py:37)."""
+
+
+class _SparseConvBase(SparseModule):
+    subm = False
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, indice_key=None):
+        super().__init__()
+        if _triple(dilation) != [1, 1, 1] or groups != 1:
+            raise NotImplementedError("dilation/groups are not used by the reference backbone")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = _triple(kernel_size), _triple(stride), _triple(padding)
+        self.indice_key = indice_key
+        self.weight = nn.Parameter(torch.empty(*self.kernel_size, in_channels, out_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.precision = None     # None -> sparse.DEFAULT_PRECISION
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        fan_in = self.in_channels * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        bound = math.sqrt(6.0 / ((1 + 5.0) * fan_in))          # kaiming_uniform_(a=sqrt(5)) on fan_in
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound)
+            if self.bias is not None:
+                b = 1.0 / math.sqrt(fan_in)
+                self.bias.uniform_(-b, b)
+
+    def weight_kio(self):
+        return self.weight.detach().reshape(-1, self.in_channels, self.out_channels)
+
+    def rulebook(self, x):
+        cached = x.find_indice_pair(self.indice_key)
+        if cached is not None:
+            return cached
+        if self.subm:
+            rb, idx = ops.rulebook_subm(x.indices, x.n_dev, x.n_cap, x.spatial_shape, self.kernel_size,
+                                        index=x.coord_index())
+        else:
+            rb, idx = ops.rulebook_conv(x.indices, x.n_dev, x.n_cap, x.batch_size, x.spatial_shape,
+                                        self.kernel_size, self.stride, self.padding, index=x.coord_index())
+        if self.indice_key is not None:
+            x.indice_dict[self.indice_key] = rb
+        return rb
+
+    def forward(self, x, bn=None, residual=None, relu=False, bev=False):
+        """out = act(bn(conv(x) [+bias]) [+ residual]); `bn` is an eval-mode BatchNorm1d folded into the epilogue."""
+        rb = self.rulebook(x)
+        scale, shift = folded_epilogue(self, bn)
+        prec = self.precision or DEFAULT_PRECISION
+        if bev:
+            D, H, W = rb.out_shape
+            return ops.sparse_conv(x.features, self.weight_kio(), rb, scale, shift, None, relu, precision=prec,
+                                   bev=(x.batch_size, D, H, W))
+        y = ops.sparse_conv(x.features, self.weight_kio(), rb, scale, shift, residual, relu, precision=prec)
+        if self.subm:
+            return x._like(y)
+        return x._like(y, rb.out_coords, rb.out_shape, rb.n_out_dev, rb.n_out_cap)
+
+
+class SubMConv3d(_SparseConvBase):
+    subm = True
+
+
+class SparseConv3d(_SparseConvBase):
+    subm = False
+
+
+def _versions(*tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+
+
+def folded_epilogue(conv, bn):
+    """(scale, shift) with shift absorbing the conv bias; cached until a parameter/buffer changes."""
+    bias = getattr(conv, "bias", None)
+    if bn is None and bias is None:
+        return None, None
+    key = _versions(bias, *( (bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else ()))
+    key = (id(bn), bn.training if bn is not None else False) + key
+    cache = conv.__dict__.setdefault("_fold_cache", {})
+    hit = cache.get("k")
+    if hit == key:
+        return cache["v"]
+    with torch.no_grad():
+        if bn is None:
+            scale, shift = None, bias.detach().float().contiguous()
+        else:
+            scale, shift = fold_bn(bn)
+            if bias is not None:
+                shift = (shift + bias.detach() * scale).contiguous()
+    cache["k"], cache["v"] = key, (scale, shift)
+    return scale, shift
+
+
+def fold_bn(bn):
+    """Eval-mode BatchNorm -> per-channel (scale, shift)."""
+    if bn.training:
+        raise NotImplementedError("futuredet_b200: train-mode BatchNorm is not implemented natively yet; "
+                                  "call model.eval() (no PyTorch fallback is provided)")
+    inv = torch.rsqrt(bn.running_var.detach() + bn.eps)
+    scale = bn.weight.detach() * inv if bn.affine else inv
+    shift = -bn.running_mean.detach() * scale
+    if bn.affine:
+        shift = shift + bn.bias.detach()
+    return scale.contiguous(), shift.contiguous()
+
+
+class SparseSequential(SparseModule):
+    """Runs sparse modules on the tensor; (conv, BatchNorm1d, ReLU) runs are fused into one kernel."""
+
+    def __init__(self, *mods):
+        super().__init__()
+        for i, m in enumerate(mods):
+            self.add_module(str(i), m)
+
+    def __len__(self):
+        return len(self._modules)
+
+    def __getitem__(self, i):
+        return list(self._modules.values())[i]
+
+    def add(self, module, name=None):
+        self.add_module(name or str(len(self._modules)), module)
+
+    def forward(self, x, bev_last=False):
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, _SparseConvBase):
+                bn = None
+                relu = False
+                j = i + 1
+                if j < len(mods) and isinstance(mods[j], nn.BatchNorm1d):
+                    bn = mods[j]
+                    j += 1
+                if j < len(mods) and isinstance(mods[j], nn.ReLU):
+                    relu = True
+                    j += 1
+                x = m(x, bn=bn, relu=relu, bev=(bev_last and j == len(mods)))
+                i = j
+            elif isinstance(m, SparseModule):
+                x = m(x)
+                i += 1
+            else:
+                raise NotImplementedError(
+                    "SparseSequential: %s outside a conv->BatchNorm1d->ReLU run has no native kernel" % type(m).__name__)
+        return x

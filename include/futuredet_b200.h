@@ -1,0 +1,169 @@
+/*
+ * futuredet_b200.h -- C ABI of the B200-native FutureDet LiDAR hot path.
+ *
+ * The reference (neeharperi/FutureDet) has no C ABI: its native code is reached
+ * through numba JIT, pybind11 (iou3d_nms_cuda / deform_conv_cuda) and spconv's
+ * torch.ops.  Every entry point below therefore cites the *reference Python/C++
+ * interface it replaces* (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / pybind types.
+ *   - every pointer named d_* is DEVICE memory owned by the caller; the library
+ *     never allocates or frees in the hot loop.
+ *   - every entry point takes the cudaStream_t (as void*) it must launch on and
+ *     returns 0 on success, <0 for an invalid argument, >0 = cudaError_t.
+ *     fd_last_error() returns a thread-local message.  Nothing ever exit()s.
+ *   - row counts that are only known on the device (number of voxels, number of
+ *     active sites after a strided sparse conv) are passed as `const int* d_n`
+ *     together with a host-side capacity; kernels are persistent / grid-stride
+ *     so no host synchronisation is needed anywhere in a forward pass.
+ *   - all feature matrices are row-major fp32 [rows, stride] ("channels last").
+ */
+#ifndef FUTUREDET_B200_H_
+#define FUTUREDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FD_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------ */
+int         fd_version(void);
+const char* fd_last_error(void);
+/* number of kernels this library has launched since load (bench "gpu_launches") */
+int64_t     fd_launch_count(void);
+
+/* ---- voxelize + VFE ------------------------------------------------------
+ * Replaces  det3d/datasets/pipelines/preprocess.py:244-271  (Voxelization)
+ *        -> det3d/core/input/voxel_generator.py:19-30       (VoxelGenerator.generate)
+ *        -> det3d/ops/point_cloud/point_cloud_ops.py:7-55,112-184 (points_to_voxel)
+ *        +  det3d/models/readers/voxel_encoder.py:17-24     (VoxelFeatureExtractorV3)
+ *        +  det3d/torchie/parallel/collate.py:199-206       (batch index column)
+ * Semantics are those of the sequential reference loop: voxel id = rank of the
+ * voxel's first point in input order, only the first `max_points` points (input
+ * order) of a voxel contribute, voxels first seen after `max_voxels` are dropped.
+ * Coordinates use float32 IEEE sub/div/floor exactly as the reference does.
+ *
+ *   d_points        [total_points, point_stride] fp32, scenes concatenated
+ *   d_batch_offsets [B+1] int32 row offsets of each scene in d_points
+ *   range           host [6] xmin,ymin,zmin,xmax,ymax,zmax ; voxel_size host [3]
+ *   grid            host [3] (gx,gy,gz) = round((hi-lo)/vs) computed by the caller in fp32
+ * outputs (capacity B*max_voxels rows):
+ *   d_feat   [*, feat_stride] fp32 mean of the first <=max_points points (cols >= num_feat zeroed)
+ *   d_coords [*, 4] int32 (b,z,y,x) ;  d_npts [*] int32 ; d_nvox [B] int32 ; d_total [1] int32
+ *   d_voxels optional (NULL to skip) [*, max_points, num_feat] fp32 zero-padded point lists, the
+ *            `voxels` array of points_to_voxel (only needed by callers of the legacy padded API)
+ */
+size_t fd_voxelize_workspace_bytes(int64_t total_points, int B, int max_voxels, int max_points);
+int fd_voxelize_vfe(const float* d_points, int64_t total_points, int point_stride, int num_feat,
+                    const int32_t* d_batch_offsets, int B,
+                    const float* range6, const float* voxel_size3, const int32_t* grid3,
+                    int max_points, int max_voxels,
+                    float* d_feat, int feat_stride, int32_t* d_coords, int32_t* d_npts,
+                    int32_t* d_nvox, int32_t* d_total, float* d_voxels,
+                    void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* VoxelFeatureExtractorV3.forward on padded voxels (det3d/models/readers/voxel_encoder.py:17-24):
+ * d_mean[v,c] = sum_s d_voxels[v,s,c] / d_npts[v]   (d_voxels [M,S,F], first num_feat columns used) */
+int fd_vfe_mean(const float* d_voxels, const int32_t* d_npts, int64_t M, int S, int F, int num_feat,
+                float* d_mean, void* stream);
+
+/* ---- rulebook ------------------------------------------------------------
+ * Replaces spconv 1.x `ops.get_indice_pairs` (external, un-vendored; call sites
+ * det3d/models/backbones/scn.py:99,105-106,110-146).  The rulebook is kept in
+ * gather form: nbr[k*nbr_stride + o] = input row feeding output row o through
+ * kernel offset k (row-major (kz,ky,kx)), or -1.  Cross-correlation:
+ * in = out*stride - pad + k.
+ *
+ * A "coordinate index" is an open-addressing hash  key=((b*D+z)*H+y)*W+x -> row.
+ *   d_keys [cap] int64, d_vals [cap] int32, cap = power of two >= 2*rows.
+ */
+int fd_coord_index_build(const int32_t* d_coords4, const int32_t* d_n, int n_cap,
+                         const int32_t* shape3, int64_t* d_keys, int32_t* d_vals, int64_t cap,
+                         void* stream);
+
+/* Active output set of a regular (strided) SparseConv3d: every in-bounds out
+ * coordinate hit by >=1 active input, ascending linear (b,z,y,x) order
+ * (spconv-1.x GPU behaviour).  d_bitmap: >= ceil(B*oD*oH*oW/32)+1 int32 words,
+ * d_wordprefix: same count, d_scan_tmp: fd_scan_tmp_bytes(words).           */
+size_t fd_scan_tmp_bytes(int64_t n);
+int fd_rulebook_out_coords(const int32_t* d_in_coords4, const int32_t* d_n_in, int n_in_cap,
+                           int B, const int32_t* in_shape3, const int32_t* ksize3,
+                           const int32_t* stride3, const int32_t* pad3, const int32_t* out_shape3,
+                           uint32_t* d_bitmap, int32_t* d_wordprefix, void* d_scan_tmp,
+                           int32_t* d_out_coords4, int n_out_cap, int32_t* d_n_out, void* stream);
+
+/* Neighbour table for SubMConv3d (out == in coords, stride 1, pad = k/2) and for
+ * SparseConv3d (out coords from fd_rulebook_out_coords).  d_pair_num [K] int32
+ * receives the number of pairs per kernel offset (spconv `indice_pair_num`).  */
+int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, int n_out_cap,
+                          const int64_t* d_in_keys, const int32_t* d_in_vals, int64_t in_cap,
+                          const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
+                          const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
+                          void* stream);
+
+/* Export to the spconv-1.x layout `indice_pairs [K,2,P_cap]` (pairs of offset k
+ * listed in ascending output row), for parity checks and interop.            */
+int fd_rulebook_to_pairs(const int32_t* d_nbr, int nbr_stride, const int32_t* d_n_out, int n_out_cap,
+                         int K, int32_t* d_pairs, int pair_cap, void* d_scan_tmp, void* stream);
+
+/* ---- gather -> implicit GEMM convolution ----------------------------------
+ * One kernel family serves
+ *   spconv SubMConv3d / SparseConv3d forward (`indice_conv`, scn.py:11-34,98-146),
+ *   nn.Conv2d / ZeroPad2d+Conv2d / ConvTranspose2d(k=s) of the RPN neck
+ *   (det3d/models/necks/rpn.py:70-142) and of CenterHead / SepHead
+ *   (det3d/models/bbox_heads/center_head.py:129-152,344-349),
+ * with the eval-mode BatchNorm, conv bias, residual add and ReLU of
+ * scn.py:64-80 / rpn.py:124-142 fused into the epilogue:
+ *     y = act( (sum_k in[nbr(o,k)] @ W[k]) * scale + shift (+ residual) )
+ * Weights are [K, Cin, Cout] fp32 (spconv-1.x layout [kD,kH,kW,Cin,Cout]).
+ */
+typedef struct fd_conv_desc {
+  /* input rows */
+  const float*   d_in;        int32_t in_stride;  int32_t cin;
+  /* weights / epilogue vectors */
+  const float*   d_w;         int32_t cout;       int32_t K;
+  const float*   d_scale;     /* [cout] or NULL (=1) */
+  const float*   d_shift;     /* [cout] or NULL (=0) */
+  const float*   d_residual;  int32_t res_stride; /* NULL: none */
+  int32_t        relu;
+  /* output rows */
+  float*         d_out;       int32_t out_stride;
+  const int32_t* d_n_out;     /* device row count, or NULL -> n_out_cap rows */
+  int32_t        n_out_cap;
+  /* gather mode */
+  int32_t        mode;        /* FD_GATHER_* */
+  const int32_t* d_nbr;       int32_t nbr_stride;          /* FD_GATHER_TABLE */
+  int32_t B, Hin, Win, Hout, Wout, kh, kw, sh, sw, ph, pw; /* FD_GATHER_CONV2D / _CONVT2D */
+  /* output row mapping */
+  int32_t        out_map;     /* FD_OUTMAP_* */
+  const int32_t* d_out_coords4; int32_t bevD, bevH, bevW;  /* FD_OUTMAP_BEV */
+  int32_t        precision;   /* FD_PREC_* */
+} fd_conv_desc;
+
+enum { FD_GATHER_TABLE = 0, FD_GATHER_CONV2D = 1, FD_GATHER_CONVT2D = 2 };
+enum { FD_OUTMAP_IDENTITY = 0, FD_OUTMAP_BEV = 1 };
+/* FD_PREC_FP32: CUDA-core fp32 FMA (exact reference arithmetic).
+ * FD_PREC_BF16X3: tcgen05 tensor cores, 3-term bf16 split (fp32-class accuracy).
+ * FD_PREC_BF16: tcgen05 single pass bf16 (fast mode, outside the 1e-3 contract). */
+enum { FD_PREC_FP32 = 0, FD_PREC_BF16X3 = 1, FD_PREC_BF16 = 2 };
+
+int fd_conv_forward(const fd_conv_desc* desc, void* stream);
+
+/* SparseConvTensor.dense() for API parity (scn.py:165-168): scatter [N,C] rows
+ * at (b,z,y,x) into a zeroed NCDHW fp32 tensor.                              */
+int fd_sparse_to_dense_ncdhw(const float* d_feat, int feat_stride, int C, const int32_t* d_coords4,
+                             const int32_t* d_n, int n_cap, int B, int D, int H, int W,
+                             float* d_dense, void* stream);
+
+/* small helpers used by the host layer */
+int fd_fill_i32(int32_t* d_ptr, int64_t n, int32_t value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUTUREDET_B200_H_ */
