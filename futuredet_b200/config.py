@@ -84,6 +84,10 @@ class Config:
         name = os.path.basename(filename)[:-3]
         if "." in name:
             raise ValueError("Dots are not allowed in config file path.")
+        import sys
+        if "det3d" not in sys.modules:      # reference configs import det3d.utils.config_tool at load time
+            from .compat import install
+            install()
         spec = importlib.util.spec_from_file_location("_fdcfg_" + name, filename)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)

@@ -1,0 +1,147 @@
+"""ORACLE tooling (test infrastructure only): generate tests/golden/* by running the REFERENCE itself.
+
+Runs only in the build container, where /root/reference exists; the fixtures it writes are committed so
+that nothing on the GPU box needs the reference.  Usage:  python oracle/gen_golden.py
+
+  voxel_<case>.npz   reference numba points_to_voxel (det3d/ops/point_cloud/point_cloud_ops.py:112-184)
+                     + reference VoxelFeatureExtractorV3 (det3d/models/readers/voxel_encoder.py:17-24)
+  neck_head.pt       reference RPN (det3d/models/necks/rpn.py) + CenterHead forward & loss
+                     (det3d/models/bbox_heads/center_head.py:375-539) at reduced widths, random BN statistics
+"""
+import importlib.util
+import logging
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torchvision  # noqa: F401  (must be imported before the reference path is appended)
+import statistics   # noqa: F401  (real stdlib module first: /root/reference/statistics.py would shadow it)
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+from futuredet_b200.synth import NUSC_RANGE, NUSC_VOXEL, random_points, synth_scene  # noqa: E402
+
+
+def load_ref_voxelizer():
+    spec = importlib.util.spec_from_file_location("pco", REF + "/det3d/ops/point_cloud/point_cloud_ops.py")
+    pco = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pco)
+    return pco
+
+
+def import_ref_models():
+    class AttrDict(dict):
+        def __init__(self, *a, **k):
+            super().__init__()
+            for key, v in dict(*a, **k).items():
+                self[key] = AttrDict(v) if isinstance(v, dict) and not isinstance(v, AttrDict) else v
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    def shim(name, **kw):
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        sys.modules[name] = m
+        return m
+    shim("addict", Dict=AttrDict)
+    shim("terminaltables", AsciiTable=object)
+    shim("pycocotools").mask = shim("pycocotools.mask")
+    sys.path.append(REF)          # append, not insert
+    import det3d.ops
+    pkg = types.ModuleType("det3d.ops.iou3d_nms")
+    pkg.__path__ = [REF + "/det3d/ops/iou3d_nms"]
+    sys.modules["det3d.ops.iou3d_nms"] = pkg
+    pkg.iou3d_nms_cuda = shim("det3d.ops.iou3d_nms.iou3d_nms_cuda")
+    import det3d.models as M
+    return M
+
+
+VOXEL_CASES = {
+    # name: (points, max_voxels)
+    "random": lambda: (random_points(12000, seed=0), 160000),
+    "boundary": lambda: (random_points(12000, seed=1, snap_frac=0.25), 160000),
+    "pile": lambda: (random_points(12000, seed=2, pile=1500), 160000),
+    "cap": lambda: (random_points(12000, seed=3), 1500),
+    "scene": lambda: (synth_scene(16000, seed=4), 5000),
+}
+
+NECK_CFG = dict(type="RPN", layer_nums=[1, 2], ds_layer_strides=[1, 2], ds_num_filters=[8, 16], us_layer_strides=[1, 2],
+                us_num_filters=[16, 16], num_input_features=8)
+HEAD_CFG = dict(type="CenterHead", in_channels=32, tasks=[dict(num_class=1, class_names=["car"])], dataset="nuscenes",
+                weight=0.25, code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2, 1.0, 1.0],
+                common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+                share_conv_channel=64, dcn_head=False, timesteps=3, two_stage=False, reverse=False, sparse=False,
+                dense=False, bev_map=False, forecast_feature=False, classify=False, wide_head=False)
+
+
+def randomise_bn(module, gen):
+    for m in module.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=gen) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=gen) * 0.1)
+
+
+def make_targets(B, H, W, timesteps, gen, max_objs=20):
+    """example[...] targets in the collate layout: key -> [timestep][task] -> Tensor[B,...] (collate.py:208-232)."""
+    ex = {k: [] for k in ("hm", "anno_box", "ind", "mask", "cat")}
+    for _ in range(timesteps):
+        hm = torch.rand((B, 1, H, W), generator=gen) ** 8
+        ind = torch.randint(0, H * W, (B, max_objs), generator=gen)
+        mask = (torch.rand((B, max_objs), generator=gen) < 0.6).to(torch.uint8)
+        for b in range(B):
+            hm[b, 0].view(-1)[ind[b][mask[b].bool()]] = 1.0
+        ex["hm"].append([hm])
+        ex["anno_box"].append([torch.randn((B, max_objs, 14), generator=gen)])
+        ex["ind"].append([ind])
+        ex["mask"].append([mask])
+        ex["cat"].append([torch.zeros((B, max_objs), dtype=torch.int64)])
+    return ex
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    pco = load_ref_voxelizer()
+    M = import_ref_models()
+    from det3d.models.readers.voxel_encoder import VoxelFeatureExtractorV3
+    vfe = VoxelFeatureExtractorV3(num_input_features=5)
+    for name, make in VOXEL_CASES.items():
+        pts, mv = make()
+        voxels, coors, npts = pco.points_to_voxel(pts, np.array(NUSC_VOXEL, np.float32), np.array(NUSC_RANGE, np.float32),
+                                                  10, True, mv)
+        mean = vfe(torch.from_numpy(voxels), torch.from_numpy(npts)).numpy()
+        np.savez_compressed(os.path.join(OUT, "voxel_%s.npz" % name), points=pts, max_voxels=np.int64(mv),
+                            coors=coors, num_points=npts, mean=mean)
+        print("voxel_%s: %d pts -> %d voxels" % (name, len(pts), len(coors)))
+
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(1)
+    neck = M.build_neck(dict(NECK_CFG, logger=logging.getLogger("RPN")))
+    head = M.build_head(dict(HEAD_CFG))
+    randomise_bn(neck, gen)
+    randomise_bn(head, gen)
+    neck.eval()
+    head.eval()
+    x = torch.randn((2, 8, 12, 12), generator=gen)
+    with torch.no_grad():
+        feat = neck(x)
+        preds = head(feat)
+        example = make_targets(2, feat.shape[2], feat.shape[3], 3, gen)
+        preds_for_loss = [{k: v.clone() for k, v in p.items()} for p in preds]
+        loss = head.loss(example, preds_for_loss)
+    torch.save(dict(neck_cfg=NECK_CFG, head_cfg=HEAD_CFG, neck_state=neck.state_dict(), head_state=head.state_dict(),
+                    x=x, neck_out=feat, preds=[{k: v for k, v in p.items()} for p in preds], example=example,
+                    loss={k: [t.detach() if torch.is_tensor(t) else t for t in v] if isinstance(v, list) else v
+                          for k, v in loss.items()}),
+               os.path.join(OUT, "neck_head.pt"))
+    print("neck_head: neck_out", tuple(feat.shape), {k: tuple(v.shape) for k, v in preds[0].items()})
+    print("loss keys", {k: (v[0] if isinstance(v, list) else v) for k, v in loss.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""GPU parity: gather->implicit-GEMM convolution (fd_conv_forward) vs CPU references.
+fp32 arm: 1e-4 (accumulation order only).  Tensor-core arm (bf16x3): 1e-3 abs as BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from futuredet_b200 import ops
+from oracle import spconv_ref as S
+
+pytestmark = pytest.mark.gpu
+PRECS = [("fp32", 1e-4)]
+
+
+def random_sites(rng, B, shape, n):
+    cells = B * shape[0] * shape[1] * shape[2]
+    lin = rng.choice(cells, size=min(n, cells), replace=False)
+    c = np.empty((len(lin), 4), np.int32)
+    c[:, 3] = lin % shape[2]; lin = lin // shape[2]
+    c[:, 2] = lin % shape[1]; lin = lin // shape[1]
+    c[:, 1] = lin % shape[0]; c[:, 0] = lin // shape[0]
+    return c
+
+
+@pytest.mark.parametrize("prec,tol", PRECS)
+@pytest.mark.parametrize("cin,cout", [(5, 16), (16, 16), (16, 32), (32, 64), (64, 64), (128, 128)])
+def test_subm_conv_fused_epilogue(cuda, prec, tol, cin, cout):
+    rng = np.random.default_rng(cin * 1000 + cout)
+    shape, B = [9, 24, 24], 2
+    c = random_sites(rng, B, shape, 3000)
+    n = len(c)
+    x = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32))
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32))
+    shift = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+    res = torch.from_numpy(rng.standard_normal((n, cout)).astype(np.float32))
+    nbr = S.subm_rulebook(c, shape, [3, 3, 3])
+    want = F.relu(S.indice_conv(x, w, nbr, n) * scale + shift + res)
+    cap = n + 300
+    ct = torch.zeros((cap, 4), dtype=torch.int32, device=cuda); ct[:n] = torch.from_numpy(c).to(cuda)
+    nd = torch.tensor([n], dtype=torch.int32, device=cuda)
+    rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3])
+    xg = torch.zeros((cap, cin), device=cuda); xg[:n] = x.to(cuda)
+    rg = torch.zeros((cap, cout), device=cuda); rg[:n] = res.to(cuda)
+    y = ops.sparse_conv(xg, w.to(cuda), rb, scale.to(cuda), shift.to(cuda), rg, True, precision=prec)
+    torch.testing.assert_close(y[:n].cpu(), want, rtol=tol, atol=tol)
+    # plain conv (no epilogue), rows beyond n untouched by contract
+    y2 = ops.sparse_conv(xg, w.to(cuda), rb, precision=prec)
+    torch.testing.assert_close(y2[:n].cpu(), S.indice_conv(x, w, nbr, n), rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("prec,tol", PRECS)
+def test_strided_conv_and_bev_epilogue(cuda, prec, tol):
+    rng = np.random.default_rng(11)
+    shape, B = [5, 16, 16], 2
+    c = random_sites(rng, B, shape, 1500)
+    n = len(c)
+    cin, cout = 32, 32
+    x = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((3, cin, cout)) / np.sqrt(3 * cin)).astype(np.float32))
+    oc, oshape, nbr = S.conv_rulebook(c, B, shape, [3, 1, 1], [2, 1, 1], [0, 0, 0])
+    feat = F.relu(S.indice_conv(x, w, nbr, len(oc)))
+    dense = torch.zeros((B, cout, *oshape))
+    ci = torch.from_numpy(oc.astype(np.int64))
+    dense[ci[:, 0], :, ci[:, 1], ci[:, 2], ci[:, 3]] = feat
+    want = dense.view(B, cout * oshape[0], oshape[1], oshape[2])                       # scn.py:165-168
+    ct = torch.from_numpy(c).to(cuda)
+    nd = torch.tensor([n], dtype=torch.int32, device=cuda)
+    rb, _ = ops.rulebook_conv(ct, nd, n, B, shape, [3, 1, 1], [2, 1, 1], [0, 0, 0])
+    bev = ops.sparse_conv(x.to(cuda), w.to(cuda), rb, relu=True, precision=prec, bev=(B, *oshape))
+    torch.testing.assert_close(bev.permute(0, 3, 1, 2).cpu(), want, rtol=tol, atol=tol)
+    # SparseConvTensor.dense() kernel agrees too
+    y = ops.sparse_conv(x.to(cuda), w.to(cuda), rb, relu=True, precision=prec)
+    d2 = ops.sparse_to_dense(y, rb.out_coords, rb.n_out_dev, rb.n_out_cap, B, oshape)
+    torch.testing.assert_close(d2.cpu(), dense, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("prec,tol", PRECS)
+@pytest.mark.parametrize("cin,cout,k,s,p,hw", [(32, 64, 3, 1, 1, 20), (64, 32, 3, 2, 1, 21), (48, 64, 1, 1, 0, 9),
+                                              (256, 128, 3, 1, 1, 12), (64, 3, 3, 1, 1, 10), (16, 16, 2, 2, 0, 12)])
+def test_conv2d_nhwc(cuda, prec, tol, cin, cout, k, s, p, hw):
+    g = torch.Generator().manual_seed(cin + cout)
+    B = 2
+    x = torch.randn((B, cin, hw, hw + 3), generator=g)
+    w = torch.randn((cout, cin, k, k), generator=g) / np.sqrt(cin * k * k)
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g)
+    want = F.relu(F.conv2d(x, w, None, stride=s, padding=p) * scale[None, :, None, None] + shift[None, :, None, None])
+    wk = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout).contiguous().to(cuda)
+    xg = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+    y = ops.conv2d_nhwc(xg, wk, (k, k), (s, s), (p, p), scale.to(cuda), shift.to(cuda), True, precision=prec)
+    torch.testing.assert_close(y.permute(0, 3, 1, 2).cpu(), want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("prec,tol", PRECS)
+def test_channel_slices_and_conv_transpose(cuda, prec, tol):
+    """Reading a channel slice / writing into a slice of a wider buffer (fused torch.cat), ConvTranspose2d(2, s2)."""
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 9, 11
+    wide = torch.randn((B, H, W, 96), generator=g)
+    x = wide[..., 32:64]
+    wt = torch.randn((32, 48, 2, 2), generator=g) / 8                                   # ConvTranspose2d layout [Cin,Cout,kh,kw]
+    want = F.conv_transpose2d(x.permute(0, 3, 1, 2), wt, None, stride=2)
+    out = torch.full((B, 2 * H, 2 * W, 80), -7.0, device=cuda)
+    wk = wt.permute(2, 3, 0, 1).reshape(4, 32, 48).contiguous().to(cuda)
+    ops.conv2d_nhwc(wide.to(cuda)[..., 32:64], wk, (2, 2), (2, 2), (0, 0), out=out[..., 16:64], precision=prec,
+                    transposed=True)
+    torch.testing.assert_close(out[..., 16:64].permute(0, 3, 1, 2).cpu(), want, rtol=tol, atol=tol)
+    assert (out[..., :16] == -7).all() and (out[..., 64:] == -7).all()                  # neighbours untouched
