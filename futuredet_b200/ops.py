@@ -184,6 +184,25 @@ def rulebook_conv(coords, n_dev, n_cap, batch_size, shape, ksize, stride, paddin
 
 
 # --------------------------------------------------------------------------- convolution
+PROFILE = None   # bench.py sets this to a list to collect per-launch CUDA-event timings of the conv family
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(e0, kind, flops, launches=1):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILE.append(dict(kind=kind, start=e0, end=e1, flops=flops, launches=launches))
+
+
 def _conv_desc(x, in_stride, cin, w, scale, shift, residual, relu, out, out_stride, precision):
     d = L.ConvDesc()
     d.d_in = x.data_ptr(); d.in_stride = in_stride; d.cin = cin
@@ -230,7 +249,9 @@ def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out
     d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
     d.d_n_out = rb.n_out_dev.data_ptr() if rb.n_out_dev is not None else None
     d.n_out_cap = n_cap
+    e0 = _prof_begin()
     L.check(lib.fd_conv_forward(C.byref(d), _stream()), "fd_conv_forward(sparse)")
+    _prof_end(e0, "sparse3d_c%d" % cout, lambda: 2.0 * float(rb.pair_num.sum().item()) * cin * cout)
     return out
 
 
@@ -267,7 +288,9 @@ def conv2d_nhwc(x, w, ksize, stride, padding, scale=None, shift=None, relu=False
     d.out_map = L.OUTMAP_IDENTITY
     d.d_n_out = None
     d.n_out_cap = B * H * Wd if transposed else B * Ho * Wo
+    e0 = _prof_begin()
     L.check(lib.fd_conv_forward(C.byref(d), _stream()), "fd_conv_forward(conv2d)")
+    _prof_end(e0, "dense2d", 2.0 * d.n_out_cap * cin * cout * (1 if transposed else K), K if transposed else 1)
     return out
 
 
