@@ -34,6 +34,7 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
   ConvArgs a{};
   a.in = d->d_in; a.in_stride = d->in_stride; a.cin = d->cin;
   a.w = d->d_w; a.cout = d->cout; a.K = d->K;
+  a.wp = d->d_w_packed;
   a.scale = d->d_scale; a.shift = d->d_shift;
   a.residual = d->d_residual; a.res_stride = d->res_stride;
   a.relu = d->relu;
@@ -92,6 +93,7 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
         p.K = 1; p.kh = p.kw = 1; p.sh = p.sw = 1; p.ph = p.pw = 0;
         p.Hout = d->Hin; p.Wout = d->Win;
         p.w = d->d_w + (size_t)k * d->cin * d->cout;
+        if (d->d_w_packed) p.wp = (const char*)d->d_w_packed + (size_t)k * fd_conv_packed_bytes(1, d->cin, d->cout);
         p.out_map = OUTMAP_UPSAMPLE;
         p.up_s = d->sh; p.up_dy = k / d->kw; p.up_dx = k % d->kw;
         int rc = run(p);

@@ -9,6 +9,7 @@ enum { OUTMAP_UPSAMPLE = 100 };  // internal: one phase of ConvTranspose2d(k == 
 struct ConvArgs {
   const float* in; int in_stride; int cin;
   const float* w; int cout; int K;
+  const void* wp;            // packed bf16 hi/lo weights (tensor-core arm)
   const float* scale; const float* shift;
   const float* residual; int res_stride;
   int relu;

@@ -19,6 +19,7 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("d_in", C.c_void_p), ("in_stride", C.c_int32), ("cin", C.c_int32),
         ("d_w", C.c_void_p), ("cout", C.c_int32), ("K", C.c_int32),
+        ("d_w_packed", C.c_void_p),
         ("d_scale", C.c_void_p), ("d_shift", C.c_void_p),
         ("d_residual", C.c_void_p), ("res_stride", C.c_int32),
         ("relu", C.c_int32),
@@ -63,6 +64,8 @@ SIGNATURES = {
     "fd_rulebook_to_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p]),
     "fd_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "fd_conv_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "fd_conv_pack_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fd_sparse_to_dense_ncdhw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fd_fill_i32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),

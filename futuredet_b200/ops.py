@@ -203,10 +203,44 @@ def _prof_end(e0, kind, flops, launches=1):
     PROFILE.append(dict(kind=kind, start=e0, end=e1, flops=flops, launches=launches))
 
 
-def _conv_desc(x, in_stride, cin, w, scale, shift, residual, relu, out, out_stride, precision):
+_PACK_CACHE = {}
+
+
+def packed_weights(w, separate_offsets=False):
+    """bf16 hi/lo K-major pack of w [K,Cin,Cout] for the tensor-core arm (fd_conv_pack_weights); cached until
+    the weight tensor changes (data_ptr / version)."""
+    lib = L.load()
+    key = (w.data_ptr(), w._version, tuple(w.shape), bool(separate_offsets))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit[1]
+    K, cin, cout = w.shape
+    if separate_offsets:
+        per = lib.fd_conv_packed_bytes(1, cin, cout)
+        buf = torch.empty((K * per,), dtype=torch.uint8, device=w.device)
+        for k in range(K):
+            L.check(lib.fd_conv_pack_weights(C.c_void_p(w[k].data_ptr()), 1, cin, cout,
+                                             C.c_void_p(buf.data_ptr() + k * per), _stream()), "fd_conv_pack_weights")
+    else:
+        buf = torch.empty((lib.fd_conv_packed_bytes(K, cin, cout),), dtype=torch.uint8, device=w.device)
+        L.check(lib.fd_conv_pack_weights(_ptr(w), K, cin, cout, _ptr(buf), _stream()), "fd_conv_pack_weights")
+    if len(_PACK_CACHE) > 512:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (w, buf)      # keep w alive so the data_ptr key cannot be recycled
+    return buf
+
+
+def tc_supported(cin, K):
+    """Shapes the tcgen05 arm accepts; anything else must be requested as fp32 explicitly by the caller."""
+    return cin % 8 == 0 and K <= 32
+
+
+def _conv_desc(x, in_stride, cin, w, scale, shift, residual, relu, out, out_stride, precision, separate=False):
     d = L.ConvDesc()
     d.d_in = x.data_ptr(); d.in_stride = in_stride; d.cin = cin
     d.d_w = w.data_ptr(); d.K, _, d.cout = w.shape
+    if (L.PRECISIONS[precision] if isinstance(precision, str) else int(precision)) != L.PREC_FP32:
+        d.d_w_packed = packed_weights(w, separate).data_ptr()
     d.d_scale = scale.data_ptr() if scale is not None else None
     d.d_shift = shift.data_ptr() if shift is not None else None
     if residual is not None:
@@ -281,7 +315,8 @@ def conv2d_nhwc(x, w, ksize, stride, padding, scale=None, shift=None, relu=False
     if out.stride(3) != 1 or out.stride(2) * Wo != out.stride(1) or out.stride(1) * Ho != out.stride(0):
         raise RuntimeError("out must be a channels-last [B,H,W,C] view with dense pixels")
     res2 = residual.reshape(-1, residual.shape[-1]) if residual is not None else None
-    d = _conv_desc(x, x.stride(2), cin, w, scale, shift, res2, relu, out, out.stride(2), precision)
+    d = _conv_desc(x, x.stride(2), cin, w, scale, shift, res2, relu, out, out.stride(2), precision,
+                   separate=transposed)
     d.mode = L.GATHER_CONVT2D if transposed else L.GATHER_CONV2D
     d.B, d.Hin, d.Win, d.Hout, d.Wout = B, H, Wd, Ho, Wo
     d.kh, d.kw, d.sh, d.sw, d.ph, d.pw = kh, kw, sh, sw, ph, pw

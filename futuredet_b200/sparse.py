@@ -124,6 +124,8 @@ class _SparseConvBase(SparseModule):
         rb = self.rulebook(x)
         scale, shift = folded_epilogue(self, bn)
         prec = self.precision or DEFAULT_PRECISION
+        if prec != "fp32" and not ops.tc_supported(self.in_channels, rb.K):
+            prec = "fp32"      # e.g. the 5-channel stem: no tensor-core tile shape; exact fp32 CUDA-core arm
         if bev:
             D, H, W = rb.out_shape
             return ops.sparse_conv(x.features, self.weight_kio(), rb, scale, shift, None, relu, precision=prec,

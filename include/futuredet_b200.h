@@ -127,6 +127,7 @@ typedef struct fd_conv_desc {
   const float*   d_in;        int32_t in_stride;  int32_t cin;
   /* weights / epilogue vectors */
   const float*   d_w;         int32_t cout;       int32_t K;
+  const void*    d_w_packed;  /* fd_conv_pack_weights output; required for FD_PREC_BF16X3 / FD_PREC_BF16 */
   const float*   d_scale;     /* [cout] or NULL (=1) */
   const float*   d_shift;     /* [cout] or NULL (=0) */
   const float*   d_residual;  int32_t res_stride; /* NULL: none */
@@ -153,6 +154,12 @@ enum { FD_OUTMAP_IDENTITY = 0, FD_OUTMAP_BEV = 1 };
 enum { FD_PREC_FP32 = 0, FD_PREC_BF16X3 = 1, FD_PREC_BF16 = 2 };
 
 int fd_conv_forward(const fd_conv_desc* desc, void* stream);
+
+/* Tensor-core weight pre-pack: fp32 [K,Cin,Cout] -> bf16 hi/lo planes, K-major, zero padded
+ * ([2][Cout_pad][pad64(K*Cin)]).  For FD_GATHER_CONVT2D pack every kernel offset on its own
+ * (K=1 per call, outputs fd_conv_packed_bytes(1,cin,cout) apart).                              */
+size_t fd_conv_packed_bytes(int K, int cin, int cout);
+int fd_conv_pack_weights(const float* d_w, int K, int cin, int cout, void* d_packed, void* stream);
 
 /* SparseConvTensor.dense() for API parity (scn.py:165-168): scatter [N,C] rows
  * at (b,z,y,x) into a zeroed NCDHW fp32 tensor.                              */

@@ -9,7 +9,7 @@ from futuredet_b200 import ops
 from oracle import spconv_ref as S
 
 pytestmark = pytest.mark.gpu
-PRECS = [("fp32", 1e-4)]
+PRECS = [("fp32", 1e-4), ("bf16x3", 3e-4), ("bf16", 6e-2)]
 
 
 def random_sites(rng, B, shape, n):
@@ -42,6 +42,10 @@ def test_subm_conv_fused_epilogue(cuda, prec, tol, cin, cout):
     rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3])
     xg = torch.zeros((cap, cin), device=cuda); xg[:n] = x.to(cuda)
     rg = torch.zeros((cap, cout), device=cuda); rg[:n] = res.to(cuda)
+    if prec != "fp32" and not ops.tc_supported(cin, 27):
+        with pytest.raises(RuntimeError, match="multiple of 8"):      # no silent fallback in the ABI
+            ops.sparse_conv(xg, w.to(cuda), rb, precision=prec)
+        return
     y = ops.sparse_conv(xg, w.to(cuda), rb, scale.to(cuda), shift.to(cuda), rg, True, precision=prec)
     torch.testing.assert_close(y[:n].cpu(), want, rtol=tol, atol=tol)
     # plain conv (no epilogue), rows beyond n untouched by contract

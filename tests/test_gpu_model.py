@@ -26,7 +26,16 @@ def randomise_bn(module, seed):
             m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
 
 
-def test_rpn_and_center_head_match_reference_golden(cuda, golden_dir):
+@pytest.fixture(params=["fp32", "bf16x3"])
+def precision(request):
+    from futuredet_b200 import neck, sparse
+    old = (sparse.DEFAULT_PRECISION, neck.DEFAULT_PRECISION)
+    sparse.DEFAULT_PRECISION = neck.DEFAULT_PRECISION = request.param
+    yield request.param
+    sparse.DEFAULT_PRECISION, neck.DEFAULT_PRECISION = old
+
+
+def test_rpn_and_center_head_match_reference_golden(cuda, golden_dir, precision):
     g = torch.load(os.path.join(golden_dir, "neck_head.pt"), weights_only=False)
     neck = fb.build_neck(dict(g["neck_cfg"])).eval()
     head = fb.build_head(dict(g["head_cfg"])).eval()
@@ -58,7 +67,7 @@ def build_model(timesteps, dev, seed=0):
     return m
 
 
-def test_backbone_matches_oracle(cuda):
+def test_backbone_matches_oracle(cuda, precision):
     m = build_model(1, cuda)
     pts = synth_scene(40000, seed=0)
     vox = V.voxelize_batch_c([pts, synth_scene(30000, seed=1)], NUSC_VOXEL, NUSC_RANGE, 10, 160000)
@@ -73,7 +82,7 @@ def test_backbone_matches_oracle(cuda):
 
 
 @pytest.mark.parametrize("timesteps", [1, 7])
-def test_voxelnet_forward_points_matches_chained_oracle(cuda, timesteps):
+def test_voxelnet_forward_points_matches_chained_oracle(cuda, timesteps, precision):
     """forecast_n0 (timesteps=1) and forecast_n3 (7-timestep vel head) on a reduced scene, end to end."""
     m = build_model(timesteps, cuda, seed=timesteps)
     scenes = [synth_scene(50000, seed=3), synth_scene(36000, seed=4)]
