@@ -49,7 +49,7 @@ class SparseBasicBlock(SparseModule):
         identity = x if self.downsample is None else self.downsample(x)
         out = self.conv1(x, bn=self.bn1, relu=True)
         # relu(bn2(conv2(out)) + identity) in one epilogue (scn.py:71-78)
-        return self.conv2(out, bn=self.bn2, residual=identity.features, relu=True)
+        return self.conv2(out, bn=self.bn2, residual=identity._feat, relu=True)
 
 
 @BACKBONES.register_module
@@ -82,10 +82,11 @@ class SpMiddleResNetFHD(nn.Module):
         self.extra_conv = SparseSequential(
             SparseConv3d(128, 128, (3, 1, 1), (2, 1, 1), bias=False), bn(128), nn.ReLU())
 
-    def forward(self, voxel_features, coors, batch_size, input_shape, n_dev=None, n_cap=None):
+    def forward(self, voxel_features, coors, batch_size, input_shape, n_dev=None, n_cap=None, out_fmt="fp32"):
         """voxel_features [M,>=5], coors [M,4] (b,z,y,x), input_shape = grid (x,y,z).
         Returns (dense [B, 256, H, W] (channels-last memory), dict of per-stage SparseConvTensors).
-        n_dev/n_cap: optional device-resident row count + capacity (fused voxelizer path)."""
+        n_dev/n_cap: optional device-resident row count + capacity (fused voxelizer path).
+        out_fmt="split" (fused pipeline only) returns the BEV map as an ops.Feat in split bf16 rows [B,H,W,256]."""
         sparse_shape = np.array([int(v) for v in input_shape][::-1]) + [1, 0, 0]
         ret = SparseConvTensor(voxel_features, coors, sparse_shape, batch_size, n_dev=n_dev, n_cap=n_cap)
         x = self.conv_input(ret)
@@ -93,6 +94,6 @@ class SpMiddleResNetFHD(nn.Module):
         x_conv2 = self.conv2(x_conv1)
         x_conv3 = self.conv3(x_conv2)
         x_conv4 = self.conv4(x_conv3)
-        bev = self.extra_conv(x_conv4, bev_last=True)      # [B, H, W, C*D] channels-last, channel = c*D + d
-        ret = bev.permute(0, 3, 1, 2)                      # logical [B, C*D, H, W] as scn.py:167-168
+        bev = self.extra_conv(x_conv4, bev_last=True, out_fmt=out_fmt)   # [B, H, W, C*D] channels-last, channel = c*D + d
+        ret = bev if out_fmt == "split" else bev.permute(0, 3, 1, 2)    # logical [B, C*D, H, W] as scn.py:167-168
         return ret, {"conv1": x_conv1, "conv2": x_conv2, "conv3": x_conv3, "conv4": x_conv4}

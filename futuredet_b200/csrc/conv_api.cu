@@ -17,6 +17,22 @@ sparse_to_dense_kernel(const float* __restrict__ feat, int feat_stride, int C, c
   }
 }
 
+__global__ void __launch_bounds__(256)
+convert_rows_kernel(const float* __restrict__ src, int sfmt, int sstride, int sctot, float* __restrict__ dst, int dfmt,
+                    int dstride, int dctot, int C, const int32_t* __restrict__ d_n, long long n_cap) {
+  const long long n = d_n ? min((long long)*d_n, n_cap) : n_cap;
+  const long long total = n * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long r = e / C;
+    int c = (int)(e - r * C);
+    const float* srow = src + (size_t)r * sstride;
+    float* drow = dst + (size_t)r * dstride;
+    float v = sfmt == FD_FMT_SPLIT_BF16 ? split_load(srow, c, sctot) : srow[c];
+    if (dfmt == FD_FMT_SPLIT_BF16) split_store(drow, c, dctot, v); else drow[c] = v;
+  }
+}
+
 }  // namespace fd
 
 extern "C" {
@@ -32,13 +48,20 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
   FD_REQUIRE(d->n_out_cap >= 0, "fd_conv_forward: negative n_out_cap");
   FD_REQUIRE(!d->d_residual || d->res_stride >= d->cout, "fd_conv_forward: res_stride < cout");
   ConvArgs a{};
-  a.in = d->d_in; a.in_stride = d->in_stride; a.cin = d->cin;
+  a.in = (const float*)d->d_in; a.in_stride = d->in_stride; a.cin = d->cin;
+  a.in_fmt = d->in_format; a.in_ctot = d->in_ctot > 0 ? d->in_ctot : d->cin;
+  a.out_fmt = d->out_format; a.out_ctot = d->out_ctot > 0 ? d->out_ctot : d->cout;
+  a.res_fmt = d->res_format; a.res_ctot = d->res_ctot > 0 ? d->res_ctot : d->cout;
+  for (int f : {d->in_format, d->out_format, d->res_format})
+    FD_REQUIRE(f == FD_FMT_FP32 || f == FD_FMT_SPLIT_BF16, "fd_conv_forward: unknown row format %d", f);
+  FD_REQUIRE(a.in_ctot >= d->cin && a.in_stride >= (d->in_format == FD_FMT_SPLIT_BF16 ? a.in_ctot : d->cin),
+             "fd_conv_forward: in_ctot/in_stride inconsistent");
   a.w = d->d_w; a.cout = d->cout; a.K = d->K;
   a.wp = d->d_w_packed;
   a.scale = d->d_scale; a.shift = d->d_shift;
-  a.residual = d->d_residual; a.res_stride = d->res_stride;
+  a.residual = (const float*)d->d_residual; a.res_stride = d->res_stride;
   a.relu = d->relu;
-  a.out = d->d_out; a.out_stride = d->out_stride;
+  a.out = (float*)d->d_out; a.out_stride = d->out_stride;
   a.d_n = d->d_n_out; a.n_cap = d->n_out_cap;
   a.mode = d->mode; a.nbr = d->d_nbr; a.nbr_stride = d->nbr_stride;
   a.Hin = d->Hin; a.Win = d->Win; a.Hout = d->Hout; a.Wout = d->Wout;
@@ -49,8 +72,8 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
   if (d->out_map == FD_OUTMAP_BEV) {
     FD_REQUIRE(d->d_out_coords4 && d->bevD >= 1 && d->bevH >= 1 && d->bevW >= 1,
                "fd_conv_forward: FD_OUTMAP_BEV needs out coords and bev dims");
-    FD_REQUIRE(d->out_stride >= d->cout * d->bevD, "fd_conv_forward: BEV out_stride %d < cout*D %d", d->out_stride,
-               d->cout * d->bevD);
+    FD_REQUIRE(d->out_stride >= d->cout * d->bevD && a.out_ctot >= d->cout * d->bevD,
+               "fd_conv_forward: BEV out_stride %d / out_ctot %d < cout*D %d", d->out_stride, a.out_ctot, d->cout * d->bevD);
     FD_REQUIRE(!d->d_residual, "fd_conv_forward: residual unsupported with FD_OUTMAP_BEV");
   } else {
     FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY, "fd_conv_forward: unknown out_map %d", d->out_map);
@@ -92,7 +115,7 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
         p.mode = FD_GATHER_CONV2D;
         p.K = 1; p.kh = p.kw = 1; p.sh = p.sw = 1; p.ph = p.pw = 0;
         p.Hout = d->Hin; p.Wout = d->Win;
-        p.w = d->d_w + (size_t)k * d->cin * d->cout;
+        p.w = (const float*)d->d_w + (size_t)k * d->cin * d->cout;
         if (d->d_w_packed) p.wp = (const char*)d->d_w_packed + (size_t)k * fd_conv_packed_bytes(1, d->cin, d->cout);
         p.out_map = OUTMAP_UPSAMPLE;
         p.up_s = d->sh; p.up_dy = k / d->kw; p.up_dx = k % d->kw;
@@ -104,6 +127,20 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
     default:
       return set_error(-1, "fd_conv_forward: unknown gather mode %d", d->mode);
   }
+}
+
+int fd_convert_rows(const void* d_src, int src_format, int src_stride, int src_ctot, void* d_dst, int dst_format,
+                    int dst_stride, int dst_ctot, int C, const int32_t* d_n, int64_t n_cap, void* stream) {
+  using namespace fd;
+  FD_REQUIRE(d_src && d_dst && C >= 1 && src_ctot >= C && dst_ctot >= C && src_stride >= 1 && dst_stride >= 1,
+             "fd_convert_rows: bad argument");
+  FD_REQUIRE((src_format | dst_format) >> 1 == 0, "fd_convert_rows: unknown format");
+  if (n_cap <= 0) return 0;
+  convert_rows_kernel<<<persistent_grid(ceil_div(n_cap * C, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)d_src, src_format, src_stride, src_ctot, (float*)d_dst, dst_format, dst_stride, dst_ctot, C, d_n,
+      n_cap);
+  FD_LAUNCHED();
+  return 0;
 }
 
 int fd_sparse_to_dense_ncdhw(const float* d_feat, int feat_stride, int C, const int32_t* d_coords4,

@@ -8,6 +8,7 @@ enum { OUTMAP_UPSAMPLE = 100 };  // internal: one phase of ConvTranspose2d(k == 
 
 struct ConvArgs {
   const float* in; int in_stride; int cin;
+  int in_fmt, in_ctot, out_fmt, out_ctot, res_fmt, res_ctot;
   const float* w; int cout; int K;
   const void* wp;            // packed bf16 hi/lo weights (tensor-core arm)
   const float* scale; const float* shift;
@@ -37,15 +38,33 @@ __device__ __forceinline__ int gather_row(const ConvArgs& a, int o, int k) {
   return (b * a.Hin + iy) * a.Win + ix;
 }
 
-// Where element (row o, channel c) of the result lives.  Returns base pointer and channel stride.
-struct OutRow { float* p; int cstride; };
+// ---- FD_FMT_SPLIT_BF16 helpers: a row is [ctot bf16 hi][ctot bf16 lo] in the same 4*ctot bytes ----------
+__device__ __forceinline__ float split_load(const float* row_base, int c, int ctot) {
+  const unsigned short* h = reinterpret_cast<const unsigned short*>(row_base);
+  return __uint_as_float((unsigned)h[c] << 16) + __uint_as_float((unsigned)h[ctot + c] << 16);
+}
+__device__ __forceinline__ unsigned short bf16_bits_rn(float x) {
+  unsigned u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (unsigned short)(u >> 16);      // inf / nan
+  return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+__device__ __forceinline__ void split_store(float* row_base, int c, int ctot, float v) {
+  unsigned short* h = reinterpret_cast<unsigned short*>(row_base);
+  unsigned short hi = bf16_bits_rn(v);
+  h[c] = hi;
+  h[ctot + c] = bf16_bits_rn(v - __uint_as_float((unsigned)hi << 16));
+}
+
+// Where the result row `o` lives: element c of the row is at (base, coff + c*cstride) -- in fp32 units for
+// FD_FMT_FP32, in bf16 units inside the hi plane (lo plane out_ctot further) for FD_FMT_SPLIT_BF16.
+struct OutRow { float* base; int coff; int cstride; };
 __device__ __forceinline__ OutRow map_out_row(const ConvArgs& a, int o) {
-  if (a.out_map == FD_OUTMAP_IDENTITY) return {a.out + (size_t)o * a.out_stride, 1};
+  if (a.out_map == FD_OUTMAP_IDENTITY) return {a.out + (size_t)o * a.out_stride, 0, 1};
   if (a.out_map == FD_OUTMAP_BEV) {
     // SparseConvTensor.dense().view(N, C*D, H, W) (scn.py:165-168): channel = c*D + z, stored channels-last
     int4 c = a.out_coords[o];
     size_t pix = ((size_t)c.x * a.bevH + c.z) * a.bevW + c.w;
-    return {a.out + pix * a.out_stride + c.y, a.bevD};
+    return {a.out + pix * a.out_stride, c.y, a.bevD};
   }
   // OUTMAP_UPSAMPLE: o = (b, y, x) on the input grid -> (b, y*s+dy, x*s+dx) on the output grid
   int hw = a.Hin * a.Win;
@@ -53,7 +72,16 @@ __device__ __forceinline__ OutRow map_out_row(const ConvArgs& a, int o) {
   int r = o - b * hw;
   int y = r / a.Win, x = r - y * a.Win;
   size_t pix = ((size_t)b * a.Hin * a.up_s + (size_t)y * a.up_s + a.up_dy) * (a.Win * a.up_s) + (size_t)x * a.up_s + a.up_dx;
-  return {a.out + pix * a.out_stride, 1};
+  return {a.out + pix * a.out_stride, 0, 1};
+}
+__device__ __forceinline__ void store_out(const ConvArgs& a, const OutRow& r, int c, float v) {
+  const int e = r.coff + c * r.cstride;
+  if (a.out_fmt == FD_FMT_SPLIT_BF16) split_store(r.base, e, a.out_ctot, v);
+  else r.base[e] = v;
+}
+__device__ __forceinline__ float load_residual(const ConvArgs& a, int o, int c) {
+  const float* row = a.residual + (size_t)o * a.res_stride;
+  return a.res_fmt == FD_FMT_SPLIT_BF16 ? split_load(row, c, a.res_ctot) : row[c];
 }
 
 int conv_forward_simt(const ConvArgs& a, cudaStream_t stream);

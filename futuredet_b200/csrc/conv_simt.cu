@@ -33,7 +33,8 @@ conv_simt_kernel(const ConvArgs a) {
   const int n = a.d_n ? min(*a.d_n, a.n_cap) : a.n_cap;
   const int n_tiles_m = (n + BM - 1) / BM;
   const int n_tiles_n = (a.cout + BN - 1) / BN;
-  const bool vec_in = (a.cin % 4 == 0) && (a.in_stride % 4 == 0) && (((uintptr_t)a.in & 15) == 0);
+  const bool split_in = a.in_fmt == FD_FMT_SPLIT_BF16;
+  const bool vec_in = !split_in && (a.cin % 4 == 0) && (a.in_stride % 4 == 0) && (((uintptr_t)a.in & 15) == 0);
   const bool vec_w = (a.cout % 4 == 0) && (((uintptr_t)a.w & 15) == 0);
 
   for (int tile = blockIdx.x; tile < n_tiles_m * n_tiles_n; tile += gridDim.x) {
@@ -76,7 +77,12 @@ conv_simt_kernel(const ConvArgs a) {
             int r = e / BK, q = e % BK;
             int c = c0 + q;
             int src = s_idx[r];
-            As[q][r] = (src >= 0 && c < a.cin) ? __ldg(a.in + (size_t)src * a.in_stride + c) : 0.f;
+            float v = 0.f;
+            if (src >= 0 && c < a.cin) {
+              const float* row = a.in + (size_t)src * a.in_stride;
+              v = split_in ? split_load(row, c, a.in_ctot) : __ldg(row + c);
+            }
+            As[q][r] = v;
           }
         }
         // ---- B tile: BK channels x BN outputs ---------------------------------------
@@ -130,9 +136,9 @@ conv_simt_kernel(const ConvArgs a) {
         int c = col0 + tx * TN + j;
         if (c >= a.cout) continue;
         float v = fmaf(acc[i][j], sc[j], sf[j]);
-        if (a.residual) v += a.residual[(size_t)o * a.res_stride + c];
+        if (a.residual) v += load_residual(a, o, c);
         if (a.relu) v = fmaxf(v, 0.f);
-        orow.p[(size_t)c * orow.cstride] = v;
+        store_out(a, orow, c, v);
       }
     }
   }

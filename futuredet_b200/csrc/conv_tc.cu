@@ -27,8 +27,9 @@ namespace fd {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements per stage row (128 bytes, one swizzle atom)
 constexpr int TC_MAXK = 32;               // max kernel offsets (27 for 3x3x3)
-constexpr int TC_PRODUCERS = 128;
-constexpr int TC_THREADS = 288;           // 4 producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
+constexpr int TC_THREADS = TC_PRODUCERS + 32 + 128;   // producer warps + 1 MMA warp + 4 epilogue warps
 constexpr int TC_A_PLANE = TC_BM * 128;   // bytes of one A plane (hi or lo) per stage
 
 __host__ __device__ constexpr int tc_stage_bytes(int NT) { return 2 * TC_A_PLANE + 2 * NT * 128; }
@@ -65,8 +66,41 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;     // src-size 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void* src, uint32_t sz) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on `bar` once every cp.async this thread has issued so far has landed (no wait in the thread)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -100,14 +134,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- weight packing ------------------------------------------------------------------------------
-// W fp32 [K, Cin, Cout]  ->  bf16 planes [2 (hi,lo)][cout_pad][ktot_pad], K-major (k*Cin + ci contiguous), zero padded.
+// W fp32 [K, Cin, Cout] -> for every (N tile tn, K stage ks) one contiguous block that is a byte-exact image of
+// the shared-memory B stage: [2 planes (hi, lo)][NT rows][64 bf16, 16-byte chunks XOR-swizzled by (row & 7)].
+// A stage's weights are then ONE cp.async.bulk (TMA bulk copy) instead of per-thread gathers.
 __global__ void __launch_bounds__(256)
-pack_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, int cout_pad, int ktot_pad,
+pack_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, int NT, int n_tiles_n, int n_kstages,
                     __nv_bfloat16* __restrict__ out) {
-  const long long total = (long long)cout_pad * ktot_pad;
+  const long long per_block = 2LL * NT * TC_BK;
+  const long long total = (long long)n_tiles_n * n_kstages * NT * TC_BK;     // elements of one plane
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    int n = (int)(e / ktot_pad), kf = (int)(e - (long long)n * ktot_pad);
+    const int kc = (int)(e % TC_BK);
+    long long r = e / TC_BK;
+    const int nrow = (int)(r % NT); r /= NT;
+    const int ks = (int)(r % n_kstages);
+    const int tn = (int)(r / n_kstages);
+    const int n = tn * NT + nrow, kf = ks * TC_BK + kc;
     float v = 0.f;
     if (n < cout && kf < K * cin) {
       int k = kf / cin, ci = kf - k * cin;
@@ -115,8 +157,10 @@ pack_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, int c
     }
     __nv_bfloat16 hi = __float2bfloat16_rn(v);
     __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    out[e] = hi;
-    out[total + e] = lo;
+    const long long blk = ((long long)tn * n_kstages + ks) * per_block;
+    const int off = nrow * TC_BK + ((((kc >> 3) ^ (nrow & 7)) << 3) | (kc & 7));
+    out[blk + off] = hi;
+    out[blk + (long long)NT * TC_BK + off] = lo;
   }
 }
 
@@ -160,7 +204,7 @@ conv_tc_kernel(const TcArgs t) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), TC_PRODUCERS);
+      mbar_init(smem_u32(&full_bar[s]), TC_PRODUCERS / (NT >= 128 ? 2 : 4));   // one producer group per stage
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -169,7 +213,7 @@ conv_tc_kernel(const TcArgs t) {
     }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == TC_PRODUCER_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -178,113 +222,153 @@ conv_tc_kernel(const TcArgs t) {
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
+  if (warp < TC_PRODUCER_WARPS) {
     // ===================================== PRODUCERS =====================================
-    const int tid = threadIdx.x;                 // 0..127
-    const int j = tid & 7, rbase = tid >> 3;     // 16-byte chunk column, first row
-    uint32_t stage = 0, phase = 0;
+    // The producer warps are split into G groups; group g fills every G-th emitted stage on its own, so G
+    // stages are being issued concurrently (a single warp's issue chain per stage is several hundred cycles).
+    constexpr int G = NT >= 128 ? 2 : 4;
+    constexpr int GT = TC_PRODUCERS / G;         // threads per group
+    constexpr int ROWS_PER_PASS = GT / 8;
+    constexpr int PASSES = TC_BM / ROWS_PER_PASS;
+    constexpr uint32_t B_BYTES = 2 * NT * 128;   // one pre-swizzled weight stage (hi + lo planes)
+    const int tid = threadIdx.x;                 // 0..TC_PRODUCERS-1
+    const int grp = tid / GT, gt = tid % GT;
+    const int j = gt & 7, rbase = gt >> 3;       // 16-byte chunk column, first row (rows rbase + p*ROWS_PER_PASS)
+    uint32_t slot = 0, phase = 0, turn = 0;      // ring slot / phase / owning group of the next emitted stage
+    const uint32_t stage_u32 = smem_u32(stage_base);
+    const uint32_t nbr_u32 = smem_u32(s_nbr);
+    // per-thread constant of the swizzled A stores ((row & 7) is the same for every pass of a thread)
+    const uint32_t a_off0 = rbase * 128 + ((j ^ (rbase & 7)) << 4);
+    // flattened-K bookkeeping without per-stage divisions: Cin is a multiple of 64, or divides 64
+    const bool wide = a.cin >= TC_BK;
+    const int spo = wide ? a.cin / TC_BK : 1;    // stages per kernel offset   (wide)
+    const int opk = wide ? 1 : TC_BK / a.cin;    // kernel offsets per stage   (narrow)
+    const int jk = wide ? 0 : (j * 8) / a.cin;   // which of the stage's offsets this thread's chunk belongs to
+    const int jc = wide ? j * 8 : (j * 8) % a.cin;
+    const uint32_t row_bytes = (uint32_t)a.in_stride * 4;
+    const char* in_b = reinterpret_cast<const char*>(a.in);
+    const char* in_lo = in_b + (size_t)a.in_ctot * 2;
+    const char* wblocks = reinterpret_cast<const char*>(t.wp);
     // rulebook rows of one tile -> s_nbr[buf] (cp.async for the table mode, arithmetic for dense 2-D)
     auto load_nbr = [&](int tile, int buf) {
       const int tm = tile / t.n_tiles_n;
-      const int o = tm * TC_BM + tid;
-      int* dst = s_nbr + buf * TC_MAXK * TC_BM;
-      if (a.mode == FD_GATHER_TABLE) {
-        if (o < n) {
-          for (int k = 0; k < a.K; ++k) cp_async4(smem_u32(dst + k * TC_BM + tid), a.nbr + (size_t)k * a.nbr_stride + o);
-        } else {
-          for (int k = 0; k < a.K; ++k) dst[k * TC_BM + tid] = -1;
-        }
-      } else {
-        for (int k = 0; k < a.K; ++k) dst[k * TC_BM + tid] = o < n ? gather_row(a, o, k) : -1;
+      for (int e = tid; e < a.K * TC_BM; e += TC_PRODUCERS) {
+        const int k = e >> 7, r = e & (TC_BM - 1);
+        const int o = tm * TC_BM + r;
+        const uint32_t dst = nbr_u32 + (uint32_t)(buf * TC_MAXK * TC_BM + e) * 4;
+        if (a.mode == FD_GATHER_TABLE && o < n) cp_async4(dst, a.nbr + (size_t)k * a.nbr_stride + o);
+        else sts_u32(dst, (uint32_t)(o < n ? gather_row(a, o, k) : -1));
       }
     };
     int it = 0;
     if ((int)blockIdx.x < n_tiles) load_nbr(blockIdx.x, 0);
+    cp_async_commit();
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int tn = tile % t.n_tiles_n;
-      const int* nb = s_nbr + buf * TC_MAXK * TC_BM;
-      cp_async_wait_all();
+      const uint32_t nb_u32 = nbr_u32 + (uint32_t)(buf * TC_MAXK * TC_BM) * 4;
+      cp_async_wait_group<0>();                            // rulebook rows of this tile (committed a whole tile ago;
+                                                           // stage gathers are never committed, so not waited for)
       if (tid == 0) s_active[buf] = 0;
       named_bar_sync(1, TC_PRODUCERS);                     // s_nbr[buf] complete, s_active cleared
       {
         uint32_t m = 0;
-        for (int k = 0; k < a.K; ++k)
-          if (__any_sync(0xffffffffu, nb[k * TC_BM + tid] >= 0)) m |= 1u << k;
+        for (int e = tid; e < a.K * TC_BM; e += TC_PRODUCERS)       // k is warp-uniform (32 consecutive rows)
+          if (__any_sync(0xffffffffu, (int)lds_u32(nb_u32 + (uint32_t)e * 4) >= 0)) m |= 1u << (e >> 7);
         if (lane == 0 && m) atomicOr(&s_active[buf], m);
       }
       if (tile + (int)gridDim.x < n_tiles) load_nbr(tile + gridDim.x, buf ^ 1);   // prefetch next tile's rows
+      cp_async_commit();
       named_bar_sync(1, TC_PRODUCERS);
       const uint32_t active = s_active[buf];
       // stage list: flattened-K stages that touch at least one active kernel offset
+      auto stage_mask = [&](int ks) -> uint32_t {
+        return wide ? (1u << (ks / spo)) : ((((1u << opk) - 1u) << (ks * opk)));
+      };
       int first_ks = -1, last_ks = -1;
-      for (int ks = 0; ks < n_kstages; ++ks) {
-        int k0 = (ks * TC_BK) / a.cin, k1 = min((ks * TC_BK + TC_BK - 1) / a.cin, a.K - 1);
-        uint32_t msk = (k1 >= 31 ? 0xffffffffu : ((1u << (k1 + 1)) - 1)) & ~((1u << k0) - 1);
-        if (active & msk) { if (first_ks < 0) first_ks = ks; last_ks = ks; }
-      }
+      for (int ks = 0; ks < n_kstages; ++ks)
+        if (active & stage_mask(ks)) { if (first_ks < 0) first_ks = ks; last_ks = ks; }
       if (first_ks < 0) first_ks = last_ks = 0;            // degenerate tile: one all-zero stage
+      const char* wtile = wblocks + (size_t)tn * n_kstages * B_BYTES;
+      int kk_run = wide ? first_ks / spo : 0, c_idx = wide ? first_ks - kk_run * spo : 0;
       for (int ks = first_ks; ks <= last_ks; ++ks) {
-        const int kf0 = ks * TC_BK;
-        {
-          int k0 = kf0 / a.cin, k1 = min((kf0 + TC_BK - 1) / a.cin, a.K - 1);
-          uint32_t msk = (k1 >= 31 ? 0xffffffffu : ((1u << (k1 + 1)) - 1)) & ~((1u << k0) - 1);
-          if (!(active & msk) && ks != first_ks && ks != last_ks) continue;
+        const uint32_t smask = wide ? (1u << kk_run) : (((1u << opk) - 1u) << (ks * opk));
+        const int kk = wide ? kk_run : ks * opk + jk;
+        const int ch = wide ? c_idx * TC_BK + jc : jc;
+        if (wide && ++c_idx == spo) { c_idx = 0; ++kk_run; }
+        if (!(active & smask) && ks != first_ks && ks != last_ks) continue;
+        // every group walks the same emitted-stage sequence; only the owner of this stage fills it
+        const uint32_t my_slot = slot, my_phase = phase;
+        const bool mine = turn == (uint32_t)grp;
+        if (++slot == STAGES) { slot = 0; phase ^= 1; }
+        if (++turn == G) turn = 0;
+        if (!mine) continue;
+        mbar_wait(smem_u32(&empty_bar[my_slot]), my_phase ^ 1);
+        const uint32_t sbase = stage_u32 + my_slot * STAGE_BYTES;
+        const uint32_t fbar = smem_u32(&full_bar[my_slot]);
+        if (gt == 0) {
+          s_meta[my_slot] = (ks == first_ks ? 1u : 0u) | (ks == last_ks ? 2u : 0u);
+          // ---- B: one TMA bulk copy of the pre-swizzled weight stage, completes (in bytes) on the full barrier
+          mbar_expect_tx(fbar, B_BYTES);
+          bulk_g2s(sbase + 2 * TC_A_PLANE, wtile + (size_t)ks * B_BYTES, B_BYTES, fbar);
         }
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        uint8_t* sA_hi = stage_base + stage * STAGE_BYTES;
-        uint8_t* sA_lo = sA_hi + TC_A_PLANE;
-        uint8_t* sB = sA_lo + TC_A_PLANE;                  // [2][NT][128 B]
-        // ---- B: packed bf16 hi/lo weight rows, 16-byte cp.async into the swizzled layout
-        for (int i = tid; i < NT * 16; i += TC_PRODUCERS) {
-          int plane = i / (NT * 8), rem = i - plane * NT * 8;
-          int nrow = rem >> 3, jj = rem & 7;
-          const __nv_bfloat16* src = t.wp + ((size_t)plane * t.cout_pad + tn * NT + nrow) * t.ktot_pad + kf0 + jj * 8;
-          cp_async16(smem_u32(sB + plane * NT * 128 + nrow * 128 + ((jj ^ (nrow & 7)) << 4)), src);
-        }
-        // ---- A: gather 128 rows x 64 channels (this thread: chunk j of rows rbase + 16 p)
-        const int kf = kf0 + j * 8;
-        const int kk = kf / a.cin, ch = kf - kk * a.cin;
+        // ---- A: gather 128 rows x 64 channels (this thread: chunk j of rows rbase + ROWS_PER_PASS p)
         const bool kvalid = kk < a.K;
-        float4 v[8][2];
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int r = p * 16 + rbase;
-          const int src = kvalid ? nb[kk * TC_BM + r] : -1;
-          if (src >= 0) {
-            const float4* g = reinterpret_cast<const float4*>(a.in + (size_t)src * a.in_stride + ch);
-            v[p][0] = __ldg(g);
-            v[p][1] = __ldg(g + 1);
-          } else {
-            v[p][0] = v[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t nb_row = nb_u32 + (uint32_t)((kvalid ? kk : 0) * TC_BM + rbase) * 4;
+        const uint32_t dst0 = sbase + a_off0;
+        if (a.in_fmt == FD_FMT_SPLIT_BF16) {
+          // pre-split bf16 hi/lo rows: pure 16-byte cp.async copies (zero-filled where the rulebook has no
+          // neighbour); nothing is waited for -- the hardware arrives on the full barrier when they land
+          const char* gh = in_b + ch * 2;
+          const char* gl = in_lo + ch * 2;
+#pragma unroll 8
+          for (int p = 0; p < PASSES; ++p) {
+            const int src = kvalid ? (int)lds_u32(nb_row + p * ROWS_PER_PASS * 4) : -1;
+            const uint32_t sz = src >= 0 ? 16u : 0u;
+            const size_t goff = (size_t)(uint32_t)max(src, 0) * row_bytes;
+            cp_async16_sz(dst0 + p * ROWS_PER_PASS * 128, gh + goff, sz);
+            cp_async16_sz(dst0 + p * ROWS_PER_PASS * 128 + TC_A_PLANE, gl + goff, sz);
           }
-        }
+          cp_async_mbar_arrive_noinc(fbar);
+        } else {
+          // fp32 rows (the stem reading voxel features): split into bf16 hi/lo in registers, 4 rows at a time
+#pragma unroll 1
+          for (int p0 = 0; p0 < PASSES; p0 += 4) {
+            float4 v[4][2];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int r = p * 16 + rbase;
-          const float f[8] = {v[p][0].x, v[p][0].y, v[p][0].z, v[p][0].w, v[p][1].x, v[p][1].y, v[p][1].z, v[p][1].w};
-          uint32_t hi[4], lo[4];
+            for (int p = 0; p < 4; ++p) {
+              const int src = kvalid ? (int)lds_u32(nb_row + (p0 + p) * ROWS_PER_PASS * 4) : -1;
+              if (src >= 0) {
+                const float4* gp = reinterpret_cast<const float4*>(a.in + (size_t)src * a.in_stride + ch);
+                v[p][0] = __ldg(gp);
+                v[p][1] = __ldg(gp + 1);
+              } else {
+                v[p][0] = v[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-            float2 hf = __bfloat1622float2(h);
-            __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
-            hi[q] = *reinterpret_cast<uint32_t*>(&h);
-            lo[q] = *reinterpret_cast<uint32_t*>(&l);
+            for (int p = 0; p < 4; ++p) {
+              const float f[8] = {v[p][0].x, v[p][0].y, v[p][0].z, v[p][0].w, v[p][1].x, v[p][1].y, v[p][1].z, v[p][1].w};
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+                float2 hf = __bfloat1622float2(h);
+                __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
+                hi[q] = *reinterpret_cast<uint32_t*>(&h);
+                lo[q] = *reinterpret_cast<uint32_t*>(&l);
+              }
+              sts_u128(dst0 + (p0 + p) * ROWS_PER_PASS * 128, hi[0], hi[1], hi[2], hi[3]);
+              sts_u128(dst0 + (p0 + p) * ROWS_PER_PASS * 128 + TC_A_PLANE, lo[0], lo[1], lo[2], lo[3]);
+            }
           }
-          const uint32_t off = r * 128 + ((j ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(sA_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(sA_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          fence_proxy_async();                             // generic-proxy smem writes -> visible to the tensor core
+          mbar_arrive(fbar);
         }
-        if (tid == 0) s_meta[stage] = (ks == first_ks ? 1u : 0u) | (ks == last_ks ? 2u : 0u);
-        cp_async_wait_all();
-        fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core
-        mbar_arrive(smem_u32(&full_bar[stage]));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
     cp_async_wait_all();
-  } else if (warp == 4) {
+  } else if (warp == TC_PRODUCER_WARPS) {
     // ===================================== MMA ISSUER =====================================
     uint32_t stage = 0, phase = 0;
     int it = 0;
@@ -297,6 +381,7 @@ conv_tc_kernel(const TcArgs t) {
       while (true) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
+        fence_proxy_async();
         const uint32_t meta = s_meta[stage];
         if (lane == 0) {
           const uint32_t sA_hi = smem_u32(stage_base + stage * STAGE_BYTES);
@@ -336,7 +421,7 @@ conv_tc_kernel(const TcArgs t) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NT;
       const bool live = o < n;
-      OutRow orow{nullptr, 1};
+      OutRow orow{nullptr, 0, 1};
       if (live) orow = map_out_row(a, o);
       const float* res = (a.residual && live) ? a.residual + (size_t)o * a.res_stride : nullptr;
 #pragma unroll 1
@@ -349,36 +434,80 @@ conv_tc_kernel(const TcArgs t) {
           mbar_arrive(smem_u32(&tempty_bar[acc]));
         }
         if (!live) continue;
+        const int cbase = col0 + c0;
+        if (cbase >= a.cout) continue;
+        const bool full16 = cbase + 16 <= a.cout;
         float y[16];
+        // residual (identity) values
+        if (res) {
+          if (a.res_fmt == FD_FMT_SPLIT_BF16 && full16) {
+            const uint4* rh = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(res) + cbase);
+            const uint4* rl = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(res) + a.res_ctot + cbase);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 a4 = __ldg(rh + h), b4 = __ldg(rl + h);
+              const uint32_t hw[4] = {a4.x, a4.y, a4.z, a4.w}, lw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                y[h * 8 + 2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+                y[h * 8 + 2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = (cbase + i < a.cout) ? load_residual(a, o, cbase + i) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int c = col0 + c0 + i;
+          const int c = cbase + i;
           float v = __uint_as_float(r[i]);
           if (c < a.cout) {
             const float sc = a.scale ? __ldg(a.scale + c) : 1.f;
             const float sh = a.shift ? __ldg(a.shift + c) : 0.f;
-            v = fmaf(v, sc, sh);
-            if (res) v += res[c];
+            v = fmaf(v, sc, sh) + y[i];
             if (a.relu) v = fmaxf(v, 0.f);
           }
           y[i] = v;
         }
-        const int cbase = col0 + c0;
-        if (orow.cstride == 1 && cbase + 16 <= a.cout && ((((uintptr_t)(orow.p + cbase)) & 15) == 0)) {
-          float4* dst = reinterpret_cast<float4*>(orow.p + cbase);
+        if (orow.cstride == 1 && full16 && a.out_fmt == FD_FMT_SPLIT_BF16 &&
+            ((((uintptr_t)orow.base) + 2 * (size_t)(orow.coff + cbase)) & 15) == 0 && (a.out_ctot & 7) == 0) {
+          // split once here so that every consumer layer gathers ready-made bf16 hi/lo planes
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+            float2 hf = __bfloat1622float2(h);
+            __nv_bfloat162 l = __floats2bfloat162_rn(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
+            hi[i] = *reinterpret_cast<uint32_t*>(&h);
+            lo[i] = *reinterpret_cast<uint32_t*>(&l);
+          }
+          unsigned short* ob = reinterpret_cast<unsigned short*>(orow.base) + orow.coff + cbase;
+          uint4* dh = reinterpret_cast<uint4*>(ob);
+          uint4* dl = reinterpret_cast<uint4*>(ob + a.out_ctot);
+          dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        } else if (orow.cstride == 1 && full16 && a.out_fmt == FD_FMT_FP32 &&
+                   ((((uintptr_t)(orow.base + orow.coff + cbase)) & 15) == 0)) {
+          float4* dst = reinterpret_cast<float4*>(orow.base + orow.coff + cbase);
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (cbase + i < a.cout) orow.p[(size_t)(cbase + i) * orow.cstride] = y[i];
+            if (cbase + i < a.cout) store_out(a, orow, cbase + i, y[i]);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_PRODUCER_WARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
@@ -406,10 +535,11 @@ static int launch_tc(const TcArgs& t, cudaStream_t stream) {
 int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
   if (a.n_cap <= 0) return 0;
   FD_REQUIRE(a.wp != nullptr, "fd_conv_forward: tensor-core precision needs d_w_packed (fd_conv_pack_weights)");
-  FD_REQUIRE(a.cin % 8 == 0, "fd_conv_forward: tensor-core arm needs Cin to be a multiple of 8 (got %d)", a.cin);
+  FD_REQUIRE(a.cin % 8 == 0 && (a.cin % TC_BK == 0 || TC_BK % a.cin == 0),
+             "fd_conv_forward: tensor-core arm needs Cin in {8,16,32} or a multiple of 64 (got %d)", a.cin);
   FD_REQUIRE(a.K <= TC_MAXK, "fd_conv_forward: tensor-core arm supports at most %d kernel offsets", TC_MAXK);
-  FD_REQUIRE(a.in_stride % 4 == 0 && (((uintptr_t)a.in) & 15) == 0,
-             "fd_conv_forward: tensor-core arm needs 16-byte aligned input rows");
+  FD_REQUIRE(a.in_stride % 4 == 0 && (((uintptr_t)a.in) & 15) == 0 && (a.in_fmt != FD_FMT_SPLIT_BF16 || a.in_ctot % 8 == 0),
+             "fd_conv_forward: tensor-core arm needs 16-byte aligned input rows / planes");
   TcArgs t{};
   t.c = a;
   t.wp = (const __nv_bfloat16*)a.wp;
@@ -417,6 +547,7 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
   t.cout_pad = pad_to(a.cout, NT);
   t.ktot_pad = pad_to(a.K * a.cin, TC_BK);
   t.n_tiles_n = t.cout_pad / NT;
+  FD_REQUIRE((((uintptr_t)a.wp) & 15) == 0, "fd_conv_forward: d_w_packed must be 16-byte aligned");
   t.split = precision == FD_PREC_BF16X3;
   switch (NT) {
     case 128: return launch_tc<128>(t, stream);
@@ -442,7 +573,7 @@ int fd_conv_pack_weights(const float* d_w, int K, int cin, int cout, void* d_pac
   const int NT = pick_nt(cout);
   const int cout_pad = pad_to(cout, NT), ktot_pad = pad_to(K * cin, TC_BK);
   pack_weights_kernel<<<persistent_grid(ceil_div((int64_t)cout_pad * ktot_pad, 256), 8), 256, 0, (cudaStream_t)stream>>>(
-      d_w, K, cin, cout, cout_pad, ktot_pad, (__nv_bfloat16*)d_packed);
+      d_w, K, cin, cout, NT, cout_pad / NT, ktot_pad / TC_BK, (__nv_bfloat16*)d_packed);
   FD_LAUNCHED();
   return 0;
 }

@@ -75,10 +75,16 @@ class VoxelNet(SingleStageDetector):
             feats = data["mean_features"]
         else:
             feats = self.reader(data["features"], data["num_voxels"])
+        # the fused pipeline hands activations between backbone, neck and head in the kernels' inter-layer format
+        # (split bf16 hi/lo rows on the tensor-core arm); `fused=False` keeps every boundary a plain fp32 tensor
+        fmt = "fp32"
+        if data.get("fused", False):
+            from .neck import act_fmt
+            fmt = act_fmt()
         x, voxel_feature = self.backbone(feats, data["coors"], data["batch_size"], data["input_shape"],
-                                         n_dev=data.get("n_dev"), n_cap=data.get("n_cap"))
+                                         n_dev=data.get("n_dev"), n_cap=data.get("n_cap"), out_fmt=fmt)
         if self.with_neck:
-            x = self.neck(x)
+            x = self.neck(x, out_fmt=fmt)
         return x, voxel_feature
 
     def forward(self, example, return_loss=True, **kwargs):
@@ -106,8 +112,10 @@ class VoxelNet(SingleStageDetector):
         c = self.voxel_cfg
         if c is None:
             raise RuntimeError("call configure_voxelizer(cfg.voxel_generator) before forward_points()")
+        nf = self.reader.num_input_features
+        # rows zero-padded to a multiple of 8 channels so the stem conv can run on the tensor-core arm
         return ops.voxelize_vfe(points, batch_offsets, c["voxel_size"], c["range"], c["max_points"], c["max_voxels"],
-                                num_feat=self.reader.num_input_features)
+                                num_feat=nf, feat_stride=(nf + 7) // 8 * 8)
 
     def forward_points(self, points, batch_offsets, return_voxels=False):
         """points [sum N, >=5] fp32 CUDA, batch_offsets [B+1] int32 CUDA -> CenterHead predictions."""
@@ -116,7 +124,7 @@ class VoxelNet(SingleStageDetector):
         B = batch_offsets.numel() - 1
         grid = ops.grid_size_of(c["range"], c["voxel_size"])
         data = dict(mean_features=vox["features"], coors=vox["coords"], batch_size=B, input_shape=grid,
-                    n_dev=vox["total"], n_cap=vox["coords"].shape[0])
+                    n_dev=vox["total"], n_cap=vox["coords"].shape[0], fused=True)
         x, _ = self.extract_feat(data)
         preds = self.bbox_head(x, None)
         return (preds, vox) if return_voxels else preds

@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .neck import conv_weight_kio, run_conv, to_nhwc
+from .neck import act_fmt, as_nhwc_feat, conv_weight_kio, run_conv, to_nhwc
 from .registry import HEADS
 from .sparse import folded_epilogue
 
@@ -90,28 +90,34 @@ class SepHead(nn.Module):
         return cache["v"]
 
     def forward(self, x, precision=None):
-        """x: channels-last [B,H,W,C] view (or logical NCHW).  Returns {head: logical [B,c,H,W]}."""
-        if x.dim() == 4 and x.stride(3) != 1:
-            x = to_nhwc(x)
+        """x: channels-last [B,H,W,C] tensor / ops.Feat (or logical NCHW tensor).  Returns {head: logical [B,c,H,W]}
+        fp32 views of one channels-last [B,H,W,sum c] result tensor."""
         from . import neck as _neck
         prec = precision or _neck.DEFAULT_PRECISION
+        fmt = act_fmt(prec)
+        if isinstance(x, torch.Tensor) and x.dim() == 4 and x.stride(3) != 1:
+            x = to_nhwc(x)
+        x = ops.as_feat(x)
+        if x.fmt != fmt:
+            x = as_nhwc_feat(x, fmt)
         groups = self._stage_groups()
         names = list(self.heads)
-        B, H, W, _ = x.shape
+        B, H, W = x.t.shape[0], x.t.shape[1], x.t.shape[2]
         total_c = sum(self.heads[h][0] for h in names)
-        out = torch.empty((B, H, W, total_c), dtype=torch.float32, device=x.device)
+        out = ops.Feat(torch.empty((B, H, W, total_c), dtype=torch.float32, device=x.t.device), "fp32")
         fuse = all(len(groups[h]) == 2 for h in names) and len({groups[h][0][0].kernel_size for h in names}) == 1
         ret, col = {}, 0
         if fuse:
             w, sc, sh = self._fused_first(groups)
             c0 = groups[names[0]][0][0]
-            mid = ops.conv2d_nhwc(x, w, c0.kernel_size, c0.stride, c0.padding, sc, sh, True, precision=prec)
+            mid = ops.as_feat(ops.conv2d_nhwc(x, w, c0.kernel_size, c0.stride, c0.padding, sc, sh, True, precision=prec,
+                                              out_fmt=fmt))
             hc = c0.out_channels
             for i, h in enumerate(names):
                 conv, bnm, relu = groups[h][1]
                 c = conv.out_channels
-                run_conv(mid[..., i * hc:(i + 1) * hc], conv, bnm, relu, out=out[..., col:col + c], precision=prec)
-                ret[h] = out[..., col:col + c].permute(0, 3, 1, 2)
+                run_conv(mid.slice(i * hc, hc), conv, bnm, relu, out=out.slice(col, c), precision=prec)
+                ret[h] = out.t[..., col:col + c].permute(0, 3, 1, 2)
                 col += c
         else:
             for h in names:
@@ -120,8 +126,8 @@ class SepHead(nn.Module):
                 for si, (conv, bnm, relu) in enumerate(steps):
                     last = si == len(steps) - 1
                     c = conv.out_channels
-                    y = run_conv(y, conv, bnm, relu, out=out[..., col:col + c] if last else None, precision=prec)
-                ret[h] = out[..., col:col + c].permute(0, 3, 1, 2)
+                    y = ops.as_feat(run_conv(y, conv, bnm, relu, out=out.slice(col, c) if last else None, precision=prec))
+                ret[h] = out.t[..., col:col + c].permute(0, 3, 1, 2)
                 col += c
         return ret
 
@@ -176,8 +182,8 @@ class CenterHead(nn.Module):
 
     def forward(self, x, bev_map=None, *kwargs):
         """x logical [B,512,H,W] -> list over tasks of {head: logical [B,c,H,W]} (center_head.py:375-390)."""
-        x = to_nhwc(x)
-        x = run_conv(x, self.shared_conv[0], self.shared_conv[1], True)
+        x = as_nhwc_feat(x, act_fmt())
+        x = ops.as_feat(run_conv(x, self.shared_conv[0], self.shared_conv[1], True))
         return [task(x) for task in self.tasks]
 
     def loss(self, example, preds_dicts, **kwargs):

@@ -18,12 +18,15 @@ class ConvDesc(C.Structure):
     """Mirror of `struct fd_conv_desc`."""
     _fields_ = [
         ("d_in", C.c_void_p), ("in_stride", C.c_int32), ("cin", C.c_int32),
+        ("in_format", C.c_int32), ("in_ctot", C.c_int32),
         ("d_w", C.c_void_p), ("cout", C.c_int32), ("K", C.c_int32),
         ("d_w_packed", C.c_void_p),
         ("d_scale", C.c_void_p), ("d_shift", C.c_void_p),
         ("d_residual", C.c_void_p), ("res_stride", C.c_int32),
+        ("res_format", C.c_int32), ("res_ctot", C.c_int32),
         ("relu", C.c_int32),
         ("d_out", C.c_void_p), ("out_stride", C.c_int32),
+        ("out_format", C.c_int32), ("out_ctot", C.c_int32),
         ("d_n_out", C.c_void_p), ("n_out_cap", C.c_int32),
         ("mode", C.c_int32),
         ("d_nbr", C.c_void_p), ("nbr_stride", C.c_int32),
@@ -68,6 +71,8 @@ SIGNATURES = {
     "fd_conv_pack_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fd_sparse_to_dense_ncdhw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "fd_convert_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_int64, C.c_void_p]),
     "fd_fill_i32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
 }
 

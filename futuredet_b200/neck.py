@@ -45,13 +45,32 @@ def conv_weight_kio(conv):
     return cache["v"]
 
 
-def run_conv(x, conv, bn, relu, out=None, pad=None, precision=None):
-    """x channels-last [B,H,W,C] -> fused conv(+bias)+BN(eval)+ReLU."""
+def act_fmt(precision=None):
+    """Inter-layer activation format of a precision: fp32 rows, or split bf16 hi/lo rows on the tensor-core arm."""
+    return "fp32" if (precision or DEFAULT_PRECISION) == "fp32" else "split"
+
+
+def run_conv(x, conv, bn, relu, out=None, pad=None, precision=None, out_fmt=None):
+    """x channels-last [B,H,W,C] (tensor or ops.Feat) -> fused conv(+bias)+BN(eval)+ReLU."""
     scale, shift = folded_epilogue(conv, bn)
     transposed = isinstance(conv, nn.ConvTranspose2d)
     padding = conv.padding if pad is None else pad
+    prec = precision or DEFAULT_PRECISION
+    if prec != "fp32" and conv.in_channels % 8 != 0:
+        prec = "fp32"
     return ops.conv2d_nhwc(x, conv_weight_kio(conv), conv.kernel_size, conv.stride, padding, scale, shift, relu,
-                           out=out, precision=precision or DEFAULT_PRECISION, transposed=transposed)
+                           out=out, precision=prec, transposed=transposed,
+                           out_fmt=out_fmt or act_fmt(prec))
+
+
+def as_nhwc_feat(x, fmt):
+    """Logical NCHW tensor / channels-last Feat -> Feat in the requested inter-layer format."""
+    if isinstance(x, ops.Feat):
+        if x.fmt == fmt:
+            return x
+        return ops.to_split(x) if fmt == "split" else ops.Feat(x.to_fp32())
+    x = to_nhwc(x)
+    return ops.to_split(x) if fmt == "split" else ops.Feat(x)
 
 
 def to_nhwc(x):
@@ -115,30 +134,36 @@ class RPN(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.xavier_uniform_(m.weight)
 
-    def forward(self, x):
-        """x logical [B,C,H,W] -> logical [B, sum(us_num_filters), H', W'] (channels-last memory)."""
-        x = to_nhwc(x)
-        B = x.shape[0]
+    def forward(self, x, out_fmt="fp32"):
+        """x logical [B,C,H,W] (or a channels-last ops.Feat) -> logical [B, sum(us_num_filters), H', W']
+        (channels-last memory); out_fmt="split" (fused pipeline) returns a split-row ops.Feat [B,H',W',C]."""
+        fmt = act_fmt()
+        x = as_nhwc_feat(x, fmt)
+        B = x.t.shape[0]
+        final_fmt = out_fmt if fmt == "split" else "fp32"
         out = None
         col = 0
         n_up = len(self.deblocks)
         for i, block in enumerate(self.blocks):
             mods = list(block)
-            x = run_conv(x, mods[1], mods[2], True, pad=(1, 1))          # ZeroPad2d(1) + conv(pad 0)
+            x = ops.as_feat(run_conv(x, mods[1], mods[2], True, pad=(1, 1)))          # ZeroPad2d(1) + conv(pad 0)
             for k in range(4, len(mods), 3):
-                x = run_conv(x, mods[k], mods[k + 1], True)
+                x = ops.as_feat(run_conv(x, mods[k], mods[k + 1], True))
             j = i - self._upsample_start_idx
             if j >= 0:
                 up, bn = self.deblocks[j][0], self.deblocks[j][1]
+                H_, W_ = x.t.shape[1], x.t.shape[2]
                 if isinstance(up, nn.ConvTranspose2d):
-                    Ho, Wo = x.shape[1] * up.stride[0], x.shape[2] * up.stride[1]
+                    Ho, Wo = H_ * up.stride[0], W_ * up.stride[1]
                 else:
-                    Ho, Wo = x.shape[1] // up.stride[0], x.shape[2] // up.stride[1]
+                    Ho, Wo = H_ // up.stride[0], W_ // up.stride[1]
                 if out is None:
-                    out = torch.empty((B, Ho, Wo, sum(self._num_upsample_filters)), dtype=torch.float32, device=x.device)
+                    out = ops.Feat(torch.empty((B, Ho, Wo, sum(self._num_upsample_filters)), dtype=torch.float32,
+                                               device=x.t.device), final_fmt)
                 c = self._num_upsample_filters[j]
-                run_conv(x, up, bn, True, out=out[..., col:col + c])
+                run_conv(x, up, bn, True, out=out.slice(col, c))
                 col += c
-        if n_up == 0:
-            return x.permute(0, 3, 1, 2)
-        return out.permute(0, 3, 1, 2)
+        res = x if n_up == 0 else out
+        if res.fmt == "split":
+            return res if out_fmt == "split" else res.to_fp32().permute(0, 3, 1, 2)
+        return res.to_fp32().permute(0, 3, 1, 2)

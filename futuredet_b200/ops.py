@@ -232,52 +232,115 @@ def packed_weights(w, separate_offsets=False):
 
 def tc_supported(cin, K):
     """Shapes the tcgen05 arm accepts; anything else must be requested as fp32 explicitly by the caller."""
-    return cin % 8 == 0 and K <= 32
+    return cin % 8 == 0 and (cin % 64 == 0 or 64 % cin == 0) and K <= 32
 
 
-def _conv_desc(x, in_stride, cin, w, scale, shift, residual, relu, out, out_stride, precision, separate=False):
+FMT = {"fp32": 0, "split": 1}
+
+
+class Feat:
+    """A row-matrix operand: `t` is an fp32-typed tensor [..., Ctot] with unit channel stride whose bytes hold
+    either plain fp32 rows (fmt "fp32") or FD_FMT_SPLIT_BF16 rows [Ctot bf16 hi | Ctot bf16 lo] (fmt "split");
+    (c0, c) selects a channel slice.  Split tensors must never be read with torch arithmetic -- use to_fp32()."""
+
+    def __init__(self, t, fmt="fp32", c0=0, c=None):
+        if t.dtype != torch.float32 or not t.is_cuda or t.stride(-1) != 1:
+            raise RuntimeError("Feat needs a CUDA fp32-typed tensor with unit channel stride")
+        self.t, self.fmt, self.c0 = t, fmt, int(c0)
+        self.ctot = int(t.shape[-1])
+        self.c = self.ctot - self.c0 if c is None else int(c)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + self.c0 * (4 if self.fmt == "fp32" else 2)
+
+    @property
+    def row_stride(self):
+        return int(self.t.stride(-2))
+
+    @property
+    def rows(self):
+        return int(self.t.numel() // self.ctot)
+
+    def slice(self, c0, c):
+        return Feat(self.t, self.fmt, self.c0 + c0, c)
+
+    def to_fp32(self, n_dev=None):
+        """fp32 tensor [..., c] of this view (copy through fd_convert_rows when split, plain slice otherwise)."""
+        if self.fmt == "fp32":
+            return self.t[..., self.c0:self.c0 + self.c]
+        lib = L.load()
+        out = torch.empty(self.t.shape[:-1] + (self.c,), dtype=torch.float32, device=self.t.device)
+        rc = lib.fd_convert_rows(C.c_void_p(self.ptr), 1, self.row_stride, self.ctot, _ptr(out), 0, self.c, self.c,
+                                 self.c, _ptr(n_dev), self.rows, _stream())
+        L.check(rc, "fd_convert_rows")
+        return out
+
+
+def as_feat(x):
+    return x if isinstance(x, Feat) else Feat(x)
+
+
+def to_split(x, n_dev=None):
+    """fp32 tensor -> new split-format Feat (API boundary helper)."""
+    lib = L.load()
+    x = as_feat(x)
+    out = torch.empty(x.t.shape[:-1] + (x.c,), dtype=torch.float32, device=x.t.device)
+    rc = lib.fd_convert_rows(C.c_void_p(x.ptr), FMT[x.fmt], x.row_stride, x.ctot, _ptr(out), 1, x.c, x.c, x.c,
+                             _ptr(n_dev), x.rows, _stream())
+    L.check(rc, "fd_convert_rows")
+    return Feat(out, "split")
+
+
+def _conv_desc(x, cin, w, scale, shift, residual, relu, out, precision, separate=False):
     d = L.ConvDesc()
-    d.d_in = x.data_ptr(); d.in_stride = in_stride; d.cin = cin
+    d.d_in = x.ptr; d.in_stride = x.row_stride; d.cin = cin
+    d.in_format = FMT[x.fmt]; d.in_ctot = x.ctot
     d.d_w = w.data_ptr(); d.K, _, d.cout = w.shape
     if (L.PRECISIONS[precision] if isinstance(precision, str) else int(precision)) != L.PREC_FP32:
         d.d_w_packed = packed_weights(w, separate).data_ptr()
     d.d_scale = scale.data_ptr() if scale is not None else None
     d.d_shift = shift.data_ptr() if shift is not None else None
     if residual is not None:
-        d.d_residual = residual.data_ptr(); d.res_stride = residual.stride(0)
+        d.d_residual = residual.ptr; d.res_stride = residual.row_stride
+        d.res_format = FMT[residual.fmt]; d.res_ctot = residual.ctot
     d.relu = int(bool(relu))
-    d.d_out = out.data_ptr(); d.out_stride = out_stride
+    d.d_out = out.ptr; d.out_stride = out.row_stride
+    d.out_format = FMT[out.fmt]; d.out_ctot = out.ctot
     d.precision = L.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
     return d
 
 
 def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out=None, precision="fp32",
-                bev=None):
+                bev=None, out_fmt="fp32"):
     """out[o] = act((sum_k x[nbr[k,o]] @ w[k]) * scale + shift (+ residual[o])).
 
-    x [n_in_cap, >=Cin] fp32 rows, w [K, Cin, Cout] fp32, rb: Rulebook.  With bev=(B,D,H,W) the result
-    is written straight into a zero-initialised channels-last BEV tensor [B,H,W,Cout*D]
-    (SparseConvTensor.dense().view(N, C*D, H, W) of scn.py:165-168) which is returned.
+    x / residual / out: torch fp32 tensors or Feat views (fp32 or split rows); w [K, Cin, Cout] fp32; rb: Rulebook.
+    With bev=(B,D,H,W) the result goes straight into a zero-initialised channels-last BEV buffer [B,H,W,Cout*D]
+    (SparseConvTensor.dense().view(N, C*D, H, W) of scn.py:165-168).  Returns a tensor for out_fmt "fp32",
+    a Feat for "split".
     """
     lib = L.load()
     _req(w, torch.float32, "w")
     K, cin, cout = w.shape
     if K != rb.K:
         raise RuntimeError("weight has %d kernel offsets, rulebook has %d" % (K, rb.K))
-    if x.dtype != torch.float32 or not x.is_cuda or x.stride(1) != 1:
-        raise RuntimeError("x must be CUDA fp32 with unit channel stride")
+    x = as_feat(x)
+    residual = as_feat(residual) if residual is not None else None
     n_cap = rb.n_out_cap
     if bev is not None:
         B, D, H, Wd = bev
         if out is None:
-            out = torch.zeros((B, H, Wd, cout * D), dtype=torch.float32, device=x.device)
-        d = _conv_desc(x, x.stride(0), cin, w, scale, shift, None, relu, out, cout * D, precision)
+            out = Feat(torch.zeros((B, H, Wd, cout * D), dtype=torch.float32, device=x.t.device), out_fmt)
+        out = as_feat(out)
+        d = _conv_desc(x, cin, w, scale, shift, None, relu, out, precision)
         d.out_map = L.OUTMAP_BEV
         d.d_out_coords4 = rb.out_coords.data_ptr(); d.bevD, d.bevH, d.bevW = D, H, Wd
     else:
         if out is None:
-            out = torch.empty((max(n_cap, 1), cout), dtype=torch.float32, device=x.device)
-        d = _conv_desc(x, x.stride(0), cin, w, scale, shift, residual, relu, out, out.stride(0), precision)
+            out = Feat(torch.empty((max(n_cap, 1), cout), dtype=torch.float32, device=x.t.device), out_fmt)
+        out = as_feat(out)
+        d = _conv_desc(x, cin, w, scale, shift, residual, relu, out, precision)
         d.out_map = L.OUTMAP_IDENTITY
     d.mode = L.GATHER_TABLE
     d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
@@ -286,37 +349,50 @@ def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out
     e0 = _prof_begin()
     L.check(lib.fd_conv_forward(C.byref(d), _stream()), "fd_conv_forward(sparse)")
     _prof_end(e0, "sparse3d_c%d" % cout, lambda: 2.0 * float(rb.pair_num.sum().item()) * cin * cout)
-    return out
+    return out.t if out.fmt == "fp32" and out.c0 == 0 and out.c == out.ctot else out
 
 
 def conv2d_nhwc(x, w, ksize, stride, padding, scale=None, shift=None, relu=False, out=None, residual=None,
-                precision="fp32", transposed=False):
+                precision="fp32", transposed=False, out_fmt="fp32"):
     """Dense 2-D convolution on channels-last activations.
 
-    x: [B,H,W,Cs] fp32 CUDA view with unit channel stride (a channel slice of a wider buffer is fine),
-    w: [kh*kw, Cin, Cout].  `out` may likewise be a channel slice [B,Ho,Wo,Cout] of a wider buffer (this is
-    how torch.cat(ups, dim=1) of rpn.py:156-157 is fused away).  transposed=True: ConvTranspose2d, kernel==stride.
+    x: [B,H,W,Cs] fp32 tensor (channel-slice views allowed) or Feat; w: [kh*kw, Cin, Cout].  `out` may be a
+    channel slice of a wider buffer (tensor view or Feat) -- this is how torch.cat(ups, dim=1) of rpn.py:156-157 is
+    fused away.  transposed=True: ConvTranspose2d with kernel == stride.  Returns a tensor for fp32 outputs given
+    as tensors/None, else a Feat.
     """
     lib = L.load()
     _req(w, torch.float32, "w")
     K, cin, cout = w.shape
-    B, H, Wd, _ = x.shape
+    out_was_tensor = out is None or isinstance(out, torch.Tensor)
+    if isinstance(x, torch.Tensor) and x.dim() == 4 and (x.storage_offset() or x.shape[-1] != x.stride(-2)):
+        # channel-slice tensor view of a wider channels-last buffer
+        base = x.as_strided((x.shape[0], x.shape[1], x.shape[2], x.stride(2)), (x.stride(0), x.stride(1), x.stride(2), 1),
+                            x.storage_offset() - x.storage_offset() % x.stride(2))
+        x = Feat(base, "fp32", x.storage_offset() % x.stride(2), x.shape[3])
+    x = as_feat(x)
+    B, H, Wd = x.t.shape[0], x.t.shape[1], x.t.shape[2]
     kh, kw = ksize
     sh, sw = stride
     ph, pw = padding
-    if x.stride(3) != 1 or x.stride(2) * Wd != x.stride(1) or x.stride(1) * H != x.stride(0):
-        raise RuntimeError("x must be a channels-last [B,H,W,C] view with dense pixels")
+    if x.t.stride(2) * Wd != x.t.stride(1) or x.t.stride(1) * H != x.t.stride(0):
+        raise RuntimeError("x must be a channels-last [B,H,W,C] buffer with dense pixels")
     if transposed:
         Ho, Wo = H * sh, Wd * sw
     else:
         Ho, Wo = (H + 2 * ph - kh) // sh + 1, (Wd + 2 * pw - kw) // sw + 1
     if out is None:
-        out = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x.device)
-    if out.stride(3) != 1 or out.stride(2) * Wo != out.stride(1) or out.stride(1) * Ho != out.stride(0):
-        raise RuntimeError("out must be a channels-last [B,H,W,C] view with dense pixels")
-    res2 = residual.reshape(-1, residual.shape[-1]) if residual is not None else None
-    d = _conv_desc(x, x.stride(2), cin, w, scale, shift, res2, relu, out, out.stride(2), precision,
-                   separate=transposed)
+        out = Feat(torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x.t.device), out_fmt)
+    elif isinstance(out, torch.Tensor) and (out.storage_offset() or out.shape[-1] != out.stride(-2)):
+        base = out.as_strided((out.shape[0], out.shape[1], out.shape[2], out.stride(2)),
+                              (out.stride(0), out.stride(1), out.stride(2), 1),
+                              out.storage_offset() - out.storage_offset() % out.stride(2))
+        out = Feat(base, "fp32", out.storage_offset() % out.stride(2), out.shape[3])
+    out = as_feat(out)
+    if out.t.stride(2) * Wo != out.t.stride(1) or out.t.stride(1) * Ho != out.t.stride(0) or out.t.shape[1] != Ho:
+        raise RuntimeError("out must be a channels-last [B,Ho,Wo,C] buffer with dense pixels")
+    residual = as_feat(residual) if residual is not None else None
+    d = _conv_desc(x, cin, w, scale, shift, residual, relu, out, precision, separate=transposed)
     d.mode = L.GATHER_CONVT2D if transposed else L.GATHER_CONV2D
     d.B, d.Hin, d.Win, d.Hout, d.Wout = B, H, Wd, Ho, Wo
     d.kh, d.kw, d.sh, d.sw, d.ph, d.pw = kh, kw, sh, sw, ph, pw
@@ -326,12 +402,16 @@ def conv2d_nhwc(x, w, ksize, stride, padding, scale=None, shift=None, relu=False
     e0 = _prof_begin()
     L.check(lib.fd_conv_forward(C.byref(d), _stream()), "fd_conv_forward(conv2d)")
     _prof_end(e0, "dense2d", 2.0 * d.n_out_cap * cin * cout * (1 if transposed else K), K if transposed else 1)
+    if out_was_tensor and out.fmt == "fp32":
+        return out.t[..., out.c0:out.c0 + out.c]
     return out
 
 
 def sparse_to_dense(features, coords, n_dev, n_cap, batch_size, shape):
     """SparseConvTensor.dense(): [N,C] rows -> zero-filled NCDHW tensor."""
     lib = L.load()
+    if isinstance(features, Feat):
+        features = features.to_fp32(n_dev)
     Cc = features.shape[1]
     D, H, Wd = [int(s) for s in shape]
     dense = torch.empty((batch_size, Cc, D, H, Wd), dtype=torch.float32, device=features.device)

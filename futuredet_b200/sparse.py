@@ -29,7 +29,8 @@ class SparseConvTensor:
     def __init__(self, features, indices, spatial_shape, batch_size, n_dev=None, n_cap=None):
         if indices.dtype != torch.int32:
             indices = indices.int()
-        self.features = features
+        self._feat = ops.as_feat(features)     # ops.Feat: fp32 rows, or split bf16 hi/lo rows between tensor-core layers
+        self._fp32 = None
         self.indices = indices.contiguous()
         self.spatial_shape = [int(s) for s in spatial_shape]
         self.batch_size = int(batch_size)
@@ -39,6 +40,20 @@ class SparseConvTensor:
         self.n_dev = n_dev
         self.indice_dict = {}     # indice_key -> (Rulebook, out spatial shape)
         self._index = None        # CoordIndex of self.indices
+
+    @property
+    def features(self):
+        """[n_cap, C] fp32 features (converted on demand when the tensor-core pipeline holds them split)."""
+        if self._feat.fmt == "fp32":
+            return self._feat.to_fp32()
+        if self._fp32 is None:
+            self._fp32 = self._feat.to_fp32(self.n_dev)
+        return self._fp32
+
+    @features.setter
+    def features(self, value):
+        self._feat = ops.as_feat(value)
+        self._fp32 = None
 
     def coord_index(self):
         if self._index is None:
@@ -58,7 +73,7 @@ class SparseConvTensor:
 
     def dense(self, channels_first=True):
         """[B, C, D, H, W] (zeros at inactive sites), as spconv's `.dense()` (scn.py:165)."""
-        d = ops.sparse_to_dense(self.features, self.indices, self.n_dev, self.n_cap, self.batch_size,
+        d = ops.sparse_to_dense(self._feat, self.indices, self.n_dev, self.n_cap, self.batch_size,
                                 self.spatial_shape)
         return d if channels_first else d.permute(0, 2, 3, 4, 1).contiguous()
 
@@ -102,8 +117,17 @@ class _SparseConvBase(SparseModule):
                 b = 1.0 / math.sqrt(fan_in)
                 self.bias.uniform_(-b, b)
 
-    def weight_kio(self):
-        return self.weight.detach().reshape(-1, self.in_channels, self.out_channels)
+    def weight_kio(self, cin_pad=None):
+        w = self.weight.detach().reshape(-1, self.in_channels, self.out_channels)
+        if cin_pad is None or cin_pad == self.in_channels:
+            return w
+        key = (self.weight.data_ptr(), self.weight._version, cin_pad)      # zero rows for the padded input channels
+        cache = self.__dict__.setdefault("_wpad_cache", {})
+        if cache.get("k") != key:
+            wp = torch.zeros((w.shape[0], cin_pad, self.out_channels), dtype=w.dtype, device=w.device)
+            wp[:, :self.in_channels] = w
+            cache["k"], cache["v"] = key, wp
+        return cache["v"]
 
     def rulebook(self, x):
         cached = x.find_indice_pair(self.indice_key)
@@ -119,18 +143,28 @@ class _SparseConvBase(SparseModule):
             x.indice_dict[self.indice_key] = rb
         return rb
 
-    def forward(self, x, bn=None, residual=None, relu=False, bev=False):
-        """out = act(bn(conv(x) [+bias]) [+ residual]); `bn` is an eval-mode BatchNorm1d folded into the epilogue."""
+    def forward(self, x, bn=None, residual=None, relu=False, bev=False, out_fmt=None):
+        """out = act(bn(conv(x) [+bias]) [+ residual]); `bn` is an eval-mode BatchNorm1d folded into the epilogue.
+        Tensor-core precisions keep activations in the split bf16 hi/lo row format between layers."""
         rb = self.rulebook(x)
         scale, shift = folded_epilogue(self, bn)
         prec = self.precision or DEFAULT_PRECISION
-        if prec != "fp32" and not ops.tc_supported(self.in_channels, rb.K):
-            prec = "fp32"      # e.g. the 5-channel stem: no tensor-core tile shape; exact fp32 CUDA-core arm
+        xin = x._feat
+        w = self.weight_kio()
+        if prec != "fp32" and self.in_channels % 8 != 0:
+            cin_pad = (self.in_channels + 7) // 8 * 8
+            if xin.fmt == "fp32" and xin.ctot >= cin_pad and xin.c0 == 0:
+                # e.g. the 5-channel stem fed by the fused voxelizer (rows zero-padded to 8 channels)
+                xin, w = ops.Feat(xin.t, "fp32", 0, cin_pad), self.weight_kio(cin_pad)
+            else:
+                prec = "fp32"       # no tensor-core tile shape for this Cin: exact fp32 CUDA-core arm, explicitly
+        if out_fmt is None:
+            out_fmt = "fp32" if prec == "fp32" else "split"
         if bev:
             D, H, W = rb.out_shape
-            return ops.sparse_conv(x.features, self.weight_kio(), rb, scale, shift, None, relu, precision=prec,
-                                   bev=(x.batch_size, D, H, W))
-        y = ops.sparse_conv(x.features, self.weight_kio(), rb, scale, shift, residual, relu, precision=prec)
+            return ops.sparse_conv(xin, w, rb, scale, shift, None, relu, precision=prec,
+                                   bev=(x.batch_size, D, H, W), out_fmt=out_fmt)
+        y = ops.sparse_conv(xin, w, rb, scale, shift, residual, relu, precision=prec, out_fmt=out_fmt)
         if self.subm:
             return x._like(y)
         return x._like(y, rb.out_coords, rb.out_shape, rb.n_out_dev, rb.n_out_cap)
@@ -200,7 +234,7 @@ class SparseSequential(SparseModule):
     def add(self, module, name=None):
         self.add_module(name or str(len(self._modules)), module)
 
-    def forward(self, x, bev_last=False):
+    def forward(self, x, bev_last=False, out_fmt=None):
         mods = list(self._modules.values())
         i = 0
         while i < len(mods):
@@ -215,7 +249,8 @@ class SparseSequential(SparseModule):
                 if j < len(mods) and isinstance(mods[j], nn.ReLU):
                     relu = True
                     j += 1
-                x = m(x, bn=bn, relu=relu, bev=(bev_last and j == len(mods)))
+                last = j == len(mods)
+                x = m(x, bn=bn, relu=relu, bev=(bev_last and last), out_fmt=out_fmt if last else None)
                 i = j
             elif isinstance(m, SparseModule):
                 x = m(x)

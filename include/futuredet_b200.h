@@ -122,18 +122,29 @@ int fd_rulebook_to_pairs(const int32_t* d_nbr, int nbr_stride, const int32_t* d_
  *     y = act( (sum_k in[nbr(o,k)] @ W[k]) * scale + shift (+ residual) )
  * Weights are [K, Cin, Cout] fp32 (spconv-1.x layout [kD,kH,kW,Cin,Cout]).
  */
+/* Row formats.  FD_FMT_FP32: row = C_tot fp32.  FD_FMT_SPLIT_BF16: row = [C_tot bf16 "hi"][C_tot bf16 "lo"]
+ * with value = hi + lo (hi = bf16_rn(x), lo = bf16_rn(x - hi)); same 4*C_tot bytes per row as fp32, so a
+ * buffer allocated for one format can hold the other.  It is the inter-layer format of the tensor-core arm:
+ * the producing kernel's epilogue splits once, consuming kernels gather both planes with cp.async and feed
+ * the bf16 tensor cores with no conversion work.  `*_ctot` = channels per row of the underlying buffer
+ * (locates the lo plane; d_in/d_out/d_residual may point at a channel slice).  Strides stay in 4-byte units. */
+enum { FD_FMT_FP32 = 0, FD_FMT_SPLIT_BF16 = 1 };
+
 typedef struct fd_conv_desc {
   /* input rows */
-  const float*   d_in;        int32_t in_stride;  int32_t cin;
+  const void*    d_in;        int32_t in_stride;  int32_t cin;
+  int32_t        in_format;   int32_t in_ctot;
   /* weights / epilogue vectors */
   const float*   d_w;         int32_t cout;       int32_t K;
   const void*    d_w_packed;  /* fd_conv_pack_weights output; required for FD_PREC_BF16X3 / FD_PREC_BF16 */
   const float*   d_scale;     /* [cout] or NULL (=1) */
   const float*   d_shift;     /* [cout] or NULL (=0) */
-  const float*   d_residual;  int32_t res_stride; /* NULL: none */
+  const void*    d_residual;  int32_t res_stride; /* NULL: none */
+  int32_t        res_format;  int32_t res_ctot;
   int32_t        relu;
   /* output rows */
-  float*         d_out;       int32_t out_stride;
+  void*          d_out;       int32_t out_stride;
+  int32_t        out_format;  int32_t out_ctot;
   const int32_t* d_n_out;     /* device row count, or NULL -> n_out_cap rows */
   int32_t        n_out_cap;
   /* gather mode */
@@ -166,6 +177,12 @@ int fd_conv_pack_weights(const float* d_w, int K, int cin, int cout, void* d_pac
 int fd_sparse_to_dense_ncdhw(const float* d_feat, int feat_stride, int C, const int32_t* d_coords4,
                              const int32_t* d_n, int n_cap, int B, int D, int H, int W,
                              float* d_dense, void* stream);
+
+/* Convert a row matrix between FD_FMT_FP32 and FD_FMT_SPLIT_BF16 (API boundaries, tests).
+ * rows from d_n (device, may be NULL -> n_cap); src/dst may be channel slices (ctot locates lo planes). */
+int fd_convert_rows(const void* d_src, int src_format, int src_stride, int src_ctot, void* d_dst,
+                    int dst_format, int dst_stride, int dst_ctot, int C, const int32_t* d_n, int64_t n_cap,
+                    void* stream);
 
 /* small helpers used by the host layer */
 int fd_fill_i32(int32_t* d_ptr, int64_t n, int32_t value, void* stream);

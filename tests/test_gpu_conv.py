@@ -43,7 +43,7 @@ def test_subm_conv_fused_epilogue(cuda, prec, tol, cin, cout):
     xg = torch.zeros((cap, cin), device=cuda); xg[:n] = x.to(cuda)
     rg = torch.zeros((cap, cout), device=cuda); rg[:n] = res.to(cuda)
     if prec != "fp32" and not ops.tc_supported(cin, 27):
-        with pytest.raises(RuntimeError, match="multiple of 8"):      # no silent fallback in the ABI
+        with pytest.raises(RuntimeError, match="tensor-core arm needs Cin"):      # no silent fallback in the ABI
             ops.sparse_conv(xg, w.to(cuda), rb, precision=prec)
         return
     y = ops.sparse_conv(xg, w.to(cuda), rb, scale.to(cuda), shift.to(cuda), rg, True, precision=prec)
@@ -92,6 +92,10 @@ def test_conv2d_nhwc(cuda, prec, tol, cin, cout, k, s, p, hw):
     want = F.relu(F.conv2d(x, w, None, stride=s, padding=p) * scale[None, :, None, None] + shift[None, :, None, None])
     wk = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout).contiguous().to(cuda)
     xg = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+    if prec != "fp32" and not ops.tc_supported(cin, k * k):
+        with pytest.raises(RuntimeError, match="tensor-core arm needs Cin"):
+            ops.conv2d_nhwc(xg, wk, (k, k), (s, s), (p, p), precision=prec)
+        return
     y = ops.conv2d_nhwc(xg, wk, (k, k), (s, s), (p, p), scale.to(cuda), shift.to(cuda), True, precision=prec)
     torch.testing.assert_close(y.permute(0, 3, 1, 2).cpu(), want, rtol=tol, atol=tol)
 
@@ -111,3 +115,61 @@ def test_channel_slices_and_conv_transpose(cuda, prec, tol):
                     transposed=True)
     torch.testing.assert_close(out[..., 16:64].permute(0, 3, 1, 2).cpu(), want, rtol=tol, atol=tol)
     assert (out[..., :16] == -7).all() and (out[..., 64:] == -7).all()                  # neighbours untouched
+
+
+def test_split_row_format_round_trip(cuda):
+    """FD_FMT_SPLIT_BF16 rows: hi + lo reproduces fp32 to ~2^-17 relative; channel slices address both planes."""
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn((1000, 48), generator=g) * 10 ** torch.randint(-3, 4, (1000, 48), generator=g).float()).to(cuda)
+    s = ops.to_split(x)
+    back = s.to_fp32()
+    rel = ((back - x).abs() / x.abs().clamp_min(1e-30)).max().item()
+    assert rel < 2 ** -16
+    torch.testing.assert_close(s.slice(16, 8).to_fp32(), back[:, 16:24], rtol=0, atol=0)
+    assert ops.to_split(torch.zeros((4, 8), device=cuda)).to_fp32().abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 32), (64, 64), (64, 128), (128, 128)])
+def test_subm_conv_split_format_pipeline(cuda, cin, cout):
+    """Tensor-core arm with split bf16 hi/lo rows for input, residual and output (the inter-layer format),
+    chained twice, against the fp32 oracle."""
+    rng = np.random.default_rng(cin + cout)
+    shape, B = [9, 24, 24], 2
+    c = random_sites(rng, B, shape, 3500)
+    n = len(c)
+    x = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32))
+    w1 = torch.from_numpy((rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32))
+    w2 = torch.from_numpy((rng.standard_normal((27, cout, cout)) / np.sqrt(27 * cout)).astype(np.float32))
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32))
+    shift = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+    nbr = S.subm_rulebook(c, shape, [3, 3, 3])
+    y1 = F.relu(S.indice_conv(x, w1, nbr, n) * scale + shift)
+    want = F.relu(S.indice_conv(y1, w2, nbr, n) * scale + shift + y1)
+    cap = n + 77
+    ct = torch.zeros((cap, 4), dtype=torch.int32, device=cuda); ct[:n] = torch.from_numpy(c).to(cuda)
+    nd = torch.tensor([n], dtype=torch.int32, device=cuda)
+    rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3])
+    xg = torch.zeros((cap, cin), device=cuda); xg[:n] = x.to(cuda)
+    xs = ops.to_split(xg)
+    g1 = ops.sparse_conv(xs, w1.to(cuda), rb, scale.to(cuda), shift.to(cuda), None, True, precision="bf16x3", out_fmt="split")
+    assert isinstance(g1, ops.Feat) and g1.fmt == "split"
+    torch.testing.assert_close(g1.to_fp32()[:n].cpu(), y1, rtol=3e-4, atol=3e-4)
+    g2 = ops.sparse_conv(g1, w2.to(cuda), rb, scale.to(cuda), shift.to(cuda), g1, True, precision="bf16x3", out_fmt="fp32")
+    torch.testing.assert_close(g2[:n].cpu(), want, rtol=5e-4, atol=5e-4)
+    # the fp32 CUDA-core arm reads the same split rows (mixed pipelines stay well-defined)
+    g3 = ops.sparse_conv(g1, w2.to(cuda), rb, scale.to(cuda), shift.to(cuda), g1, True, precision="fp32", out_fmt="split")
+    torch.testing.assert_close(g3.to_fp32()[:n].cpu(), want, rtol=5e-4, atol=5e-4)
+
+
+def test_dense_conv_split_format_and_slices(cuda):
+    g = torch.Generator().manual_seed(3)
+    B, H, W, cin, cout = 2, 14, 13, 64, 32
+    x = torch.randn((B, cin, H, W), generator=g)
+    w = torch.randn((cout, cin, 3, 3), generator=g) / np.sqrt(cin * 9)
+    want = F.relu(F.conv2d(x, w, None, padding=1))
+    wk = w.permute(2, 3, 1, 0).reshape(9, cin, cout).contiguous().to(cuda)
+    xs = ops.to_split(x.permute(0, 2, 3, 1).contiguous().to(cuda))
+    wide = ops.Feat(torch.zeros((B, H, W, 96), device=cuda), "split")
+    ops.conv2d_nhwc(xs, wk, (3, 3), (1, 1), (1, 1), relu=True, out=wide.slice(32, cout), precision="bf16x3")
+    torch.testing.assert_close(wide.slice(32, cout).to_fp32().permute(0, 3, 1, 2).cpu(), want, rtol=3e-4, atol=3e-4)
+    assert wide.slice(0, 32).to_fp32().abs().max().item() == 0 and wide.slice(64, 32).to_fp32().abs().max().item() == 0
