@@ -63,7 +63,7 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
   a.relu = d->relu;
   a.out = (float*)d->d_out; a.out_stride = d->out_stride;
   a.d_n = d->d_n_out; a.n_cap = d->n_out_cap;
-  a.mode = d->mode; a.nbr = d->d_nbr; a.nbr_stride = d->nbr_stride;
+  a.mode = d->mode; a.nbr = d->d_nbr; a.nbr_stride = d->nbr_stride; a.tile_mask = d->d_tile_mask;
   a.Hin = d->Hin; a.Win = d->Win; a.Hout = d->Hout; a.Wout = d->Wout;
   a.kh = d->kh; a.kw = d->kw; a.sh = d->sh; a.sw = d->sw; a.ph = d->ph; a.pw = d->pw;
   a.out_map = d->out_map;

@@ -18,6 +18,7 @@ struct ConvArgs {
   const int32_t* d_n; int n_cap;
   int mode;
   const int32_t* nbr; int nbr_stride;
+  const uint32_t* tile_mask;
   int Hin, Win, Hout, Wout, kh, kw, sh, sw, ph, pw;
   int out_map;
   const int4* out_coords; int bevD, bevH, bevW;

@@ -2,23 +2,27 @@
 //
 //   out[o, :] = act( (sum_k in[nbr(o,k), :] @ W[k]) * scale + shift (+ residual[o, :]) )
 //
-// GEMM view: M = output rows (active sites / pixels), N = Cout, K = (kernel offsets x Cin) flattened.
-// One CTA owns a 128-row x NT-column output tile; the fp32 accumulator lives in TMEM (double buffered),
-// operands are staged in shared memory in the UMMA canonical K-major SWIZZLE_128B layout
-// (64 bf16 = 128 B per row, 16-byte chunk index XOR (row & 7)), 3-4 stage mbarrier ring.
+// GEMM view: M = output rows (active sites / pixels), N = Cout, K = (kernel offsets x Cin) flattened into
+// 64-element "K stages".  The kernel is L2->SM bandwidth bound (measured: same time with 1/3 of the MMAs), so
+// the schedule is organised around bytes moved:
+//   * a work unit is a SUPER-TILE of T consecutive 128-row M tiles x one NT-column N tile; for every K stage the
+//     weight tile B(ks) is fetched ONCE (one cp.async.bulk of a pre-swizzled block) and reused by the T M tiles,
+//     whose fp32 accumulators all live in TMEM (2 buffers x T x NT columns <= 512);
+//   * activations travel between layers as FD_FMT_SPLIT_BF16 rows (bf16 hi | bf16 lo), so the A operand is
+//     gathered with plain 16-byte cp.async copies (zero-filled where the rulebook has no neighbour) straight into
+//     the UMMA canonical K-major SWIZZLE_128B layout -- no register staging, no conversion work, and the
+//     hardware arrives on the stage's mbarrier when the bytes land (cp.async.mbarrier.arrive.noinc);
+//   * kernel offsets that are empty for the whole super-tile are skipped (per-tile masks from the rulebook).
 //
-// Warp roles (288 threads):
-//   warps 0-3  producers : gather 128 input rows per stage through the rulebook (or the dense 2-D index
-//                          arithmetic), split every fp32 into bf16 hi + bf16 lo on the fly and store both
-//                          planes swizzled; cp.async the pre-packed bf16 hi/lo weight tile; kernel offsets
-//                          with no neighbour in the whole tile are skipped.
-//   warp  4    MMA issuer: one lane issues tcgen05.mma (M=128, N=NT, K=16, kind::f16, bf16 x bf16 -> fp32):
-//                          D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi   (3-term split, ~2^-16 relative error,
-//                          i.e. fp32-class results on the bf16 tensor pipe); tcgen05.commit releases stages.
-//   warps 5-8  epilogue  : tcgen05.ld the accumulator, fused BN(eval)/bias, residual, ReLU, mapped store.
-//
-// fp32 activations stay fp32 in HBM (the reference's interface); precision is a property of the kernel.
+// Warp roles (416 threads):
+//   warps 0-7   producers, split into 4 groups that fill different A stages concurrently (A ring of 4-5 x 32 KB);
+//               the group that opens a K stage also issues the B bulk copy (B ring of 2 slots);
+//   warp  8     MMA issuer: one lane issues tcgen05.mma (M=128, N=NT, K=16, kind::f16, bf16 x bf16 -> fp32):
+//               D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (3-term split, ~2^-16 relative error: fp32-class results
+//               on the bf16 tensor pipe); tcgen05.commit releases A / B slots and publishes the accumulators;
+//   warps 9-12  epilogue: tcgen05.ld, fused BN(eval)/bias, residual, ReLU, split once into bf16 hi/lo, store.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "conv_common.cuh"
 
@@ -27,13 +31,16 @@ namespace fd {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements per stage row (128 bytes, one swizzle atom)
 constexpr int TC_MAXK = 32;               // max kernel offsets (27 for 3x3x3)
+constexpr int TC_DENSE_MAXK = 9;          // dense 2-D mode: up to 3x3 taps (row indices cached in shared memory)
+constexpr int TC_GROUPS = 4;              // producer groups (each fills whole A stages on its own)
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
-constexpr int TC_THREADS = TC_PRODUCERS + 32 + 128;   // producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;         // warp 8
+constexpr int TC_B_WARP = TC_PRODUCER_WARPS + 5;       // warp 13 (warps 9-12: epilogue, TMEM lane quarters 1,2,3,0)
+constexpr int TC_THREADS = TC_PRODUCERS + 32 + 128 + 32;
+constexpr int TC_SS_MAX = 512;                         // folded BN scale / shift cached in shared memory up to this Cout
 constexpr int TC_A_PLANE = TC_BM * 128;   // bytes of one A plane (hi or lo) per stage
 
-__host__ __device__ constexpr int tc_stage_bytes(int NT) { return 2 * TC_A_PLANE + 2 * NT * 128; }
-__host__ __device__ constexpr int tc_num_stages(int NT) { return NT >= 128 ? 3 : 4; }
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -44,16 +51,155 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol bug must never hang the GPU (a hung box is a lost box).  After ~1 s of spinning the
+// waiter reports which barrier starved, raises g_tc_abort and gives up; every other waiter then falls through
+// too, the kernel drains (its output is garbage) and conv_forward_tc() turns the flag into an error.
+__device__ int g_tc_abort = 0;
+// FD_TC_DEBUG & 32: block 0 records clock64() timestamps of its pipeline events (perf triage only)
+constexpr int TC_TRACE_N = 8192;
+__device__ long long g_tc_trace[4][TC_TRACE_N];
+#define TC_TRACE(role, i, v) do { if ((t.dbg & 32) && blockIdx.x == 0 && (i) < TC_TRACE_N) g_tc_trace[role][i] = (v); } while (0)
+// `backoff_ns` > 0: the waiter sleeps between polls.  Twelve of the thirteen warps of a CTA spend most of their
+// life waiting; polling in a tight loop they would steal the issue slots of the one warp that feeds the tensor core
+// (measured: 2.3 M + 3.6 M spin iterations per launch and an MMA warp running at a third of its speed).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0, uint32_t backoff_ns = 0,
+                                          uint32_t hint_ns = 0x989680u) {
   uint32_t done;
+  long long t0 = 0;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");   // suspend-time hint (ns)
+    if (!done) {
+      if (backoff_ns) __nanosleep(backoff_ns);
+      if ((++spins & 0x3ff) == 0) {
+        if (*(volatile int*)&g_tc_abort) return;
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000LL) {
+          if (atomicAdd(&g_tc_abort, 1) < 8)
+            printf("futuredet_b200: mbarrier wait timed out (tag %d, block %d, thread %d, bar 0x%x, parity %u)\n", tag,
+                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+          return;
+        }
+      }
+    }
   } while (!done);
+}
+// Non-blocking probe (mbarrier.test_wait): issued one stage ahead so that its ~350-cycle latency overlaps the MMA
+// issue of the current stage; the result is only consumed an iteration later.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+// One A stage of the MMA role as a single asm block, so that the instruction order is exactly
+//   [probe of the NEXT stage's full barrier] [all tcgen05.mma of THIS stage] [tcgen05.commit] [read probe result]
+// and the ~350-cycle latency of the barrier probe is hidden behind the MMA issue instead of heading every stage.
+// MODE 0: single pass (A_hi*B_hi); 1: fused  A_hi*[B_hi|B_lo] (width 2N, idesc2) + A_lo*B_hi; 2: three products.
+// Every lane executes it with identical (warp-uniform) operands; the elected lane issues mma / commit.
+#define FD_UMMA_STAGE_OPERANDS                                                                                      \
+  : "=r"(ready)                                                                                                     \
+  : "r"(tmem_d), "l"(dA_hi), "l"(dA_lo), "l"(dB_hi), "l"(dB_lo), "r"(idesc), "r"(idesc2), "r"(acc0), "r"(next_bar), \
+    "r"(next_parity), "r"(commit_bar)                                                                               \
+  : "memory"
+template <int MODE>
+__device__ __forceinline__ uint32_t umma_stage(uint32_t tmem_d, uint64_t dA_hi, uint64_t dA_lo, uint64_t dB_hi,
+                                               uint64_t dB_lo, uint32_t idesc, uint32_t idesc2, uint32_t acc0,
+                                               uint32_t next_bar, uint32_t next_parity, uint32_t commit_bar) {
+  uint32_t ready;
+  if constexpr (MODE == 0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pn, pa, q, one;\n\t"
+        ".reg .b64 ah, al, bh, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pn, [%9], %10;\n\t"
+        "setp.ne.b32 pa, %8, 0;\n\t"
+        "setp.eq.b32 one, 0, 0;\n\t"
+        "add.u64 ah, %2, 0; add.u64 al, %3, 0; add.u64 bh, %4, 0; add.u64 bl, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, pa;\n\t"
+        "add.u64 ah, %2, 2; add.u64 al, %3, 2; add.u64 bh, %4, 2; add.u64 bl, %5, 2;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
+        "add.u64 ah, %2, 4; add.u64 al, %3, 4; add.u64 bh, %4, 4; add.u64 bl, %5, 4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
+        "add.u64 ah, %2, 6; add.u64 al, %3, 6; add.u64 bh, %4, 6; add.u64 bl, %5, 6;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+        "selp.u32 %0, 1, 0, pn;\n\t"
+        "}"
+        FD_UMMA_STAGE_OPERANDS);
+  } else if constexpr (MODE == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pn, pa, q, one;\n\t"
+        ".reg .b64 ah, al, bh, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pn, [%9], %10;\n\t"
+        "setp.ne.b32 pa, %8, 0;\n\t"
+        "setp.eq.b32 one, 0, 0;\n\t"
+        "add.u64 ah, %2, 0; add.u64 al, %3, 0; add.u64 bh, %4, 0; add.u64 bl, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %7, pa;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+        "add.u64 ah, %2, 2; add.u64 al, %3, 2; add.u64 bh, %4, 2; add.u64 bl, %5, 2;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %7, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+        "add.u64 ah, %2, 4; add.u64 al, %3, 4; add.u64 bh, %4, 4; add.u64 bl, %5, 4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %7, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+        "add.u64 ah, %2, 6; add.u64 al, %3, 6; add.u64 bh, %4, 6; add.u64 bl, %5, 6;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %7, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+        "selp.u32 %0, 1, 0, pn;\n\t"
+        "}"
+        FD_UMMA_STAGE_OPERANDS);
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pn, pa, q, one;\n\t"
+        ".reg .b64 ah, al, bh, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pn, [%9], %10;\n\t"
+        "setp.ne.b32 pa, %8, 0;\n\t"
+        "setp.eq.b32 one, 0, 0;\n\t"
+        "add.u64 ah, %2, 0; add.u64 al, %3, 0; add.u64 bh, %4, 0; add.u64 bl, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, pa;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+        "add.u64 ah, %2, 2; add.u64 al, %3, 2; add.u64 bh, %4, 2; add.u64 bl, %5, 2;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+        "add.u64 ah, %2, 4; add.u64 al, %3, 4; add.u64 bh, %4, 4; add.u64 bl, %5, 4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+        "add.u64 ah, %2, 6; add.u64 al, %3, 6; add.u64 bh, %4, 6; add.u64 bl, %5, 6;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+        "selp.u32 %0, 1, 0, pn;\n\t"
+        "}"
+        FD_UMMA_STAGE_OPERANDS);
+  }
+  return ready;
+}
+// Warp-level wait: ONE lane polls, the rest of the warp parks at __syncwarp().  32 lanes polling the same mbarrier
+// word serialise in the shared-memory pipe (measured: ~450 cycles per already-completed wait vs ~100).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int tag = 0, uint32_t backoff_ns = 0) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, tag, backoff_ns);
+  __syncwarp();
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -77,6 +223,9 @@ __device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void* src, uin
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -120,6 +269,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// Warp-uniform variants: every lane of the (converged) MMA warp executes them with identical operands so the
+// compiler keeps descriptors in uniform registers; one elected lane issues the instruction.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -167,54 +335,100 @@ pack_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, int N
 struct TcArgs {
   ConvArgs c;
   const __nv_bfloat16* wp;   // packed weights
+  const uint32_t* tile_mask; // per 128-row tile: active kernel offsets (NULL: all)
   int cout_pad, ktot_pad;
   int n_tiles_n;
+  int T;                     // M tiles per super-tile (weight reuse factor)
   int split;                 // 1: bf16x3, 0: single-pass bf16
+  int dbg;                   // FD_TC_DEBUG ablation bits (perf triage only): 1 no A gather, 2 no MMA, 4 no B copy, 8 no stores
 };
 
-// ---- the kernel -----------------------------------------------------------------------------------
+template <int NT> struct TcCfg {
+  static constexpr int SA = NT >= 128 ? 4 : 5;                 // A ring slots (32 KB each)
+  static constexpr int SB = NT >= 32 ? 2 : 3;                  // B ring slots
+  static constexpr int A_BYTES = 2 * TC_A_PLANE;
+  static constexpr int B_BYTES = 2 * NT * 128;
+  // NT <= 64: the split products A_hi*B_hi and A_hi*B_lo are issued as ONE MMA of width 2*NT against the adjacent
+  // [B_hi | B_lo] planes (each MMA re-reads its whole A tile from shared memory, which is what bounds narrow tiles),
+  // so a tile owns two accumulator column blocks that the epilogue adds.
+  static constexpr bool FUSE_N = NT <= 64;
+  static constexpr int ACC_COLS = FUSE_N ? 2 * NT : NT;
+  static constexpr int TMAX = 256 / ACC_COLS > 4 ? 4 : 256 / ACC_COLS;   // M tiles sharing one weight fetch
+  static constexpr int TMEM_COLS = 2 * TMAX * ACC_COLS < 32 ? 32 : 2 * TMAX * ACC_COLS;
+  static constexpr int IDX_BYTES = TMAX * TC_DENSE_MAXK * TC_BM * 4;   // dense-mode row index cache
+  static constexpr int NBAR = 2 * SA + 2 * SB + 4;
+  static constexpr size_t SMEM = 1024 + (size_t)SA * A_BYTES + (size_t)SB * B_BYTES + IDX_BYTES + 2 * TC_SS_MAX * 4 + NBAR * 8 + 64;
+};
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* v) {
+  if constexpr (N == 16) {
+    tmem_ld16(taddr, v);
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+  }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const TcArgs t) {
-  constexpr int STAGES = tc_num_stages(NT);
-  constexpr int STAGE_BYTES = tc_stage_bytes(NT);
-  constexpr int TMEM_COLS = (2 * NT) < 32 ? 32 : 2 * NT;
+  using Cfg = TcCfg<NT>;
+  constexpr int SA = Cfg::SA, SB = Cfg::SB;
   constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, NT);
+  constexpr uint32_t IDESC2 = umma_idesc_bf16(TC_BM, Cfg::FUSE_N ? 2 * NT : NT);
+  constexpr int ACC = Cfg::ACC_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B alignment
-  uint8_t* stage_base = smem;
-  int* s_nbr = (int*)(smem + STAGES * STAGE_BYTES);                 // [2][TC_MAXK][128]
-  uint64_t* bars = (uint64_t*)(s_nbr + 2 * TC_MAXK * TC_BM);
-  uint64_t* full_bar = bars;                       // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;         // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;    // [2]
-  uint32_t* s_meta = (uint32_t*)(bars + 2 * STAGES + 4);   // [STAGES] bit0 first, bit1 last
-  uint32_t* s_tmem = s_meta + STAGES;                      // [1]
-  uint32_t* s_active = s_tmem + 1;                         // [2]
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + SA * Cfg::A_BYTES;
+  int* s_idx = (int*)(b_ring + SB * Cfg::B_BYTES);                // [TMAX][TC_DENSE_MAXK][128] (dense mode)
+  float* s_scale = (float*)((uint8_t*)s_idx + Cfg::IDX_BYTES);    // [TC_SS_MAX] folded BN scale, then shift
+  float* s_shift = s_scale + TC_SS_MAX;
+  uint64_t* bars = (uint64_t*)(s_shift + TC_SS_MAX);
+  uint64_t* a_full = bars;                  // [SA]
+  uint64_t* a_empty = a_full + SA;          // [SA]
+  uint64_t* b_full = a_empty + SA;          // [SB]
+  uint64_t* b_empty = b_full + SB;          // [SB]
+  uint64_t* t_full = b_empty + SB;          // [2]
+  uint64_t* t_empty = t_full + 2;           // [2]
+  uint32_t* s_tmem = (uint32_t*)(t_empty + 2);
 
   const ConvArgs& a = t.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.d_n ? min(*a.d_n, a.n_cap) : a.n_cap;
+  const int T = t.T;
   const int n_tiles_m = (n + TC_BM - 1) / TC_BM;
-  const int n_tiles = n_tiles_m * t.n_tiles_n;
+  const int n_super = (n_tiles_m + T - 1) / T;
+  const int n_units = n_super * t.n_tiles_n;
   const int ktot = a.K * a.cin;
-  const int n_kstages = (ktot + TC_BK - 1) / TC_BK;
+  const int n_kstages = (ktot + TC_BK - 1) / TC_BK;      // <= 64 (checked on the host)
+  const bool wide = a.cin >= TC_BK;
+  const int spo = wide ? a.cin / TC_BK : 1;      // stages per kernel offset   (wide:   Cin multiple of 64)
+  const int opk = wide ? 1 : TC_BK / a.cin;      // kernel offsets per stage   (narrow: Cin divides 64)
+  constexpr int G = TC_GROUPS, GT = TC_PRODUCERS / G;
+  const bool ss_smem = t.cout_pad <= TC_SS_MAX;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), TC_PRODUCERS / (NT >= 128 ? 2 : 4));   // one producer group per stage
-      mbar_init(smem_u32(&empty_bar[s]), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 128);
-    }
+    for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), GT); mbar_init(smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 128); }
     fence_barrier_init();
   }
-  if (warp == TC_PRODUCER_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS));
+  if (ss_smem)
+    for (int c = threadIdx.x; c < t.cout_pad; c += TC_THREADS) {
+      s_scale[c] = (a.scale && c < a.cout) ? a.scale[c] : 1.f;
+      s_shift[c] = (a.shift && c < a.cout) ? a.shift[c] : 0.f;
+    }
+  if (warp == TC_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(Cfg::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -222,293 +436,363 @@ conv_tc_kernel(const TcArgs t) {
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
+  // K stages of a super-tile that touch an active kernel offset, as a bit mask over ks (ks = 0 is forced for an
+  // all-empty unit so that the accumulator is always defined).  Identical in every role.
+  // Without a rulebook mask (dense 2-D convolutions) every stage is active and ks == position; the bit mask is only
+  // built for masked launches (n_kstages <= 64 is checked on the host for those).
+  const bool all_active = t.tile_mask == nullptr;
+  auto unit_ksmask = [&](int st) -> unsigned long long {
+    if (all_active) return ~0ull;
+    uint32_t m = 0;
+    {
+      for (int i = 0; i < T; ++i) {
+        const int tm = st * T + i;
+        if (tm < n_tiles_m) m |= __ldg(t.tile_mask + tm);
+      }
+    }
+    unsigned long long ksm = 0;
+    for (int ks = 0; ks < n_kstages; ++ks) {
+      const uint32_t km = wide ? (1u << (ks / spo)) : (((1u << opk) - 1u) << (ks * opk));
+      if (m & km) ksm |= 1ull << ks;
+    }
+    return ksm ? ksm : 1ull;
+  };
+
   if (warp < TC_PRODUCER_WARPS) {
-    // ===================================== PRODUCERS =====================================
-    // The producer warps are split into G groups; group g fills every G-th emitted stage on its own, so G
-    // stages are being issued concurrently (a single warp's issue chain per stage is several hundred cycles).
-    constexpr int G = NT >= 128 ? 2 : 4;
-    constexpr int GT = TC_PRODUCERS / G;         // threads per group
+    // ===================================== PRODUCERS (A gather) =====================================
+    // 4 groups of 64 threads; group g fills emitted A stages g, g+4, ... on its own, so several stages are being
+    // issued concurrently, and the rulebook indices of a group's next stage are prefetched while it waits for a slot.
     constexpr int ROWS_PER_PASS = GT / 8;
     constexpr int PASSES = TC_BM / ROWS_PER_PASS;
-    constexpr uint32_t B_BYTES = 2 * NT * 128;   // one pre-swizzled weight stage (hi + lo planes)
     const int tid = threadIdx.x;                 // 0..TC_PRODUCERS-1
     const int grp = tid / GT, gt = tid % GT;
     const int j = gt & 7, rbase = gt >> 3;       // 16-byte chunk column, first row (rows rbase + p*ROWS_PER_PASS)
-    uint32_t slot = 0, phase = 0, turn = 0;      // ring slot / phase / owning group of the next emitted stage
-    const uint32_t stage_u32 = smem_u32(stage_base);
-    const uint32_t nbr_u32 = smem_u32(s_nbr);
-    // per-thread constant of the swizzled A stores ((row & 7) is the same for every pass of a thread)
-    const uint32_t a_off0 = rbase * 128 + ((j ^ (rbase & 7)) << 4);
-    // flattened-K bookkeeping without per-stage divisions: Cin is a multiple of 64, or divides 64
-    const bool wide = a.cin >= TC_BK;
-    const int spo = wide ? a.cin / TC_BK : 1;    // stages per kernel offset   (wide)
-    const int opk = wide ? 1 : TC_BK / a.cin;    // kernel offsets per stage   (narrow)
+    const uint32_t a_ring_u32 = smem_u32(a_ring), idx_u32 = smem_u32(s_idx);
+    const uint32_t a_off0 = rbase * 128 + ((j ^ (rbase & 7)) << 4);   // (row & 7) is the same for every pass
     const int jk = wide ? 0 : (j * 8) / a.cin;   // which of the stage's offsets this thread's chunk belongs to
     const int jc = wide ? j * 8 : (j * 8) % a.cin;
     const uint32_t row_bytes = (uint32_t)a.in_stride * 4;
     const char* in_b = reinterpret_cast<const char*>(a.in);
     const char* in_lo = in_b + (size_t)a.in_ctot * 2;
-    const char* wblocks = reinterpret_cast<const char*>(t.wp);
-    // rulebook rows of one tile -> s_nbr[buf] (cp.async for the table mode, arithmetic for dense 2-D)
-    auto load_nbr = [&](int tile, int buf) {
-      const int tm = tile / t.n_tiles_n;
-      for (int e = tid; e < a.K * TC_BM; e += TC_PRODUCERS) {
-        const int k = e >> 7, r = e & (TC_BM - 1);
-        const int o = tm * TC_BM + r;
-        const uint32_t dst = nbr_u32 + (uint32_t)(buf * TC_MAXK * TC_BM + e) * 4;
-        if (a.mode == FD_GATHER_TABLE && o < n) cp_async4(dst, a.nbr + (size_t)k * a.nbr_stride + o);
-        else sts_u32(dst, (uint32_t)(o < n ? gather_row(a, o, k) : -1));
-      }
-    };
-    int it = 0;
-    if ((int)blockIdx.x < n_tiles) load_nbr(blockIdx.x, 0);
-    cp_async_commit();
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const int tn = tile % t.n_tiles_n;
-      const uint32_t nb_u32 = nbr_u32 + (uint32_t)(buf * TC_MAXK * TC_BM) * 4;
-      cp_async_wait_group<0>();                            // rulebook rows of this tile (committed a whole tile ago;
-                                                           // stage gathers are never committed, so not waited for)
-      if (tid == 0) s_active[buf] = 0;
-      named_bar_sync(1, TC_PRODUCERS);                     // s_nbr[buf] complete, s_active cleared
-      {
-        uint32_t m = 0;
-        for (int e = tid; e < a.K * TC_BM; e += TC_PRODUCERS)       // k is warp-uniform (32 consecutive rows)
-          if (__any_sync(0xffffffffu, (int)lds_u32(nb_u32 + (uint32_t)e * 4) >= 0)) m |= 1u << (e >> 7);
-        if (lane == 0 && m) atomicOr(&s_active[buf], m);
-      }
-      if (tile + (int)gridDim.x < n_tiles) load_nbr(tile + gridDim.x, buf ^ 1);   // prefetch next tile's rows
-      cp_async_commit();
-      named_bar_sync(1, TC_PRODUCERS);
-      const uint32_t active = s_active[buf];
-      // stage list: flattened-K stages that touch at least one active kernel offset
-      auto stage_mask = [&](int ks) -> uint32_t {
-        return wide ? (1u << (ks / spo)) : ((((1u << opk) - 1u) << (ks * opk)));
-      };
-      int first_ks = -1, last_ks = -1;
-      for (int ks = 0; ks < n_kstages; ++ks)
-        if (active & stage_mask(ks)) { if (first_ks < 0) first_ks = ks; last_ks = ks; }
-      if (first_ks < 0) first_ks = last_ks = 0;            // degenerate tile: one all-zero stage
-      const char* wtile = wblocks + (size_t)tn * n_kstages * B_BYTES;
-      int kk_run = wide ? first_ks / spo : 0, c_idx = wide ? first_ks - kk_run * spo : 0;
-      for (int ks = first_ks; ks <= last_ks; ++ks) {
-        const uint32_t smask = wide ? (1u << kk_run) : (((1u << opk) - 1u) << (ks * opk));
-        const int kk = wide ? kk_run : ks * opk + jk;
-        const int ch = wide ? c_idx * TC_BK + jc : jc;
-        if (wide && ++c_idx == spo) { c_idx = 0; ++kk_run; }
-        if (!(active & smask) && ks != first_ks && ks != last_ks) continue;
-        // every group walks the same emitted-stage sequence; only the owner of this stage fills it
-        const uint32_t my_slot = slot, my_phase = phase;
-        const bool mine = turn == (uint32_t)grp;
-        if (++slot == STAGES) { slot = 0; phase ^= 1; }
-        if (++turn == G) turn = 0;
-        if (!mine) continue;
-        mbar_wait(smem_u32(&empty_bar[my_slot]), my_phase ^ 1);
-        const uint32_t sbase = stage_u32 + my_slot * STAGE_BYTES;
-        const uint32_t fbar = smem_u32(&full_bar[my_slot]);
-        if (gt == 0) {
-          s_meta[my_slot] = (ks == first_ks ? 1u : 0u) | (ks == last_ks ? 2u : 0u);
-          // ---- B: one TMA bulk copy of the pre-swizzled weight stage, completes (in bytes) on the full barrier
-          mbar_expect_tx(fbar, B_BYTES);
-          bulk_g2s(sbase + 2 * TC_A_PLANE, wtile + (size_t)ks * B_BYTES, B_BYTES, fbar);
+    const bool table = a.mode == FD_GATHER_TABLE;
+    uint32_t c_base = 0;                         // emitted A stages before this unit (ring position bookkeeping)
+    int ptrace_i = 0;
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int st = unit / t.n_tiles_n;
+      const int live = min(T, n_tiles_m - st * T);
+      if (!table) {
+        // dense 2-D: row indices are arithmetic; computed once per unit into shared memory
+        named_bar_sync(1, TC_PRODUCERS);                   // every group is done reading the previous unit's indices
+        for (int e = tid; e < live * a.K * TC_BM; e += TC_PRODUCERS) {
+          const int ti = e / (a.K * TC_BM), rem = e - ti * a.K * TC_BM;
+          const int k = rem >> 7, r = rem & (TC_BM - 1);
+          const int o = (st * T + ti) * TC_BM + r;
+          sts_u32(idx_u32 + (uint32_t)((ti * TC_DENSE_MAXK + k) * TC_BM + r) * 4, (uint32_t)(o < n ? gather_row(a, o, k) : -1));
         }
-        // ---- A: gather 128 rows x 64 channels (this thread: chunk j of rows rbase + ROWS_PER_PASS p)
-        const bool kvalid = kk < a.K;
-        const uint32_t nb_row = nb_u32 + (uint32_t)((kvalid ? kk : 0) * TC_BM + rbase) * 4;
-        const uint32_t dst0 = sbase + a_off0;
-        if (a.in_fmt == FD_FMT_SPLIT_BF16) {
+        named_bar_sync(1, TC_PRODUCERS);
+      }
+      const unsigned long long ksmask = unit_ksmask(st);
+      const int n_emit = (all_active ? n_kstages : __popcll(ksmask)) * live;
+      // this group's positions in the unit's emitted-stage list: p = p0, p0 + G, ...
+      int p = (int)((grp + G - (c_base % G)) % G);
+      uint32_t slot = (c_base + p) % SA, phase = ((c_base + p) / SA) & 1;
+      unsigned long long rem = ksmask;             // active stages not yet passed
+      int act_idx = 0;                              // index (among active stages) of the lowest bit of `rem`
+      int src[PASSES], kk_n = 0, ch_n = 0, ti_n = 0;
+      // (ks, ti) of position p, this thread's kernel offset / channel, and the 16 gathered row indices
+      auto fetch = [&](int pos) {
+        const int want = pos / live;
+        ti_n = pos - want * live;
+        int ks = want;
+        if (!all_active) {
+          while (act_idx < want) { rem &= rem - 1; ++act_idx; }
+          ks = __ffsll((long long)rem) - 1;
+        }
+        const int kq = wide ? ks / spo : 0;
+        kk_n = wide ? kq : ks * opk + jk;
+        ch_n = wide ? (ks - kq * spo) * TC_BK + jc : jc;
+        const bool kvalid = kk_n < a.K;
+        const int row0 = (st * T + ti_n) * TC_BM + rbase;
+        if (table) {
+          const int32_t* nrow = a.nbr + (size_t)(kvalid ? kk_n : 0) * a.nbr_stride + row0;
+#pragma unroll
+          for (int q = 0; q < PASSES; ++q)
+            src[q] = (kvalid && row0 + q * ROWS_PER_PASS < n) ? __ldg(nrow + q * ROWS_PER_PASS) : -1;
+        } else {
+          const uint32_t ib = idx_u32 + (uint32_t)((ti_n * TC_DENSE_MAXK + (kvalid ? kk_n : 0)) * TC_BM + rbase) * 4;
+#pragma unroll
+          for (int q = 0; q < PASSES; ++q) src[q] = kvalid ? (int)lds_u32(ib + q * ROWS_PER_PASS * 4) : -1;
+        }
+      };
+      if (p < n_emit) fetch(p);
+      for (; p < n_emit; p += G) {
+        int cur[PASSES];
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) cur[q] = src[q];
+        const int ch = ch_n;
+        if (p + G < n_emit) fetch(p + G);                  // prefetch the next owned stage's indices (in flight during the wait)
+        if (tid == 0) TC_TRACE(1, 4 * ptrace_i, clock64());
+        mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1, 2);
+        if (tid == 0) { TC_TRACE(1, 4 * ptrace_i + 1, clock64()); TC_TRACE(1, 4 * ptrace_i + 3, (long long)(c_base + p)); }
+        const uint32_t fbar = smem_u32(&a_full[slot]);
+        const uint32_t dst0 = a_ring_u32 + slot * Cfg::A_BYTES + a_off0;
+        slot += G;
+        if (slot >= SA) { slot -= SA; phase ^= 1; }
+        // ---- A: gather 128 rows x 64 channels (this thread: chunk j of rows rbase + ROWS_PER_PASS q)
+        if (t.dbg & 1) {
+          mbar_arrive(fbar);
+        } else if (a.in_fmt == FD_FMT_SPLIT_BF16) {
           // pre-split bf16 hi/lo rows: pure 16-byte cp.async copies (zero-filled where the rulebook has no
           // neighbour); nothing is waited for -- the hardware arrives on the full barrier when they land
           const char* gh = in_b + ch * 2;
           const char* gl = in_lo + ch * 2;
-#pragma unroll 8
-          for (int p = 0; p < PASSES; ++p) {
-            const int src = kvalid ? (int)lds_u32(nb_row + p * ROWS_PER_PASS * 4) : -1;
-            const uint32_t sz = src >= 0 ? 16u : 0u;
-            const size_t goff = (size_t)(uint32_t)max(src, 0) * row_bytes;
-            cp_async16_sz(dst0 + p * ROWS_PER_PASS * 128, gh + goff, sz);
-            cp_async16_sz(dst0 + p * ROWS_PER_PASS * 128 + TC_A_PLANE, gl + goff, sz);
+#pragma unroll
+          for (int q = 0; q < PASSES; ++q) {
+            const uint32_t sz = cur[q] >= 0 ? 16u : 0u;
+            const size_t goff = (size_t)(uint32_t)max(cur[q], 0) * row_bytes;
+            cp_async16_sz(dst0 + q * ROWS_PER_PASS * 128, gh + goff, sz);
+            cp_async16_sz(dst0 + q * ROWS_PER_PASS * 128 + TC_A_PLANE, gl + goff, sz);
           }
           cp_async_mbar_arrive_noinc(fbar);
         } else {
           // fp32 rows (the stem reading voxel features): split into bf16 hi/lo in registers, 4 rows at a time
-#pragma unroll 1
+#pragma unroll
           for (int p0 = 0; p0 < PASSES; p0 += 4) {
             float4 v[4][2];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              const int src = kvalid ? (int)lds_u32(nb_row + (p0 + p) * ROWS_PER_PASS * 4) : -1;
-              if (src >= 0) {
-                const float4* gp = reinterpret_cast<const float4*>(a.in + (size_t)src * a.in_stride + ch);
-                v[p][0] = __ldg(gp);
-                v[p][1] = __ldg(gp + 1);
+            for (int q = 0; q < 4; ++q) {
+              if (cur[p0 + q] >= 0) {
+                const float4* gp = reinterpret_cast<const float4*>(a.in + (size_t)cur[p0 + q] * a.in_stride + ch);
+                v[q][0] = __ldg(gp);
+                v[q][1] = __ldg(gp + 1);
               } else {
-                v[p][0] = v[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[q][0] = v[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
             }
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              const float f[8] = {v[p][0].x, v[p][0].y, v[p][0].z, v[p][0].w, v[p][1].x, v[p][1].y, v[p][1].z, v[p][1].w};
+            for (int q = 0; q < 4; ++q) {
+              const float f[8] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w, v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
               uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
                 float2 hf = __bfloat1622float2(h);
-                __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
-                hi[q] = *reinterpret_cast<uint32_t*>(&h);
-                lo[q] = *reinterpret_cast<uint32_t*>(&l);
+                __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+                hi[e] = *reinterpret_cast<uint32_t*>(&h);
+                lo[e] = *reinterpret_cast<uint32_t*>(&l);
               }
-              sts_u128(dst0 + (p0 + p) * ROWS_PER_PASS * 128, hi[0], hi[1], hi[2], hi[3]);
-              sts_u128(dst0 + (p0 + p) * ROWS_PER_PASS * 128 + TC_A_PLANE, lo[0], lo[1], lo[2], lo[3]);
+              sts_u128(dst0 + (p0 + q) * ROWS_PER_PASS * 128, hi[0], hi[1], hi[2], hi[3]);
+              sts_u128(dst0 + (p0 + q) * ROWS_PER_PASS * 128 + TC_A_PLANE, lo[0], lo[1], lo[2], lo[3]);
             }
           }
           fence_proxy_async();                             // generic-proxy smem writes -> visible to the tensor core
           mbar_arrive(fbar);
         }
+        if (tid == 0) TC_TRACE(1, 4 * ptrace_i + 2, clock64());
+        ++ptrace_i;
       }
+      c_base += (uint32_t)n_emit;
     }
     cp_async_wait_all();
-  } else if (warp == TC_PRODUCER_WARPS) {
+    (void)ptrace_i;
+  } else if (warp == TC_MMA_WARP) {
     // ===================================== MMA ISSUER =====================================
-    uint32_t stage = 0, phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    // the whole warp walks the loop converged with warp-uniform operands; an elected lane issues mma / commit
+    uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
+    const uint32_t a_ring_u32 = smem_u32(a_ring), b_ring_u32 = smem_u32(b_ring);
+    uint32_t a_ready = 0, b_ready = 0;          // probe results for the upcoming A / B slot (issued one step ahead)
+    int it = 0, trace_i = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+      const int st = unit / t.n_tiles_n;
+      const int live = min(T, n_tiles_m - st * T);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);       // epilogue has drained this accumulator
+      const int n_act = all_active ? n_kstages : __popcll(unit_ksmask(st));
+      mbar_wait(smem_u32(&t_empty[acc]), acc_phase ^ 1, 3);        // epilogue has drained this accumulator buffer
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * NT;
-      while (true) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        tc_fence_after();
-        fence_proxy_async();
-        const uint32_t meta = s_meta[stage];
-        if (lane == 0) {
-          const uint32_t sA_hi = smem_u32(stage_base + stage * STAGE_BYTES);
-          const uint32_t sA_lo = sA_hi + TC_A_PLANE;
-          const uint32_t sB_hi = sA_lo + TC_A_PLANE;
-          const uint32_t sB_lo = sB_hi + NT * 128;
+      uint32_t accumulate = 0;
+      for (int ia = 0; ia < n_act; ++ia) {
+        if (!b_ready) mbar_wait(smem_u32(&b_full[b_slot]), b_phase, 4);
+        const uint32_t sB_hi = b_ring_u32 + b_slot * Cfg::B_BYTES, sB_lo = sB_hi + NT * 128;
+        const uint64_t dB_hi = umma_desc_sw128(sB_hi), dB_lo = umma_desc_sw128(sB_lo);
+        const uint32_t nb_slot = b_slot + 1 == SB ? 0 : b_slot + 1, nb_phase = b_slot + 1 == SB ? b_phase ^ 1 : b_phase;
+        b_ready = mbar_test(smem_u32(&b_full[nb_slot]), nb_phase);   // consumed at the next K stage
+        for (int ti = 0; ti < live; ++ti) {
+          if (lane == 0) TC_TRACE(3, 4 * trace_i + 2, clock64());
+          if (!a_ready) mbar_wait(smem_u32(&a_full[a_slot]), a_phase, 5);
+          if (lane == 0) TC_TRACE(0, 2 * trace_i, clock64());
+          tc_fence_after();
+          if (lane == 0) TC_TRACE(3, 4 * trace_i + 3, clock64());
+          const uint32_t na_slot = a_slot + 1 == SA ? 0 : a_slot + 1, na_phase = a_slot + 1 == SA ? a_phase ^ 1 : a_phase;
+          const uint32_t sA_hi = a_ring_u32 + a_slot * Cfg::A_BYTES, sA_lo = sA_hi + TC_A_PLANE;
           const uint64_t dA_hi = umma_desc_sw128(sA_hi), dA_lo = umma_desc_sw128(sA_lo);
-          const uint64_t dB_hi = umma_desc_sw128(sB_hi), dB_lo = umma_desc_sw128(sB_lo);
-#pragma unroll
-          for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
-            const uint64_t adv = (uint64_t)(k4 * 2);       // 16 bf16 = 32 bytes = 2 x 16-byte units
-            umma_bf16(tmem_d, dA_hi + adv, dB_hi + adv, IDESC, ((meta & 1u) && k4 == 0) ? 0u : 1u);
-            if (t.split) {
-              umma_bf16(tmem_d, dA_hi + adv, dB_lo + adv, IDESC, 1u);
-              umma_bf16(tmem_d, dA_lo + adv, dB_hi + adv, IDESC, 1u);
-            }
+          const uint32_t tmem_d = tmem_base + (uint32_t)((acc * T + ti) * ACC);
+          const uint32_t nbar = smem_u32(&a_full[na_slot]), cbar = smem_u32(&a_empty[a_slot]);
+          if (t.dbg & 2) {
+            umma_commit_elect(cbar);
+            a_ready = 0;
+          } else if (!t.split) {
+            a_ready = umma_stage<0>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, na_phase, cbar);
+          } else if (Cfg::FUSE_N) {
+            a_ready = umma_stage<1>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, na_phase, cbar);
+          } else {
+            a_ready = umma_stage<2>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, na_phase, cbar);
           }
-          umma_commit(smem_u32(&empty_bar[stage]));        // smem stage reusable once these MMAs retire
-          if (meta & 2u) umma_commit(smem_u32(&tfull_bar[acc]));
+          if (lane == 0) TC_TRACE(0, 2 * trace_i + 1, clock64());
+          ++trace_i;
+          a_slot = na_slot; a_phase = na_phase;
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        if (meta & 2u) break;
+        umma_commit_elect(smem_u32(&b_empty[b_slot]));     // weight slot free after the unit's last tile
+        b_slot = nb_slot; b_phase = nb_phase;
+        accumulate = 1;
+      }
+      umma_commit_elect(smem_u32(&t_full[acc]));
+    }
+    __syncwarp();
+  } else if (warp == TC_B_WARP) {
+    // ===================================== WEIGHT LOADER =====================================
+    // one lane: per (unit, active K stage) one TMA bulk copy of the pre-swizzled weight stage, shared by the T tiles
+    if (lane == 0) {
+      uint32_t b_slot = 0, b_phase = 0;
+      const uint32_t b_ring_u32 = smem_u32(b_ring);
+      const char* wblocks = reinterpret_cast<const char*>(t.wp);
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int st = unit / t.n_tiles_n, tn = unit - st * t.n_tiles_n;
+        const char* wtile = wblocks + (size_t)tn * n_kstages * Cfg::B_BYTES;
+        unsigned long long rem = unit_ksmask(st);
+        const int n_act = all_active ? n_kstages : __popcll(rem);
+        for (int ia = 0; ia < n_act; ++ia, rem &= rem - 1) {
+          const int ks = all_active ? ia : __ffsll((long long)rem) - 1;
+          const uint32_t bbar = smem_u32(&b_full[b_slot]);
+          mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1);
+          if (!(t.dbg & 4)) {
+            mbar_expect_tx(bbar, Cfg::B_BYTES);
+            bulk_g2s(b_ring_u32 + b_slot * Cfg::B_BYTES, wtile + (size_t)ks * Cfg::B_BYTES, Cfg::B_BYTES, bbar);
+          }
+          mbar_arrive(bbar);
+          if (++b_slot == SB) { b_slot = 0; b_phase ^= 1; }
+        }
       }
     }
+    __syncwarp();
   } else {
     // ===================================== EPILOGUE =====================================
+    constexpr int CH = NT >= 32 ? 32 : 16;                 // accumulator columns per TMEM load
     const int q = warp & 3;                                 // TMEM lane quarter this warp may access
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+      const int st = unit / t.n_tiles_n, tn = unit - st * t.n_tiles_n;
+      const int live = min(T, n_tiles_m - st * T);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tm = tile / t.n_tiles_n, tn = tile - tm * t.n_tiles_n;
-      const int o = tm * TC_BM + q * 32 + lane;
       const int col0 = tn * NT;
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      mbar_wait(smem_u32(&t_full[acc]), acc_phase, 6, 64);
+      if (threadIdx.x == (TC_MMA_WARP + 1) * 32) TC_TRACE(2, 2 * it, clock64());
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NT;
-      const bool live = o < n;
-      OutRow orow{nullptr, 0, 1};
-      if (live) orow = map_out_row(a, o);
-      const float* res = (a.residual && live) ? a.residual + (size_t)o * a.res_stride : nullptr;
+      for (int ti = 0; ti < live; ++ti) {
+        const int o = (st * T + ti) * TC_BM + q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + ti) * ACC);
+        const bool live_row = o < n;
+        OutRow orow{nullptr, 0, 1};
+        if (live_row) orow = map_out_row(a, o);
+        const float* res = (a.residual && live_row) ? a.residual + (size_t)o * a.res_stride : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (c0 + 16 >= NT) {                                // all TMEM reads of this tile are done
-          tc_fence_before();
-          mbar_arrive(smem_u32(&tempty_bar[acc]));
-        }
-        if (!live) continue;
-        const int cbase = col0 + c0;
-        if (cbase >= a.cout) continue;
-        const bool full16 = cbase + 16 <= a.cout;
-        float y[16];
-        // residual (identity) values
-        if (res) {
-          if (a.res_fmt == FD_FMT_SPLIT_BF16 && full16) {
-            const uint4* rh = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(res) + cbase);
-            const uint4* rl = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(res) + a.res_ctot + cbase);
+        for (int c0 = 0; c0 < NT; c0 += CH) {
+          const int cbase = col0 + c0;
+          const bool work = live_row && !(t.dbg & 8) && cbase < a.cout;
+          const bool fullc = cbase + CH <= a.cout;
+          // identity (residual) values first: they do not depend on the accumulator, so their latency overlaps
+          // the TMEM load
+          float y[CH];
+          if (work && res) {
+            if (a.res_fmt == FD_FMT_SPLIT_BF16 && fullc) {
+              const uint4* rh = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(res) + cbase);
+              const uint4* rl = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(res) + a.res_ctot + cbase);
+              uint4 hv[CH / 8], lv[CH / 8];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint4 a4 = __ldg(rh + h), b4 = __ldg(rl + h);
-              const uint32_t hw[4] = {a4.x, a4.y, a4.z, a4.w}, lw[4] = {b4.x, b4.y, b4.z, b4.w};
+              for (int h = 0; h < CH / 8; ++h) { hv[h] = __ldg(rh + h); lv[h] = __ldg(rl + h); }
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                y[h * 8 + 2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
-                y[h * 8 + 2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+              for (int h = 0; h < CH / 8; ++h) {
+                const uint32_t hw[4] = {hv[h].x, hv[h].y, hv[h].z, hv[h].w}, lw[4] = {lv[h].x, lv[h].y, lv[h].z, lv[h].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  y[h * 8 + 2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+                  y[h * 8 + 2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+                }
               }
+            } else {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) y[i] = (cbase + i < a.cout) ? load_residual(a, o, cbase + i) : 0.f;
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = (cbase + i < a.cout) ? load_residual(a, o, cbase + i) : 0.f;
+            for (int i = 0; i < CH; ++i) y[i] = 0.f;
           }
-        } else {
+          uint32_t r[CH];
+          tmem_ld<CH>(taddr + c0, r);
+          if (Cfg::FUSE_N && t.split) {                      // second accumulator block: the A_hi*B_lo products
+            uint32_t r2[CH];
+            tmem_ld<CH>(taddr + NT + c0, r2);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = 0.f;
-        }
+            for (int i = 0; i < CH; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+          }
+          tmem_ld_wait();
+          if (ti == live - 1 && c0 + CH >= NT) {              // all TMEM reads of this unit are done
+            tc_fence_before();
+            mbar_arrive(smem_u32(&t_empty[acc]));
+          }
+          if (!work) continue;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = cbase + i;
-          float v = __uint_as_float(r[i]);
-          if (c < a.cout) {
-            const float sc = a.scale ? __ldg(a.scale + c) : 1.f;
-            const float sh = a.shift ? __ldg(a.shift + c) : 0.f;
-            v = fmaf(v, sc, sh) + y[i];
+          for (int i = 0; i < CH; ++i) {
+            const int c = cbase + i;
+            float sc, sh;
+            if (ss_smem) { sc = s_scale[c]; sh = s_shift[c]; }
+            else { sc = (a.scale && c < a.cout) ? __ldg(a.scale + c) : 1.f; sh = (a.shift && c < a.cout) ? __ldg(a.shift + c) : 0.f; }
+            float v = fmaf(__uint_as_float(r[i]), sc, sh) + y[i];
             if (a.relu) v = fmaxf(v, 0.f);
+            y[i] = v;
           }
-          y[i] = v;
-        }
-        if (orow.cstride == 1 && full16 && a.out_fmt == FD_FMT_SPLIT_BF16 &&
-            ((((uintptr_t)orow.base) + 2 * (size_t)(orow.coff + cbase)) & 15) == 0 && (a.out_ctot & 7) == 0) {
-          // split once here so that every consumer layer gathers ready-made bf16 hi/lo planes
-          uint32_t hi[8], lo[8];
+          if (orow.cstride == 1 && fullc && a.out_fmt == FD_FMT_SPLIT_BF16 &&
+              ((((uintptr_t)orow.base) + 2 * (size_t)(orow.coff + cbase)) & 15) == 0 && (a.out_ctot & 7) == 0) {
+            // split once here so that every consumer layer gathers ready-made bf16 hi/lo planes
+            unsigned short* ob = reinterpret_cast<unsigned short*>(orow.base) + orow.coff + cbase;
+            uint4* dh = reinterpret_cast<uint4*>(ob);
+            uint4* dl = reinterpret_cast<uint4*>(ob + a.out_ctot);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
-            float2 hf = __bfloat1622float2(h);
-            __nv_bfloat162 l = __floats2bfloat162_rn(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
-            hi[i] = *reinterpret_cast<uint32_t*>(&h);
-            lo[i] = *reinterpret_cast<uint32_t*>(&l);
+            for (int g8 = 0; g8 < CH / 8; ++g8) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(y[g8 * 8 + 2 * i], y[g8 * 8 + 2 * i + 1]);
+                float2 hf = __bfloat1622float2(h);
+                __nv_bfloat162 l = __floats2bfloat162_rn(y[g8 * 8 + 2 * i] - hf.x, y[g8 * 8 + 2 * i + 1] - hf.y);
+                hi[i] = *reinterpret_cast<uint32_t*>(&h);
+                lo[i] = *reinterpret_cast<uint32_t*>(&l);
+              }
+              dh[g8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              dl[g8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else if (orow.cstride == 1 && fullc && a.out_fmt == FD_FMT_FP32 &&
+                     ((((uintptr_t)(orow.base + orow.coff + cbase)) & 15) == 0)) {
+            float4* dst = reinterpret_cast<float4*>(orow.base + orow.coff + cbase);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+              if (cbase + i < a.cout) store_out(a, orow, cbase + i, y[i]);
           }
-          unsigned short* ob = reinterpret_cast<unsigned short*>(orow.base) + orow.coff + cbase;
-          uint4* dh = reinterpret_cast<uint4*>(ob);
-          uint4* dl = reinterpret_cast<uint4*>(ob + a.out_ctot);
-          dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        } else if (orow.cstride == 1 && full16 && a.out_fmt == FD_FMT_FP32 &&
-                   ((((uintptr_t)(orow.base + orow.coff + cbase)) & 15) == 0)) {
-          float4* dst = reinterpret_cast<float4*>(orow.base + orow.coff + cbase);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (cbase + i < a.cout) store_out(a, orow, cbase + i, y[i]);
         }
       }
+      if (threadIdx.x == (TC_MMA_WARP + 1) * 32) TC_TRACE(2, 2 * it + 1, clock64());
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_PRODUCER_WARPS) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  if (warp == TC_MMA_WARP) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS));
   }
 }
 
@@ -516,18 +800,21 @@ static int pick_nt(int cout) { return cout >= 128 ? 128 : cout >= 64 ? 64 : cout
 static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 
 template <int NT>
-static int launch_tc(const TcArgs& t, cudaStream_t stream) {
-  constexpr int STAGES = tc_num_stages(NT);
-  const size_t smem = 1024 + (size_t)STAGES * tc_stage_bytes(NT) + 2 * TC_MAXK * TC_BM * sizeof(int) +
-                      (2 * STAGES + 4) * sizeof(uint64_t) + (STAGES + 4) * sizeof(uint32_t);
+static int launch_tc(TcArgs& t, cudaStream_t stream) {
+  using Cfg = TcCfg<NT>;
   static bool configured = false;
   if (!configured) {
-    FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     configured = true;
   }
-  int tiles = ceil_div(t.c.n_cap, TC_BM) * t.n_tiles_n;
-  int grid = tiles < kNumSMs ? tiles : kNumSMs;           // persistent: one CTA per SM
-  conv_tc_kernel<NT><<<grid, TC_THREADS, smem, stream>>>(t);
+  // weight reuse factor: as many M tiles per weight fetch as TMEM allows while keeping >= one unit per SM
+  const int tiles_m = ceil_div(t.c.n_cap, TC_BM);
+  int T = Cfg::TMAX;
+  while (T > 1 && (int64_t)ceil_div(tiles_m, T) * t.n_tiles_n < kNumSMs) T >>= 1;
+  t.T = T;
+  const int64_t units = (int64_t)ceil_div(tiles_m, T) * t.n_tiles_n;
+  const int grid = units < kNumSMs ? (int)units : kNumSMs;   // persistent: one CTA per SM
+  conv_tc_kernel<NT><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(t);
   FD_LAUNCHED();
   return 0;
 }
@@ -538,17 +825,23 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
   FD_REQUIRE(a.cin % 8 == 0 && (a.cin % TC_BK == 0 || TC_BK % a.cin == 0),
              "fd_conv_forward: tensor-core arm needs Cin in {8,16,32} or a multiple of 64 (got %d)", a.cin);
   FD_REQUIRE(a.K <= TC_MAXK, "fd_conv_forward: tensor-core arm supports at most %d kernel offsets", TC_MAXK);
+  FD_REQUIRE(a.mode != FD_GATHER_TABLE || !a.tile_mask || (a.K * a.cin + TC_BK - 1) / TC_BK <= 64,
+             "fd_conv_forward: tensor-core arm supports K*Cin <= 4096 with a rulebook tile mask");
+  FD_REQUIRE(a.mode == FD_GATHER_TABLE || a.K <= TC_DENSE_MAXK,
+             "fd_conv_forward: tensor-core arm supports dense 2-D kernels of at most %d taps", TC_DENSE_MAXK);
   FD_REQUIRE(a.in_stride % 4 == 0 && (((uintptr_t)a.in) & 15) == 0 && (a.in_fmt != FD_FMT_SPLIT_BF16 || a.in_ctot % 8 == 0),
              "fd_conv_forward: tensor-core arm needs 16-byte aligned input rows / planes");
+  FD_REQUIRE((((uintptr_t)a.wp) & 15) == 0, "fd_conv_forward: d_w_packed must be 16-byte aligned");
   TcArgs t{};
   t.c = a;
   t.wp = (const __nv_bfloat16*)a.wp;
+  t.tile_mask = a.mode == FD_GATHER_TABLE ? a.tile_mask : nullptr;
   const int NT = pick_nt(a.cout);
   t.cout_pad = pad_to(a.cout, NT);
   t.ktot_pad = pad_to(a.K * a.cin, TC_BK);
   t.n_tiles_n = t.cout_pad / NT;
-  FD_REQUIRE((((uintptr_t)a.wp) & 15) == 0, "fd_conv_forward: d_w_packed must be 16-byte aligned");
   t.split = precision == FD_PREC_BF16X3;
+  { static const int dbg = getenv("FD_TC_DEBUG") ? atoi(getenv("FD_TC_DEBUG")) : 0; t.dbg = dbg; }
   switch (NT) {
     case 128: return launch_tc<128>(t, stream);
     case 64: return launch_tc<64>(t, stream);
@@ -560,6 +853,13 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
 }  // namespace fd
 
 extern "C" {
+
+/* perf-triage helper (not part of the documented ABI): copy the FD_TC_DEBUG&32 trace of block 0 to the host */
+int fd_debug_read_tc_trace(long long* out, int role) {
+  if (role < 0 || role >= 4) return -1;
+  return (int)cudaMemcpyFromSymbol(out, fd::g_tc_trace, sizeof(long long) * fd::TC_TRACE_N,
+                                   sizeof(long long) * fd::TC_TRACE_N * role, cudaMemcpyDeviceToHost);
+}
 
 size_t fd_conv_packed_bytes(int K, int cin, int cout) {
   if (K < 1 || cin < 1 || cout < 1) return 0;

@@ -22,32 +22,34 @@ __device__ __forceinline__ long long lin_key(int b, int z, int y, int x, Shape3 
   return (((long long)b * sh.d + z) * sh.h + y) * sh.w + x;
 }
 
+// One 64-bit word per hash entry: (linear coordinate << 32) | row, 0xFFFF...F = empty.  A lookup is a single
+// 8-byte load (L2 resident table), and the 27 probes of a row are issued back to back before any is consumed.
+constexpr unsigned long long kEmptyEntry = ~0ull;
+
 __global__ void __launch_bounds__(256)
 coord_index_insert(const int4* __restrict__ coords, const int32_t* __restrict__ d_n, int n_cap, Shape3 sh,
-                   long long* __restrict__ keys, int* __restrict__ vals, uint32_t mask) {
+                   unsigned long long* __restrict__ table, uint32_t mask) {
   int n = d_n ? min(*d_n, n_cap) : n_cap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int4 c = coords[i];
-    long long key = lin_key(c.x, c.y, c.z, c.w, sh);
-    uint32_t h = hash64((uint64_t)key) & mask;
+    const uint32_t key = (uint32_t)lin_key(c.x, c.y, c.z, c.w, sh);
+    const unsigned long long entry = ((unsigned long long)key << 32) | (uint32_t)i;
+    uint32_t h = hash64(key) & mask;
     while (true) {
-      long long prev = atomicCAS((unsigned long long*)&keys[h], (unsigned long long)kEmptyKey,
-                                 (unsigned long long)key);
-      if (prev == kEmptyKey || prev == key) break;
+      unsigned long long prev = atomicCAS(&table[h], kEmptyEntry, entry);
+      if (prev == kEmptyEntry || (uint32_t)(prev >> 32) == key) break;     // duplicates: first writer wins
       h = (h + 1) & mask;
     }
-    vals[h] = i;
   }
 }
 
-__device__ __forceinline__ int coord_index_find(const long long* __restrict__ keys, const int* __restrict__ vals,
-                                                uint32_t mask, long long key) {
-  uint32_t h = hash64((uint64_t)key) & mask;
+__device__ __forceinline__ int coord_index_resolve(const unsigned long long* __restrict__ table, uint32_t mask,
+                                                   uint32_t key, uint32_t h, unsigned long long e) {
   while (true) {
-    long long k = keys[h];
-    if (k == key) return vals[h];
-    if (k == kEmptyKey) return -1;
+    if ((uint32_t)(e >> 32) == key) return (int)(uint32_t)e;
+    if (e == kEmptyEntry) return -1;
     h = (h + 1) & mask;
+    e = table[h];
   }
 }
 
@@ -108,33 +110,77 @@ __global__ void clamp_count(int32_t* n, int cap) {
   if (threadIdx.x == 0 && blockIdx.x == 0 && *n > cap) *n = cap;
 }
 
-// nbr[k][o]: one thread per output row, loop over kernel offsets (warp-uniform k -> ballot count)
+// nbr[k][o]: one thread per output row; kernel offsets in groups of kx-rows so that the first probes of a group
+// are independent loads in flight together (the lookups are pure latency otherwise)
 __global__ void __launch_bounds__(256)
 neighbors_kernel(const int4* __restrict__ out_coords, const int32_t* __restrict__ d_n, int n_cap,
-                 const long long* __restrict__ keys, const int* __restrict__ vals, uint32_t mask,
-                 Shape3 ish, Conv3Geom g, int* __restrict__ nbr, int nbr_stride, int* __restrict__ pair_num) {
+                 const unsigned long long* __restrict__ table, uint32_t mask, Shape3 ish, Conv3Geom g,
+                 int* __restrict__ nbr, int nbr_stride, int* __restrict__ pair_num, uint32_t* __restrict__ tile_mask) {
   const int n = d_n ? min(*d_n, n_cap) : n_cap;
-  const int K = g.k[0] * g.k[1] * g.k[2];
   const int lane = threadIdx.x & 31;
   const int n_round = (n + 31) & ~31;  // keep warps converged for the ballots
+  constexpr int MAXG = 9;              // probes in flight per thread (ky x kx up to 3x3)
+  const int gsz = g.k[1] * g.k[2];
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_round; o += gridDim.x * blockDim.x) {
     const bool live = o < n;
     int4 c = live ? out_coords[o] : make_int4(0, 0, 0, 0);
     const int z0 = c.y * g.s[0] - g.p[0], y0 = c.z * g.s[1] - g.p[1], x0 = c.w * g.s[2] - g.p[2];
-    int k = 0;
-    for (int kz = 0; kz < g.k[0]; ++kz)
-      for (int ky = 0; ky < g.k[1]; ++ky)
-        for (int kx = 0; kx < g.k[2]; ++kx, ++k) {
-          int z = z0 + kz, y = y0 + ky, x = x0 + kx;
+    uint32_t my_mask = 0;
+    for (int kz = 0; kz < g.k[0]; ++kz) {
+      const int z = z0 + kz;
+      const bool zok = live && z >= 0 && z < ish.d;
+      if (gsz <= MAXG) {
+        uint32_t key[MAXG], h[MAXG];
+        unsigned long long e[MAXG];
+        bool ok[MAXG];
+#pragma unroll
+        for (int q = 0; q < MAXG; ++q) {
+          ok[q] = false;
+          if (q < gsz) {
+            const int ky = q / g.k[2], kx = q - ky * g.k[2];
+            const int y = y0 + ky, x = x0 + kx;
+            ok[q] = zok && y >= 0 && y < ish.h && x >= 0 && x < ish.w;
+            key[q] = (uint32_t)lin_key(c.x, z, y, x, ish);
+            h[q] = hash64(key[q]) & mask;
+            e[q] = ok[q] ? __ldg(&table[h[q]]) : kEmptyEntry;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < MAXG; ++q) {
+          if (q < gsz) {
+            const int k = kz * gsz + q;
+            int r = ok[q] ? coord_index_resolve(table, mask, key[q], h[q], e[q]) : -1;
+            if (live) nbr[(size_t)k * nbr_stride + o] = r;
+            unsigned m = __ballot_sync(0xffffffffu, r >= 0);
+            if (m) {
+              if (lane == 0) atomicAdd(&pair_num[k], __popc(m));
+              my_mask |= 1u << (k & 31);
+            }
+          }
+        }
+      } else {
+        for (int q = 0; q < gsz; ++q) {
+          const int ky = q / g.k[2], kx = q - ky * g.k[2];
+          const int y = y0 + ky, x = x0 + kx, k = kz * gsz + q;
           int r = -1;
-          if (live && z >= 0 && z < ish.d && y >= 0 && y < ish.h && x >= 0 && x < ish.w)
-            r = coord_index_find(keys, vals, mask, lin_key(c.x, z, y, x, ish));
+          if (zok && y >= 0 && y < ish.h && x >= 0 && x < ish.w) {
+            const uint32_t key = (uint32_t)lin_key(c.x, z, y, x, ish);
+            const uint32_t hh = hash64(key) & mask;
+            r = coord_index_resolve(table, mask, key, hh, table[hh]);
+          }
           if (live) nbr[(size_t)k * nbr_stride + o] = r;
           unsigned m = __ballot_sync(0xffffffffu, r >= 0);
-          if (lane == 0 && m) atomicAdd(&pair_num[k], __popc(m));
+          if (m) {
+            if (lane == 0) atomicAdd(&pair_num[k], __popc(m));
+            my_mask |= 1u << (k & 31);
+          }
         }
+      }
+    }
+    // per 128-row tile activity mask (bit k: some row of the tile has a neighbour through offset k); consumed by
+    // the implicit-GEMM kernels to skip kernel offsets that are empty for a whole tile
+    if (tile_mask && lane == 0 && my_mask) atomicOr(&tile_mask[o >> 7], my_mask);
   }
-  (void)K;
 }
 
 // ---- export to spconv layout ----------------------------------------------------
@@ -174,19 +220,22 @@ static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 
 extern "C" {
 
-int fd_coord_index_build(const int32_t* d_coords4, const int32_t* d_n, int n_cap, const int32_t* shape3,
-                         int64_t* d_keys, int32_t* d_vals, int64_t cap, void* stream_) {
+int fd_coord_index_build(const int32_t* d_coords4, const int32_t* d_n, int n_cap, int B, const int32_t* shape3,
+                         uint64_t* d_table, int64_t cap, void* stream_) {
   using namespace fd;
   cudaStream_t stream = (cudaStream_t)stream_;
-  FD_REQUIRE(d_coords4 && shape3 && d_keys && d_vals, "fd_coord_index_build: null argument");
+  FD_REQUIRE(d_coords4 && shape3 && d_table && B >= 1, "fd_coord_index_build: null argument");
+  FD_REQUIRE((int64_t)B * shape3[0] * shape3[1] * shape3[2] < 0xFFFFFFFFLL,
+             "fd_coord_index_build: B*D*H*W = %lld does not fit the 32-bit key of the packed index",
+             (long long)B * shape3[0] * shape3[1] * shape3[2]);
   FD_REQUIRE(is_pow2(cap) && cap >= 2 * (int64_t)n_cap && cap <= (1LL << 31),
              "fd_coord_index_build: cap %lld must be a power of two >= 2*n_cap (%d)", (long long)cap, n_cap);
   FD_REQUIRE(((uintptr_t)d_coords4 & 15) == 0, "fd_coord_index_build: coords must be 16-byte aligned");
-  FD_CUDA(cudaMemsetAsync(d_keys, 0xff, sizeof(int64_t) * cap, stream));
+  FD_CUDA(cudaMemsetAsync(d_table, 0xff, sizeof(uint64_t) * cap, stream));
   if (n_cap <= 0) return 0;
   Shape3 sh{shape3[0], shape3[1], shape3[2]};
   coord_index_insert<<<persistent_grid(ceil_div(n_cap, 256), 8), 256, 0, stream>>>(
-      (const int4*)d_coords4, d_n, n_cap, sh, (long long*)d_keys, d_vals, (uint32_t)(cap - 1));
+      (const int4*)d_coords4, d_n, n_cap, sh, (unsigned long long*)d_table, (uint32_t)(cap - 1));
   FD_LAUNCHED();
   return 0;
 }
@@ -230,14 +279,13 @@ int fd_rulebook_out_coords(const int32_t* d_in_coords4, const int32_t* d_n_in, i
 }
 
 int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, int n_out_cap,
-                          const int64_t* d_in_keys, const int32_t* d_in_vals, int64_t in_cap,
+                          const uint64_t* d_in_table, int64_t in_cap,
                           const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
                           const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
-                          void* stream_) {
+                          uint32_t* d_tile_mask, void* stream_) {
   using namespace fd;
   cudaStream_t stream = (cudaStream_t)stream_;
-  FD_REQUIRE(d_out_coords4 && d_in_keys && d_in_vals && in_shape3 && ksize3 && stride3 && pad3 && d_nbr &&
-                 d_pair_num,
+  FD_REQUIRE(d_out_coords4 && d_in_table && in_shape3 && ksize3 && stride3 && pad3 && d_nbr && d_pair_num,
              "fd_rulebook_neighbors: null argument");
   FD_REQUIRE(is_pow2(in_cap), "fd_rulebook_neighbors: in_cap must be a power of two");
   FD_REQUIRE(nbr_stride >= n_out_cap, "fd_rulebook_neighbors: nbr_stride < n_out_cap");
@@ -245,12 +293,14 @@ int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, 
   for (int j = 0; j < 3; ++j) { g.k[j] = ksize3[j]; g.s[j] = stride3[j]; g.p[j] = pad3[j]; }
   const int K = g.k[0] * g.k[1] * g.k[2];
   FD_REQUIRE(K >= 1 && K <= 343, "fd_rulebook_neighbors: kernel volume %d unsupported", K);
+  FD_REQUIRE(!d_tile_mask || K <= 32, "fd_rulebook_neighbors: tile masks support at most 32 kernel offsets");
   FD_CUDA(cudaMemsetAsync(d_pair_num, 0, sizeof(int32_t) * K, stream));
+  if (d_tile_mask) FD_CUDA(cudaMemsetAsync(d_tile_mask, 0, sizeof(uint32_t) * (size_t)ceil_div(n_out_cap > 0 ? n_out_cap : 1, 128), stream));
   if (n_out_cap <= 0) return 0;
   Shape3 ish{in_shape3[0], in_shape3[1], in_shape3[2]};
   neighbors_kernel<<<persistent_grid(ceil_div(n_out_cap, 256), 8), 256, 0, stream>>>(
-      (const int4*)d_out_coords4, d_n_out, n_out_cap, (const long long*)d_in_keys, d_in_vals,
-      (uint32_t)(in_cap - 1), ish, g, d_nbr, nbr_stride, d_pair_num);
+      (const int4*)d_out_coords4, d_n_out, n_out_cap, (const unsigned long long*)d_in_table,
+      (uint32_t)(in_cap - 1), ish, g, d_nbr, nbr_stride, d_pair_num, d_tile_mask);
   FD_LAUNCHED();
   return 0;
 }

@@ -30,6 +30,7 @@ class ConvDesc(C.Structure):
         ("d_n_out", C.c_void_p), ("n_out_cap", C.c_int32),
         ("mode", C.c_int32),
         ("d_nbr", C.c_void_p), ("nbr_stride", C.c_int32),
+        ("d_tile_mask", C.c_void_p),
         ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
         ("kh", C.c_int32), ("kw", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("ph", C.c_int32), ("pw", C.c_int32),
@@ -55,15 +56,15 @@ SIGNATURES = {
                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "fd_vfe_mean": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "fd_coord_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_int_p, C.c_void_p, C.c_void_p,
+    "fd_coord_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_int_p, C.c_void_p,
                                         C.c_int64, C.c_void_p]),
     "fd_scan_tmp_bytes": (C.c_size_t, [C.c_int64]),
     "fd_rulebook_out_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p,
                                           c_int_p, c_int_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_void_p]),
-    "fd_rulebook_neighbors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+    "fd_rulebook_neighbors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                          c_int_p, c_int_p, c_int_p, c_int_p, C.c_void_p, C.c_int, C.c_void_p,
-                                         C.c_void_p]),
+                                         C.c_void_p, C.c_void_p]),
     "fd_rulebook_to_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p]),
     "fd_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),

@@ -96,23 +96,23 @@ def vfe_mean(voxels, num_points, num_feat=None):
 class CoordIndex:
     """Hash (b,z,y,x) -> row for one set of active sites."""
 
-    def __init__(self, coords, n_dev, n_cap, shape):
+    def __init__(self, coords, n_dev, n_cap, shape, batch_size):
         lib = L.load()
         _req(coords, torch.int32, "coords")
         self.cap = _pow2_at_least(2 * max(n_cap, 1))
-        self.keys = torch.empty((self.cap,), dtype=torch.int64, device=coords.device)
-        self.vals = torch.empty((self.cap,), dtype=torch.int32, device=coords.device)
+        self.table = torch.empty((self.cap,), dtype=torch.int64, device=coords.device)   # (key << 32) | row
         self.shape = [int(s) for s in shape]
-        rc = lib.fd_coord_index_build(_ptr(coords), _ptr(n_dev), n_cap, L.i32x3(self.shape), _ptr(self.keys),
-                                      _ptr(self.vals), self.cap, _stream())
+        rc = lib.fd_coord_index_build(_ptr(coords), _ptr(n_dev), n_cap, int(batch_size), L.i32x3(self.shape),
+                                      _ptr(self.table), self.cap, _stream())
         L.check(rc, "fd_coord_index_build")
 
 
 class Rulebook:
     """Gather-form rulebook: nbr [K, n_out_cap] int32 (input row or -1), pair_num [K]."""
 
-    def __init__(self, nbr, pair_num, K, out_coords, n_out_dev, n_out_cap, out_shape, ksize, stride, padding):
-        self.nbr, self.pair_num, self.K = nbr, pair_num, K
+    def __init__(self, nbr, pair_num, K, out_coords, n_out_dev, n_out_cap, out_shape, ksize, stride, padding,
+                 tile_mask=None):
+        self.nbr, self.pair_num, self.K, self.tile_mask = nbr, pair_num, K, tile_mask
         self.out_coords, self.n_out_dev, self.n_out_cap = out_coords, n_out_dev, n_out_cap
         self.out_shape, self.ksize, self.stride, self.padding = out_shape, ksize, stride, padding
 
@@ -137,19 +137,24 @@ def _neighbors(out_coords, n_out_dev, n_out_cap, index, ksize, stride, padding):
     dev = out_coords.device
     nbr = torch.empty((K, max(n_out_cap, 1)), dtype=torch.int32, device=dev)
     pair_num = torch.empty((K,), dtype=torch.int32, device=dev)
-    rc = lib.fd_rulebook_neighbors(_ptr(out_coords), _ptr(n_out_dev), n_out_cap, _ptr(index.keys), _ptr(index.vals),
+    tile_mask = torch.empty(((max(n_out_cap, 1) + 127) // 128,), dtype=torch.int32, device=dev) if K <= 32 else None
+    rc = lib.fd_rulebook_neighbors(_ptr(out_coords), _ptr(n_out_dev), n_out_cap, _ptr(index.table),
                                    index.cap, L.i32x3(index.shape), L.i32x3(ksize), L.i32x3(stride),
-                                   L.i32x3(padding), _ptr(nbr), max(n_out_cap, 1), _ptr(pair_num), _stream())
+                                   L.i32x3(padding), _ptr(nbr), max(n_out_cap, 1), _ptr(pair_num), _ptr(tile_mask),
+                                   _stream())
     L.check(rc, "fd_rulebook_neighbors")
-    return nbr, pair_num, K
+    return nbr, pair_num, K, tile_mask
 
 
-def rulebook_subm(coords, n_dev, n_cap, shape, ksize, index=None):
+def rulebook_subm(coords, n_dev, n_cap, shape, ksize, index=None, batch_size=None):
     """SubMConv3d rulebook: outputs == inputs (same order), centred window."""
-    index = index or CoordIndex(coords, n_dev, n_cap, shape)
+    if index is None:
+        if batch_size is None:
+            raise RuntimeError("rulebook_subm needs batch_size (or a prebuilt CoordIndex)")
+        index = CoordIndex(coords, n_dev, n_cap, shape, batch_size)
     pad = [k // 2 for k in ksize]
-    nbr, pair_num, K = _neighbors(coords, n_dev, n_cap, index, ksize, [1, 1, 1], pad)
-    return Rulebook(nbr, pair_num, K, coords, n_dev, n_cap, list(shape), list(ksize), [1, 1, 1], pad), index
+    nbr, pair_num, K, tmask = _neighbors(coords, n_dev, n_cap, index, ksize, [1, 1, 1], pad)
+    return Rulebook(nbr, pair_num, K, coords, n_dev, n_cap, list(shape), list(ksize), [1, 1, 1], pad, tmask), index
 
 
 def conv_out_shape(shape, ksize, stride, padding):
@@ -177,10 +182,10 @@ def rulebook_conv(coords, n_dev, n_cap, batch_size, shape, ksize, stride, paddin
                                     L.i32x3(stride), L.i32x3(padding), L.i32x3(out_shape), _ptr(bitmap),
                                     _ptr(prefix), _ptr(tmp), _ptr(out_coords), n_out_cap, _ptr(n_out), _stream())
     L.check(rc, "fd_rulebook_out_coords")
-    index = index or CoordIndex(coords, n_dev, n_cap, shape)
-    nbr, pair_num, K = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
+    index = index or CoordIndex(coords, n_dev, n_cap, shape, batch_size)
+    nbr, pair_num, K, tmask = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
     return Rulebook(nbr, pair_num, K, out_coords, n_out, n_out_cap, out_shape, list(ksize), list(stride),
-                    list(padding)), index
+                    list(padding), tmask), index
 
 
 # --------------------------------------------------------------------------- convolution
@@ -344,6 +349,7 @@ def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out
         d.out_map = L.OUTMAP_IDENTITY
     d.mode = L.GATHER_TABLE
     d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
+    d.d_tile_mask = rb.tile_mask.data_ptr() if rb.tile_mask is not None else None
     d.d_n_out = rb.n_out_dev.data_ptr() if rb.n_out_dev is not None else None
     d.n_out_cap = n_cap
     e0 = _prof_begin()

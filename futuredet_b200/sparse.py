@@ -57,7 +57,7 @@ class SparseConvTensor:
 
     def coord_index(self):
         if self._index is None:
-            self._index = ops.CoordIndex(self.indices, self.n_dev, self.n_cap, self.spatial_shape)
+            self._index = ops.CoordIndex(self.indices, self.n_dev, self.n_cap, self.spatial_shape, self.batch_size)
         return self._index
 
     def find_indice_pair(self, key):

@@ -79,12 +79,12 @@ int fd_vfe_mean(const float* d_voxels, const int32_t* d_npts, int64_t M, int S, 
  * kernel offset k (row-major (kz,ky,kx)), or -1.  Cross-correlation:
  * in = out*stride - pad + k.
  *
- * A "coordinate index" is an open-addressing hash  key=((b*D+z)*H+y)*W+x -> row.
- *   d_keys [cap] int64, d_vals [cap] int32, cap = power of two >= 2*rows.
+ * A "coordinate index" is an open-addressing hash  key=((b*D+z)*H+y)*W+x -> row, one 64-bit word per
+ * entry ((key << 32) | row, all-ones = empty): d_table [cap] uint64, cap = power of two >= 2*rows;
+ * B*D*H*W must be < 2^32 - 1.
  */
-int fd_coord_index_build(const int32_t* d_coords4, const int32_t* d_n, int n_cap,
-                         const int32_t* shape3, int64_t* d_keys, int32_t* d_vals, int64_t cap,
-                         void* stream);
+int fd_coord_index_build(const int32_t* d_coords4, const int32_t* d_n, int n_cap, int B,
+                         const int32_t* shape3, uint64_t* d_table, int64_t cap, void* stream);
 
 /* Active output set of a regular (strided) SparseConv3d: every in-bounds out
  * coordinate hit by >=1 active input, ascending linear (b,z,y,x) order
@@ -99,12 +99,14 @@ int fd_rulebook_out_coords(const int32_t* d_in_coords4, const int32_t* d_n_in, i
 
 /* Neighbour table for SubMConv3d (out == in coords, stride 1, pad = k/2) and for
  * SparseConv3d (out coords from fd_rulebook_out_coords).  d_pair_num [K] int32
- * receives the number of pairs per kernel offset (spconv `indice_pair_num`).  */
+ * receives the number of pairs per kernel offset (spconv `indice_pair_num`).
+ * d_tile_mask (optional, [ceil(n_out_cap/128)] uint32, K <= 32): bit k of word t is set when some row of
+ * the 128-row tile t has a neighbour through offset k; fd_conv_forward skips the other offsets.        */
 int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, int n_out_cap,
-                          const int64_t* d_in_keys, const int32_t* d_in_vals, int64_t in_cap,
+                          const uint64_t* d_in_table, int64_t in_cap,
                           const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
                           const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
-                          void* stream);
+                          uint32_t* d_tile_mask, void* stream);
 
 /* Export to the spconv-1.x layout `indice_pairs [K,2,P_cap]` (pairs of offset k
  * listed in ascending output row), for parity checks and interop.            */
@@ -150,6 +152,7 @@ typedef struct fd_conv_desc {
   /* gather mode */
   int32_t        mode;        /* FD_GATHER_* */
   const int32_t* d_nbr;       int32_t nbr_stride;          /* FD_GATHER_TABLE */
+  const uint32_t* d_tile_mask;                             /* FD_GATHER_TABLE, optional (fd_rulebook_neighbors) */
   int32_t B, Hin, Win, Hout, Wout, kh, kw, sh, sw, ph, pw; /* FD_GATHER_CONV2D / _CONVT2D */
   /* output row mapping */
   int32_t        out_map;     /* FD_OUTMAP_* */

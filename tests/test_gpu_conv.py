@@ -39,7 +39,7 @@ def test_subm_conv_fused_epilogue(cuda, prec, tol, cin, cout):
     cap = n + 300
     ct = torch.zeros((cap, 4), dtype=torch.int32, device=cuda); ct[:n] = torch.from_numpy(c).to(cuda)
     nd = torch.tensor([n], dtype=torch.int32, device=cuda)
-    rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3])
+    rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3], batch_size=B)
     xg = torch.zeros((cap, cin), device=cuda); xg[:n] = x.to(cuda)
     rg = torch.zeros((cap, cout), device=cuda); rg[:n] = res.to(cuda)
     if prec != "fp32" and not ops.tc_supported(cin, 27):
@@ -148,7 +148,7 @@ def test_subm_conv_split_format_pipeline(cuda, cin, cout):
     cap = n + 77
     ct = torch.zeros((cap, 4), dtype=torch.int32, device=cuda); ct[:n] = torch.from_numpy(c).to(cuda)
     nd = torch.tensor([n], dtype=torch.int32, device=cuda)
-    rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3])
+    rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3], batch_size=B)
     xg = torch.zeros((cap, cin), device=cuda); xg[:n] = x.to(cuda)
     xs = ops.to_split(xg)
     g1 = ops.sparse_conv(xs, w1.to(cuda), rb, scale.to(cuda), shift.to(cuda), None, True, precision="bf16x3", out_fmt="split")

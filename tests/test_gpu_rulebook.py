@@ -34,11 +34,19 @@ def test_subm_rulebook(cuda, n, extra):
     shape, B = [9, 20, 24], 2
     c = random_sites(rng, B, shape, n)
     ct, nd = dev_coords(c, cuda, extra)
-    rb, _ = ops.rulebook_subm(ct, nd, len(c) + extra, shape, [3, 3, 3])
+    rb, _ = ops.rulebook_subm(ct, nd, len(c) + extra, shape, [3, 3, 3], batch_size=B)
     want = S.subm_rulebook(c, shape, [3, 3, 3])
     got = rb.nbr[:, :len(c)].cpu().numpy()
     assert np.array_equal(got, want)
     assert np.array_equal(rb.pair_num.cpu().numpy(), (want >= 0).sum(1))
+    if len(c):                                                   # per-128-row-tile activity masks
+        tm = rb.tile_mask.cpu().numpy().astype(np.uint32)
+        for t in range((len(c) + 127) // 128):
+            bits = 0
+            for k in range(27):
+                if (want[k, t * 128:(t + 1) * 128] >= 0).any():
+                    bits |= 1 << k
+            assert int(tm[t]) == bits
 
 
 @pytest.mark.parametrize("ksize,stride,pad", [([3, 3, 3], [2, 2, 2], [1, 1, 1]), ([3, 3, 3], [2, 2, 2], [0, 1, 1]),
@@ -75,7 +83,7 @@ def test_backbone_rulebook_chain_on_real_scene(cuda):
              ([3, 1, 1], [2, 1, 1], [0, 0, 0])]
     cur_c, cur_t, cur_n, cur_cap, cur_shape = c, ct, nd, cap, shape
     for li, (k, s, p) in enumerate(geoms):
-        rb, idx = ops.rulebook_subm(cur_t, cur_n, cur_cap, cur_shape, [3, 3, 3])
+        rb, idx = ops.rulebook_subm(cur_t, cur_n, cur_cap, cur_shape, [3, 3, 3], batch_size=1)
         want = S.subm_rulebook(cur_c, cur_shape, [3, 3, 3])
         assert np.array_equal(rb.nbr[:, :len(cur_c)].cpu().numpy(), want), "subm level %d" % li
         rbc, _ = ops.rulebook_conv(cur_t, cur_n, cur_cap, 1, cur_shape, k, s, p, index=idx)
