@@ -105,11 +105,11 @@ class ClockSampler:
                     samples=len(rows), reasons=sorted(reasons))
 
 
-def dist_setup(n_gpus):
+def dist_setup(n_gpus, init):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    if world > 1 and init:
         import torch.distributed as dist
         if not dist.is_initialized():
             dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
@@ -117,12 +117,8 @@ def dist_setup(n_gpus):
 
 
 def barrier_max(value, world, dev):
-    if world == 1:
-        return value
-    import torch.distributed as dist
-    t = torch.tensor([value], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from futuredet_b200 import shard
+    return shard.reduce_throughput(value, 0, device=dev)[1] if world > 1 else value
 
 
 # ----------------------------------------------------------------------------------------- CPU arms
@@ -152,13 +148,17 @@ def run_reference(args, rank, world):
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     full_pts = len(synth_scene(N_TARGET, seed=0))
     budget_s = 170.0
-    # probe with a 1/8 scene to size the per-step sample
-    t_probe, n_probe = cpu_time_scene(sd, N_TARGET // 8, seed=99)
-    est_full = t_probe * 8
-    frac = 1
-    while frac < 8 and est_full / frac * (args.steps + args.warmup) > budget_s:
-        frac *= 2
-    n_target = N_TARGET // frac
+    if os.environ.get("FD_REF_N_TARGET"):          # test hook: tiny scene
+        n_target = int(os.environ["FD_REF_N_TARGET"])
+        frac = max(N_TARGET // n_target, 1)
+    else:
+        # probe with a 1/8 scene to size the per-step sample
+        t_probe, n_probe = cpu_time_scene(sd, N_TARGET // 8, seed=99)
+        est_full = t_probe * 8
+        frac = 1
+        while frac < 8 and est_full / frac * (args.steps + args.warmup) > budget_s:
+            frac *= 2
+        n_target = N_TARGET // frac
     for w in range(args.warmup):
         cpu_time_scene(sd, n_target, seed=1000 + w)
     t_total, pts_total = 0.0, 0
@@ -207,7 +207,7 @@ def conv_profile(model, pts, off):
 
 
 def run_gpu(args, rank, world, local):
-    from futuredet_b200 import lib, neck, sparse
+    from futuredet_b200 import lib, neck, shard, sparse
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -221,7 +221,7 @@ def run_gpu(args, rank, world, local):
     n_pool = 4
     pool_host = []
     for i in range(n_pool):                     # distinct scenes per rank and per pool slot
-        scenes = [synth_scene(N_TARGET, seed=rank * 1000 + i * B + b) for b in range(B)]
+        scenes = [synth_scene(N_TARGET, seed=shard.scene_seed(rank, i, b, B)) for b in range(B)]
         pts = torch.from_numpy(np.concatenate(scenes)).pin_memory()
         off = torch.tensor(np.r_[0, np.cumsum([len(s) for s in scenes])], dtype=torch.int32).pin_memory()
         pool_host.append((pts, off))
@@ -236,15 +236,12 @@ def run_gpu(args, rank, world, local):
     out_host = None
 
     def step_e2e(i):
+        # the public host-buffer API: pinned points -> H2D -> fused forward -> every head tensor D2H into pinned memory
         nonlocal out_host
         flush.zero_()
         p, o = pool_host[i % n_pool]
-        preds = model.forward_points(p.to(dev, non_blocking=True), o.to(dev, non_blocking=True))
-        res = torch.cat([preds[0][h].reshape(B, -1) for h in HEADS], dim=1)      # plumbing: pack the step's result
-        if out_host is None:
-            out_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
-        out_host.copy_(res, non_blocking=True)
-        return res
+        out_host, _ = model.forward_host(p, o, out_host)
+        return out_host
 
     def timed(step_fn):
         for i in range(args.warmup):
@@ -279,11 +276,15 @@ def run_gpu(args, rank, world, local):
     e2e_value = scenes / (ms_e2e / 1e3)
     pk = peaks()
     h2d = int(pool_host[0][0].numel() * 4 + pool_host[0][1].numel() * 4)
-    d2h = int(out_host.numel() * 4)
+    d2h = int(sum(h.numel() for h in out_host) * 4)
     achieved = prof["flop"] / max(prof["ms"], 1e-9) / 1e9      # TFLOP/s
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "r1_traffic.json")      # dram bytes of the same kernels from one ncu capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("conv_family_dram_bytes_per_step")
     roofline = dict(bound="tensor", kernel="gather->implicit-GEMM conv family (%s), %d launches/step" %
                     (args.precision, prof["launches"]), achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s",
-                    frac=achieved / pk["tf_sustained"], traffic=None, peak_source=pk["src"] + " bf16 dense, sustained",
+                    frac=achieved / pk["tf_sustained"], traffic=traffic, peak_source=pk["src"] + " bf16 dense, sustained",
                     algorithmic_gflop_per_step=prof["flop"] / 1e9, kernel_ms_per_step=prof["ms"], by_kind=prof["by_kind"])
     cpu_t, cpu_n = cpu_time_scene(sd_cpu, N_TARGET, seed=0)
     cpu_baseline = dict(value=1.0 / cpu_t, unit="scenes/s", cores=torch.get_num_threads(), kind="port",
@@ -310,16 +311,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="scenes per step per GPU (reference: samples_per_gpu=1)")
-    ap.add_argument("--precision", default=os.environ.get("FD_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("FD_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
+                    help="bf16x3 (default): tcgen05 tensor cores with a 3-term bf16 split, holds the 1e-3 parity contract; "
+                         "fp32: CUDA-core exact arm; bf16: single pass, outside the parity contract")
     args = ap.parse_args()
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_setup(args.gpus, init=args.impl != "reference")
     if args.impl == "reference":
         if args.steps > 3 and "--steps" not in sys.argv:
             args.steps, args.warmup = 3, 1
-        run_reference(args, rank, world)
-    else:
-        args.warmup = max(args.warmup, 3)
-        run_gpu(args, rank, world, local)
+        run_reference(args, rank, world)        # rank 0 alone; no process group needed
+        return
+    args.warmup = max(args.warmup, 3)
+    run_gpu(args, rank, world, local)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

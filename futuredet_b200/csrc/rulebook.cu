@@ -183,6 +183,58 @@ neighbors_kernel(const int4* __restrict__ out_coords, const int32_t* __restrict_
   }
 }
 
+// Same neighbour search against a BITMAP index: the active set of a strided conv's output grid is already available
+// as (1 bit per cell, exclusive popcount prefix per word) from fd_rulebook_out_coords, and its rows are in ascending
+// linear order, so  row(cell) = prefix[word] + popc(bits below).  The three x-neighbours of a (kz,ky) pair share one
+// or two words, so a row needs ~9 word loads with high locality instead of 27 random hash probes.
+__global__ void __launch_bounds__(256)
+neighbors_bitmap_kernel(const int4* __restrict__ out_coords, const int32_t* __restrict__ d_n, int n_cap,
+                        const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ prefix, Shape3 ish, Conv3Geom g,
+                        int* __restrict__ nbr, int nbr_stride, int* __restrict__ pair_num, uint32_t* __restrict__ tile_mask) {
+  const int n = d_n ? min(*d_n, n_cap) : n_cap;
+  const int lane = threadIdx.x & 31;
+  const int n_round = (n + 31) & ~31;
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_round; o += gridDim.x * blockDim.x) {
+    const bool live = o < n;
+    int4 c = live ? out_coords[o] : make_int4(0, 0, 0, 0);
+    const int z0 = c.y * g.s[0] - g.p[0], y0 = c.z * g.s[1] - g.p[1], x0 = c.w * g.s[2] - g.p[2];
+    uint32_t my_mask = 0;
+    int k = 0;
+    for (int kz = 0; kz < g.k[0]; ++kz) {
+      const int z = z0 + kz;
+      for (int ky = 0; ky < g.k[1]; ++ky) {
+        const int y = y0 + ky;
+        const bool rowok = live && z >= 0 && z < ish.d && y >= 0 && y < ish.h;
+        const long long lin0 = lin_key(c.x, z, y, 0, ish);       // cell (x = 0) of this line
+        long long cached_w = -1;
+        uint32_t bits = 0;
+        int base = 0;
+        for (int kx = 0; kx < g.k[2]; ++kx, ++k) {
+          const int x = x0 + kx;
+          int r = -1;
+          if (rowok && x >= 0 && x < ish.w) {
+            const long long lin = lin0 + x;
+            const long long w = lin >> 5;
+            if (w != cached_w) { cached_w = w; bits = __ldg(bitmap + w); base = -1; }
+            const uint32_t bit = 1u << (lin & 31);
+            if (bits & bit) {
+              if (base < 0) base = __ldg(prefix + w);
+              r = base + __popc(bits & (bit - 1));
+            }
+          }
+          if (live) nbr[(size_t)k * nbr_stride + o] = r;
+          unsigned m = __ballot_sync(0xffffffffu, r >= 0);
+          if (m) {
+            if (lane == 0) atomicAdd(&pair_num[k], __popc(m));
+            my_mask |= 1u << (k & 31);
+          }
+        }
+      }
+    }
+    if (tile_mask && lane == 0 && my_mask) atomicOr(&tile_mask[o >> 7], my_mask);
+  }
+}
+
 // ---- export to spconv layout ----------------------------------------------------
 struct LoadValid {
   const int* nbr;
@@ -301,6 +353,32 @@ int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, 
   neighbors_kernel<<<persistent_grid(ceil_div(n_out_cap, 256), 8), 256, 0, stream>>>(
       (const int4*)d_out_coords4, d_n_out, n_out_cap, (const unsigned long long*)d_in_table,
       (uint32_t)(in_cap - 1), ish, g, d_nbr, nbr_stride, d_pair_num, d_tile_mask);
+  FD_LAUNCHED();
+  return 0;
+}
+
+int fd_rulebook_neighbors_bitmap(const int32_t* d_out_coords4, const int32_t* d_n_out, int n_out_cap,
+                                 const uint32_t* d_in_bitmap, const int32_t* d_in_wordprefix, const int32_t* in_shape3,
+                                 const int32_t* ksize3, const int32_t* stride3, const int32_t* pad3, int32_t* d_nbr,
+                                 int nbr_stride, int32_t* d_pair_num, uint32_t* d_tile_mask, void* stream_) {
+  using namespace fd;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FD_REQUIRE(d_out_coords4 && d_in_bitmap && d_in_wordprefix && in_shape3 && ksize3 && stride3 && pad3 && d_nbr &&
+                 d_pair_num,
+             "fd_rulebook_neighbors_bitmap: null argument");
+  FD_REQUIRE(nbr_stride >= n_out_cap, "fd_rulebook_neighbors_bitmap: nbr_stride < n_out_cap");
+  Conv3Geom g;
+  for (int j = 0; j < 3; ++j) { g.k[j] = ksize3[j]; g.s[j] = stride3[j]; g.p[j] = pad3[j]; }
+  const int K = g.k[0] * g.k[1] * g.k[2];
+  FD_REQUIRE(K >= 1 && K <= 343, "fd_rulebook_neighbors_bitmap: kernel volume %d unsupported", K);
+  FD_REQUIRE(!d_tile_mask || K <= 32, "fd_rulebook_neighbors_bitmap: tile masks support at most 32 kernel offsets");
+  FD_CUDA(cudaMemsetAsync(d_pair_num, 0, sizeof(int32_t) * K, stream));
+  if (d_tile_mask) FD_CUDA(cudaMemsetAsync(d_tile_mask, 0, sizeof(uint32_t) * (size_t)ceil_div(n_out_cap > 0 ? n_out_cap : 1, 128), stream));
+  if (n_out_cap <= 0) return 0;
+  Shape3 ish{in_shape3[0], in_shape3[1], in_shape3[2]};
+  neighbors_bitmap_kernel<<<persistent_grid(ceil_div(n_out_cap, 256), 8), 256, 0, stream>>>(
+      (const int4*)d_out_coords4, d_n_out, n_out_cap, d_in_bitmap, d_in_wordprefix, ish, g, d_nbr, nbr_stride,
+      d_pair_num, d_tile_mask);
   FD_LAUNCHED();
   return 0;
 }

@@ -117,6 +117,37 @@ class VoxelNet(SingleStageDetector):
         return ops.voxelize_vfe(points, batch_offsets, c["voxel_size"], c["range"], c["max_points"], c["max_voxels"],
                                 num_feat=nf, feat_stride=(nf + 7) // 8 * 8)
 
+    def forward_host(self, points_host, batch_offsets_host, out_host=None):
+        """End-to-end entry for host-resident inputs: pinned `points_host [sum N, >=5]` fp32 and `batch_offsets_host
+        [B+1]` int32 are copied to the module's device, the fused forward runs, and every head tensor of every task is
+        copied back into one pinned host tensor `[B, H, W, sum c]` (returned with the per-head channel ranges).
+        Nothing synchronises until the caller touches the result (`torch.cuda.current_stream().synchronize()`)."""
+        dev = next(self.parameters()).device
+        pts = points_host.to(dev, non_blocking=True)
+        off = batch_offsets_host.to(dev, non_blocking=True)
+        preds = self.forward_points(pts, off)
+        outs, layout = [], []
+        for t_id, p in enumerate(preds):
+            for name, v in p.items():
+                base = v.permute(0, 2, 3, 1)                    # channels-last view of the head's result buffer
+                layout.append((t_id, name, v.shape[1]))
+                outs.append(base)
+        # all heads of a task are channel slices of one buffer: copy that buffer once per task
+        bufs = []
+        seen = set()
+        for v in outs:
+            key = v.untyped_storage().data_ptr()
+            if key not in seen:
+                seen.add(key)
+                bufs.append(v.as_strided((v.shape[0], v.shape[1], v.shape[2], v.stride(2)),
+                                         (v.stride(0), v.stride(1), v.stride(2), 1),
+                                         v.storage_offset() - v.storage_offset() % v.stride(2)))
+        if out_host is None:
+            out_host = [torch.empty(b.shape, dtype=b.dtype).pin_memory() for b in bufs]
+        for h, b in zip(out_host, bufs):
+            h.copy_(b, non_blocking=True)
+        return out_host, layout
+
     def forward_points(self, points, batch_offsets, return_voxels=False):
         """points [sum N, >=5] fp32 CUDA, batch_offsets [B+1] int32 CUDA -> CenterHead predictions."""
         c = self.voxel_cfg

@@ -107,6 +107,14 @@ class CoordIndex:
         L.check(rc, "fd_coord_index_build")
 
 
+class BitmapIndex:
+    """Coordinate index of a strided conv's output set: 1 bit per cell + exclusive popcount prefix per 32-bit word
+    (left behind by fd_rulebook_out_coords); rows of the set are in ascending linear order, so row == rank."""
+
+    def __init__(self, bitmap, prefix, shape):
+        self.bitmap, self.prefix, self.shape = bitmap, prefix, [int(s) for s in shape]
+
+
 class Rulebook:
     """Gather-form rulebook: nbr [K, n_out_cap] int32 (input row or -1), pair_num [K]."""
 
@@ -138,6 +146,13 @@ def _neighbors(out_coords, n_out_dev, n_out_cap, index, ksize, stride, padding):
     nbr = torch.empty((K, max(n_out_cap, 1)), dtype=torch.int32, device=dev)
     pair_num = torch.empty((K,), dtype=torch.int32, device=dev)
     tile_mask = torch.empty(((max(n_out_cap, 1) + 127) // 128,), dtype=torch.int32, device=dev) if K <= 32 else None
+    if isinstance(index, BitmapIndex):
+        rc = lib.fd_rulebook_neighbors_bitmap(_ptr(out_coords), _ptr(n_out_dev), n_out_cap, _ptr(index.bitmap),
+                                              _ptr(index.prefix), L.i32x3(index.shape), L.i32x3(ksize), L.i32x3(stride),
+                                              L.i32x3(padding), _ptr(nbr), max(n_out_cap, 1), _ptr(pair_num),
+                                              _ptr(tile_mask), _stream())
+        L.check(rc, "fd_rulebook_neighbors_bitmap")
+        return nbr, pair_num, K, tile_mask
     rc = lib.fd_rulebook_neighbors(_ptr(out_coords), _ptr(n_out_dev), n_out_cap, _ptr(index.table),
                                    index.cap, L.i32x3(index.shape), L.i32x3(ksize), L.i32x3(stride),
                                    L.i32x3(padding), _ptr(nbr), max(n_out_cap, 1), _ptr(pair_num), _ptr(tile_mask),
@@ -184,8 +199,10 @@ def rulebook_conv(coords, n_dev, n_cap, batch_size, shape, ksize, stride, paddin
     L.check(rc, "fd_rulebook_out_coords")
     index = index or CoordIndex(coords, n_dev, n_cap, shape, batch_size)
     nbr, pair_num, K, tmask = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
-    return Rulebook(nbr, pair_num, K, out_coords, n_out, n_out_cap, out_shape, list(ksize), list(stride),
-                    list(padding), tmask), index
+    rb = Rulebook(nbr, pair_num, K, out_coords, n_out, n_out_cap, out_shape, list(ksize), list(stride),
+                  list(padding), tmask)
+    rb.out_index = BitmapIndex(bitmap, prefix, out_shape)      # index of the OUTPUT set for the layers that follow
+    return rb, index
 
 
 # --------------------------------------------------------------------------- convolution

@@ -167,7 +167,9 @@ class _SparseConvBase(SparseModule):
         y = ops.sparse_conv(xin, w, rb, scale, shift, residual, relu, precision=prec, out_fmt=out_fmt)
         if self.subm:
             return x._like(y)
-        return x._like(y, rb.out_coords, rb.out_shape, rb.n_out_dev, rb.n_out_cap)
+        out = x._like(y, rb.out_coords, rb.out_shape, rb.n_out_dev, rb.n_out_cap)
+        out._index = getattr(rb, "out_index", None)       # bitmap index of the new active set (no hash build needed)
+        return out
 
 
 class SubMConv3d(_SparseConvBase):

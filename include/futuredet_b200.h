@@ -108,6 +108,15 @@ int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, 
                           const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
                           uint32_t* d_tile_mask, void* stream);
 
+/* Same search against the bitmap + per-word popcount prefix that fd_rulebook_out_coords left behind for a
+ * strided conv's OUTPUT set (rows of that set are in ascending linear order, so row = rank): use it as the
+ * coordinate index of every later layer at that resolution instead of building a hash.                    */
+int fd_rulebook_neighbors_bitmap(const int32_t* d_out_coords4, const int32_t* d_n_out, int n_out_cap,
+                                 const uint32_t* d_in_bitmap, const int32_t* d_in_wordprefix,
+                                 const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
+                                 const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
+                                 uint32_t* d_tile_mask, void* stream);
+
 /* Export to the spconv-1.x layout `indice_pairs [K,2,P_cap]` (pairs of offset k
  * listed in ascending output row), for parity checks and interop.            */
 int fd_rulebook_to_pairs(const int32_t* d_nbr, int nbr_stride, const int32_t* d_n_out, int n_out_cap,
@@ -186,6 +195,26 @@ int fd_sparse_to_dense_ncdhw(const float* d_feat, int feat_stride, int C, const 
 int fd_convert_rows(const void* d_src, int src_format, int src_stride, int src_ctot, void* d_dst,
                     int dst_format, int dst_stride, int dst_ctot, int C, const int32_t* d_n, int64_t n_cap,
                     void* stream);
+
+/* ---- CenterHead.loss forward (standard branch) ----------------------------------------------------
+ * Replaces det3d/models/bbox_heads/center_head.py:396-539 (+ _sigmoid :392-394, in place on d_hm),
+ * det3d/models/losses/centernet_loss.py:18-25,75-95 and det3d/core/utils/center_utils.py:66-80.
+ *   d_hm        heat-map logits of one task, element (b,c,s) at d_hm[b*hm_sb + c*hm_sc + s*hm_ssp], s = y*W + x;
+ *               overwritten with clamp(sigmoid(x), 1e-4, 1-1e-4) as the reference does
+ *   d_hm_target [B,C,H,W] fp32 ; d_ind / d_cat [B,M] int64 ; d_mask [B,M] uint8 (timestep 0, as the reference uses)
+ *   d_mask_t    [T] device pointers to the per-timestep masks (only for `num_positive`)
+ *   d_pred_ptr / d_pred_sb / d_pred_ssp  [T*NC]: channel c of timestep t of anno_box = cat(reg,height,dim,
+ *               vel[2t:2t+2],rot) lives at ptr[b*sb + s*ssp]
+ *   d_tgt_ptr   [T] pointers to anno_box targets [B,M,tgt_dim]; d_tgt_sel [NC] = columns [0..7,-2,-1]
+ *   d_out       [3 + T + T*NC] fp32: loss, hm_loss, num_positive, loc_loss[T], loc_loss_elem[T][NC]            */
+size_t fd_center_loss_workspace_bytes(void);
+int fd_center_head_loss(float* d_hm, int64_t hm_sb, int64_t hm_sc, int64_t hm_ssp, const float* d_hm_target,
+                        int B, int C, int H, int W, const int64_t* d_ind, const uint8_t* d_mask,
+                        const int64_t* d_cat, const uint8_t* const* d_mask_t, int M, int T, int NC,
+                        const float* const* d_pred_ptr, const int64_t* d_pred_sb, const int64_t* d_pred_ssp,
+                        const float* const* d_tgt_ptr, int tgt_dim, const int32_t* d_tgt_sel,
+                        const float* d_code_w, const float* d_code_w_forecast, float weight, float* d_out,
+                        void* d_workspace, void* stream);
 
 /* small helpers used by the host layer */
 int fd_fill_i32(int32_t* d_ptr, int64_t n, int32_t value, void* stream);

@@ -117,3 +117,50 @@ def test_voxelnet_forward_points_matches_chained_oracle(cuda, timesteps, precisi
     p2 = m.bbox_head(x)
     for k in want[0]:
         torch.testing.assert_close(p2[0][k], preds[0][k], rtol=1e-4, atol=1e-4)   # API path re-rounds at module boundaries
+
+
+def test_center_head_loss_matches_reference_golden(cuda, golden_dir):
+    """CenterHead.loss (focal + masked-L1, 3 forecast timesteps) vs the reference's own `head.loss` output."""
+    g = torch.load(os.path.join(golden_dir, "neck_head.pt"), weights_only=False)
+    head = fb.build_head(dict(g["head_cfg"])).eval()
+    preds = [{k: v.clone().to(cuda) for k, v in p.items()} for p in g["preds"]]       # reference predictions (NCHW)
+    ex = {k: [[t.to(cuda) for t in ts] for ts in v] for k, v in g["example"].items()}
+    out = head.loss(ex, preds)
+    ref = g["loss"]
+    torch.testing.assert_close(out["loss"][0].cpu(), ref["loss"][0], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out["hm_loss"][0], ref["hm_loss"][0], rtol=1e-4, atol=1e-5)
+    for a, b in zip(out["loc_loss"][0], ref["loc_loss"][0]):
+        torch.testing.assert_close(a.cpu(), b, rtol=1e-4, atol=1e-5)
+    for a, b in zip(out["loc_loss_elem"][0], ref["loc_loss_elem"][0]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    assert float(out["num_positive"][0]) == float(ref["num_positive"][0])
+    # in-place _sigmoid side effect of the reference (center_head.py:392-394,402)
+    want_hm = torch.clamp(torch.sigmoid(g["preds"][0]["hm"]), 1e-4, 1 - 1e-4)
+    torch.testing.assert_close(preds[0]["hm"].cpu(), want_hm, rtol=1e-5, atol=1e-6)
+    # and on the head's own channels-last outputs (strided views)
+    neck = fb.build_neck(dict(g["neck_cfg"])).eval()
+    neck.load_state_dict(g["neck_state"]); head.load_state_dict(g["head_state"])
+    neck.to(cuda); head.to(cuda)
+    preds2 = head(neck(g["x"].to(cuda)))
+    out2 = head.loss(ex, preds2)
+    torch.testing.assert_close(out2["loss"][0].cpu(), ref["loss"][0], rtol=1e-3, atol=1e-3)
+
+
+def test_forward_host_matches_forward_points(cuda):
+    """Host-buffer entry (pinned points in, pinned head tensors out) == device entry."""
+    m = build_model(7, cuda).to(cuda)
+    m.configure_voxelizer(dict(range=NUSC_RANGE, voxel_size=NUSC_VOXEL, max_points_in_voxel=10,
+                               max_voxel_num=[120000, 160000]))
+    scene = synth_scene(20000, seed=11)
+    pts_h = torch.from_numpy(scene).pin_memory()
+    off_h = torch.tensor([0, len(scene)], dtype=torch.int32).pin_memory()
+    outs, layout = m.forward_host(pts_h, off_h)
+    torch.cuda.synchronize()
+    preds = m.forward_points(pts_h.to(cuda), off_h.to(cuda))
+    assert len(outs) == 1 and outs[0].is_pinned() and outs[0].shape == (1, 180, 180, 23)
+    col = 0
+    for t_id, name, c in layout:
+        want = preds[t_id][name].permute(0, 2, 3, 1).cpu()
+        torch.testing.assert_close(outs[0][..., col:col + c], want, rtol=0, atol=0)
+        col += c
+    assert [n for _, n, _ in layout] == ["reg", "height", "dim", "rot", "vel", "hm"]

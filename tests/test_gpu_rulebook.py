@@ -82,8 +82,10 @@ def test_backbone_rulebook_chain_on_real_scene(cuda):
     geoms = [([3, 3, 3], [2, 2, 2], [1, 1, 1]), ([3, 3, 3], [2, 2, 2], [1, 1, 1]), ([3, 3, 3], [2, 2, 2], [0, 1, 1]),
              ([3, 1, 1], [2, 1, 1], [0, 0, 0])]
     cur_c, cur_t, cur_n, cur_cap, cur_shape = c, ct, nd, cap, shape
+    cur_index = None                                   # level 0: hash index; levels >= 1: bitmap index of the out set
     for li, (k, s, p) in enumerate(geoms):
-        rb, idx = ops.rulebook_subm(cur_t, cur_n, cur_cap, cur_shape, [3, 3, 3], batch_size=1)
+        rb, idx = ops.rulebook_subm(cur_t, cur_n, cur_cap, cur_shape, [3, 3, 3], index=cur_index, batch_size=1)
+        assert (li == 0) == isinstance(idx, ops.CoordIndex)
         want = S.subm_rulebook(cur_c, cur_shape, [3, 3, 3])
         assert np.array_equal(rb.nbr[:, :len(cur_c)].cpu().numpy(), want), "subm level %d" % li
         rbc, _ = ops.rulebook_conv(cur_t, cur_n, cur_cap, 1, cur_shape, k, s, p, index=idx)
@@ -93,4 +95,5 @@ def test_backbone_rulebook_chain_on_real_scene(cuda):
         assert np.array_equal(rbc.out_coords[:n_out].cpu().numpy(), oc), "out coords level %d" % li
         assert np.array_equal(rbc.nbr[:, :n_out].cpu().numpy(), nbr), "conv nbr level %d" % li
         cur_c, cur_t, cur_n, cur_cap, cur_shape = oc, rbc.out_coords, rbc.n_out_dev, rbc.n_out_cap, oshape
+        cur_index = rbc.out_index
     assert cur_shape == [2, 180, 180]

@@ -1,0 +1,67 @@
+"""CPU, world_size 2 over gloo: the host-side multi-GPU logic (scene sharding + throughput reduction) and the
+bench.py --impl reference contract under a multi-rank launch (rank 0 prints, other ranks exit 0 silently)."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from futuredet_b200 import shard
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = shard.shard_indices(11, rank, world)
+    seeds = [shard.scene_seed(rank, s, b, 2) for s in range(4) for b in range(2)]
+    # rank 1 is "slower": whole-job throughput must use the max time and the summed scenes
+    value, t_max, units = shard.reduce_throughput(100.0 if rank == 0 else 250.0, len(mine))
+    q.put((rank, mine, seeds, value, t_max, units))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scene_sharding_and_throughput_reduction_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, m0, s0, v0, t0, u0), (r1, m1, s1, v1, t1, u1) = res
+    assert sorted(m0 + m1) == list(range(11)) and not set(m0) & set(m1)          # every scene exactly once
+    assert not set(s0) & set(s1)                                                 # replicas never share a scene
+    assert t0 == t1 == 250.0 and u0 == u1 == 11.0
+    assert abs(v0 - 11 / 0.25) < 1e-9 and v0 == v1
+
+
+def test_single_process_reduce_is_identity():
+    v, t, u = shard.reduce_throughput(50.0, 4)
+    assert (v, t, u) == (80.0, 50.0, 4.0)
+
+
+def test_bench_reference_arm_contract_two_ranks():
+    """`bench.py --impl reference` under a 2-rank launch: rank 0 prints one JSON line, rank 1 exits 0 without work."""
+    env = dict(os.environ, FD_REF_N_TARGET="6000", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", WORLD_SIZE="2")
+    outs = []
+    for rank in (1, 0):
+        r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                            "--warmup", "0"], env=dict(env, RANK=str(rank), LOCAL_RANK=str(rank)), capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == ""
+    line = json.loads(outs[1].splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "scenes/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["higher_is_better"] is True and line["n_gpus"] == 2
