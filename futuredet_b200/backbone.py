@@ -94,6 +94,13 @@ class SpMiddleResNetFHD(nn.Module):
         x_conv2 = self.conv2(x_conv1)
         x_conv3 = self.conv3(x_conv2)
         x_conv4 = self.conv4(x_conv3)
-        bev = self.extra_conv(x_conv4, bev_last=True, out_fmt=out_fmt)   # [B, H, W, C*D] channels-last, channel = c*D + d
-        ret = bev if out_fmt == "split" else bev.permute(0, 3, 1, 2)    # logical [B, C*D, H, W] as scn.py:167-168
+        # [B, H, W, C*D] channels-last; channel = c*D + d as scn.py:165-168, except on the fused split path where the
+        # rows are written d-major (channel = d*C + c, contiguous vector stores) and tagged so that the consumer
+        # (RPN) permutes its first conv's input channels accordingly
+        dmajor = out_fmt == "split"
+        bev = self.extra_conv(x_conv4, bev_last=True, out_fmt=out_fmt, bev_dmajor=dmajor)
+        if dmajor:
+            c_out = self.extra_conv[0].out_channels
+            bev.bev_dmajor = (c_out, bev.ctot // c_out)
+        ret = bev if out_fmt == "split" else bev.permute(0, 3, 1, 2)    # logical [B, C*D, H, W]
         return ret, {"conv1": x_conv1, "conv2": x_conv2, "conv3": x_conv3, "conv4": x_conv4}

@@ -69,7 +69,7 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
   a.out_map = d->out_map;
   a.out_coords = (const int4*)d->d_out_coords4; a.bevD = d->bevD; a.bevH = d->bevH; a.bevW = d->bevW;
 
-  if (d->out_map == FD_OUTMAP_BEV) {
+  if (d->out_map == FD_OUTMAP_BEV || d->out_map == FD_OUTMAP_BEV_DMAJOR) {
     FD_REQUIRE(d->d_out_coords4 && d->bevD >= 1 && d->bevH >= 1 && d->bevW >= 1,
                "fd_conv_forward: FD_OUTMAP_BEV needs out coords and bev dims");
     FD_REQUIRE(d->out_stride >= d->cout * d->bevD && a.out_ctot >= d->cout * d->bevD,

@@ -67,6 +67,11 @@ __device__ __forceinline__ OutRow map_out_row(const ConvArgs& a, int o) {
     size_t pix = ((size_t)c.x * a.bevH + c.z) * a.bevW + c.w;
     return {a.out + pix * a.out_stride, c.y, a.bevD};
   }
+  if (a.out_map == FD_OUTMAP_BEV_DMAJOR) {
+    int4 c = a.out_coords[o];
+    size_t pix = ((size_t)c.x * a.bevH + c.z) * a.bevW + c.w;
+    return {a.out + pix * a.out_stride, c.y * a.cout, 1};
+  }
   // OUTMAP_UPSAMPLE: o = (b, y, x) on the input grid -> (b, y*s+dy, x*s+dx) on the output grid
   int hw = a.Hin * a.Win;
   int b = o / hw;

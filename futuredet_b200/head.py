@@ -89,6 +89,25 @@ class SepHead(nn.Module):
             cache["k"] = key
         return cache["v"]
 
+    def _fused_last(self, groups):
+        """Block-diagonal [K, n_heads*head_conv, sum c] weight + bias of the final conv of every head (one launch
+        instead of n_heads tiny ones); cached on parameter versions."""
+        lasts = [groups[h][1][0] for h in self.heads]
+        key = tuple((c.weight.data_ptr(), c.weight._version, c.bias._version) for c in lasts)
+        cache = self.__dict__.setdefault("_fused_last_cache", {})
+        if cache.get("k") != key:
+            ws = [conv_weight_kio(c) for c in lasts]
+            K, hc = ws[0].shape[0], ws[0].shape[1]
+            total = sum(w.shape[2] for w in ws)
+            wbd = torch.zeros((K, hc * len(ws), total), dtype=torch.float32, device=ws[0].device)
+            col = 0
+            for i, w in enumerate(ws):
+                wbd[:, i * hc:(i + 1) * hc, col:col + w.shape[2]] = w
+                col += w.shape[2]
+            bias = torch.cat([c.bias.detach().float() for c in lasts]).contiguous()
+            cache["k"], cache["v"] = key, (wbd.contiguous(), bias)
+        return cache["v"]
+
     def forward(self, x, precision=None):
         """x: channels-last [B,H,W,C] tensor / ops.Feat (or logical NCHW tensor).  Returns {head: logical [B,c,H,W]}
         fp32 views of one channels-last [B,H,W,sum c] result tensor."""
@@ -112,13 +131,26 @@ class SepHead(nn.Module):
             c0 = groups[names[0]][0][0]
             mid = ops.as_feat(ops.conv2d_nhwc(x, w, c0.kernel_size, c0.stride, c0.padding, sc, sh, True, precision=prec,
                                               out_fmt=fmt))
-            hc = c0.out_channels
-            for i, h in enumerate(names):
-                conv, bnm, relu = groups[h][1]
-                c = conv.out_channels
-                run_conv(mid.slice(i * hc, hc), conv, bnm, relu, out=out.slice(col, c), precision=prec)
-                ret[h] = out.t[..., col:col + c].permute(0, 3, 1, 2)
-                col += c
+            lasts = [groups[h][1] for h in names]
+            same = (len({(c.kernel_size, c.stride, c.padding) for c, _, _ in lasts}) == 1
+                    and all(b is None and not r for _, b, r in lasts))
+            if same:
+                # final convs of all heads as ONE block-diagonal conv over the fused activation (n_heads*64 -> sum c)
+                wbd, bias = self._fused_last(groups)
+                cl = lasts[0][0]
+                ops.conv2d_nhwc(mid, wbd, cl.kernel_size, cl.stride, cl.padding, None, bias, False, out=out, precision=prec)
+                for h in names:
+                    c = self.heads[h][0]
+                    ret[h] = out.t[..., col:col + c].permute(0, 3, 1, 2)
+                    col += c
+            else:
+                hc = c0.out_channels
+                for i, h in enumerate(names):
+                    conv, bnm, relu = groups[h][1]
+                    c = conv.out_channels
+                    run_conv(mid.slice(i * hc, hc), conv, bnm, relu, out=out.slice(col, c), precision=prec)
+                    ret[h] = out.t[..., col:col + c].permute(0, 3, 1, 2)
+                    col += c
         else:
             for h in names:
                 y = x

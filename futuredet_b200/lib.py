@@ -41,7 +41,7 @@ class ConvDesc(C.Structure):
 
 
 GATHER_TABLE, GATHER_CONV2D, GATHER_CONVT2D = 0, 1, 2
-OUTMAP_IDENTITY, OUTMAP_BEV = 0, 1
+OUTMAP_IDENTITY, OUTMAP_BEV, OUTMAP_BEV_DMAJOR = 0, 1, 2
 PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 

@@ -50,7 +50,19 @@ def act_fmt(precision=None):
     return "fp32" if (precision or DEFAULT_PRECISION) == "fp32" else "split"
 
 
-def run_conv(x, conv, bn, relu, out=None, pad=None, precision=None, out_fmt=None):
+def conv_weight_kio_dmajor(conv, C, D):
+    """Weight for an input whose channels arrive d-major (j = d*C + c) instead of the reference's c*D + d."""
+    w = conv_weight_kio(conv)
+    key = (w.data_ptr(), C, D)
+    cache = conv.__dict__.setdefault("_kio_dmajor_cache", {})
+    if cache.get("k") != key:
+        j = torch.arange(C * D, device=w.device)
+        cache["v"] = w[:, (j % C) * D + j // C, :].contiguous()
+        cache["k"] = key
+    return cache["v"]
+
+
+def run_conv(x, conv, bn, relu, out=None, pad=None, precision=None, out_fmt=None, dmajor=None):
     """x channels-last [B,H,W,C] (tensor or ops.Feat) -> fused conv(+bias)+BN(eval)+ReLU."""
     scale, shift = folded_epilogue(conv, bn)
     transposed = isinstance(conv, nn.ConvTranspose2d)
@@ -58,7 +70,8 @@ def run_conv(x, conv, bn, relu, out=None, pad=None, precision=None, out_fmt=None
     prec = precision or DEFAULT_PRECISION
     if prec != "fp32" and conv.in_channels % 8 != 0:
         prec = "fp32"
-    return ops.conv2d_nhwc(x, conv_weight_kio(conv), conv.kernel_size, conv.stride, padding, scale, shift, relu,
+    w = conv_weight_kio(conv) if dmajor is None else conv_weight_kio_dmajor(conv, *dmajor)
+    return ops.conv2d_nhwc(x, w, conv.kernel_size, conv.stride, padding, scale, shift, relu,
                            out=out, precision=prec, transposed=transposed,
                            out_fmt=out_fmt or act_fmt(prec))
 
@@ -138,6 +151,7 @@ class RPN(nn.Module):
         """x logical [B,C,H,W] (or a channels-last ops.Feat) -> logical [B, sum(us_num_filters), H', W']
         (channels-last memory); out_fmt="split" (fused pipeline) returns a split-row ops.Feat [B,H',W',C]."""
         fmt = act_fmt()
+        dmajor = getattr(x, "bev_dmajor", None)          # set by the fused backbone (channel = d*C + c)
         x = as_nhwc_feat(x, fmt)
         B = x.t.shape[0]
         final_fmt = out_fmt if fmt == "split" else "fp32"
@@ -146,7 +160,7 @@ class RPN(nn.Module):
         n_up = len(self.deblocks)
         for i, block in enumerate(self.blocks):
             mods = list(block)
-            x = ops.as_feat(run_conv(x, mods[1], mods[2], True, pad=(1, 1)))          # ZeroPad2d(1) + conv(pad 0)
+            x = ops.as_feat(run_conv(x, mods[1], mods[2], True, pad=(1, 1), dmajor=dmajor if i == 0 else None))   # ZeroPad2d(1) + conv(pad 0)
             for k in range(4, len(mods), 3):
                 x = ops.as_feat(run_conv(x, mods[k], mods[k + 1], True))
             j = i - self._upsample_start_idx

@@ -334,7 +334,7 @@ def _conv_desc(x, cin, w, scale, shift, residual, relu, out, precision, separate
 
 
 def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out=None, precision="fp32",
-                bev=None, out_fmt="fp32"):
+                bev=None, out_fmt="fp32", bev_dmajor=False):
     """out[o] = act((sum_k x[nbr[k,o]] @ w[k]) * scale + shift (+ residual[o])).
 
     x / residual / out: torch fp32 tensors or Feat views (fp32 or split rows); w [K, Cin, Cout] fp32; rb: Rulebook.
@@ -356,7 +356,7 @@ def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out
             out = Feat(torch.zeros((B, H, Wd, cout * D), dtype=torch.float32, device=x.t.device), out_fmt)
         out = as_feat(out)
         d = _conv_desc(x, cin, w, scale, shift, None, relu, out, precision)
-        d.out_map = L.OUTMAP_BEV
+        d.out_map = L.OUTMAP_BEV_DMAJOR if bev_dmajor else L.OUTMAP_BEV
         d.d_out_coords4 = rb.out_coords.data_ptr(); d.bevD, d.bevH, d.bevW = D, H, Wd
     else:
         if out is None:

@@ -143,7 +143,7 @@ class _SparseConvBase(SparseModule):
             x.indice_dict[self.indice_key] = rb
         return rb
 
-    def forward(self, x, bn=None, residual=None, relu=False, bev=False, out_fmt=None):
+    def forward(self, x, bn=None, residual=None, relu=False, bev=False, out_fmt=None, bev_dmajor=False):
         """out = act(bn(conv(x) [+bias]) [+ residual]); `bn` is an eval-mode BatchNorm1d folded into the epilogue.
         Tensor-core precisions keep activations in the split bf16 hi/lo row format between layers."""
         rb = self.rulebook(x)
@@ -163,7 +163,7 @@ class _SparseConvBase(SparseModule):
         if bev:
             D, H, W = rb.out_shape
             return ops.sparse_conv(xin, w, rb, scale, shift, None, relu, precision=prec,
-                                   bev=(x.batch_size, D, H, W), out_fmt=out_fmt)
+                                   bev=(x.batch_size, D, H, W), out_fmt=out_fmt, bev_dmajor=bev_dmajor)
         y = ops.sparse_conv(xin, w, rb, scale, shift, residual, relu, precision=prec, out_fmt=out_fmt)
         if self.subm:
             return x._like(y)
@@ -236,7 +236,7 @@ class SparseSequential(SparseModule):
     def add(self, module, name=None):
         self.add_module(name or str(len(self._modules)), module)
 
-    def forward(self, x, bev_last=False, out_fmt=None):
+    def forward(self, x, bev_last=False, out_fmt=None, bev_dmajor=False):
         mods = list(self._modules.values())
         i = 0
         while i < len(mods):
@@ -252,7 +252,8 @@ class SparseSequential(SparseModule):
                     relu = True
                     j += 1
                 last = j == len(mods)
-                x = m(x, bn=bn, relu=relu, bev=(bev_last and last), out_fmt=out_fmt if last else None)
+                x = m(x, bn=bn, relu=relu, bev=(bev_last and last), out_fmt=out_fmt if last else None,
+                      bev_dmajor=bev_dmajor and bev_last and last)
                 i = j
             elif isinstance(m, SparseModule):
                 x = m(x)

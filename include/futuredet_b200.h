@@ -170,7 +170,9 @@ typedef struct fd_conv_desc {
 } fd_conv_desc;
 
 enum { FD_GATHER_TABLE = 0, FD_GATHER_CONV2D = 1, FD_GATHER_CONVT2D = 2 };
-enum { FD_OUTMAP_IDENTITY = 0, FD_OUTMAP_BEV = 1 };
+/* FD_OUTMAP_BEV: channel = c*D + z (the reference's dense().view() order).  FD_OUTMAP_BEV_DMAJOR: channel = z*C + c
+ * (contiguous per row -> vector stores); only for consumers that permute their input channels accordingly. */
+enum { FD_OUTMAP_IDENTITY = 0, FD_OUTMAP_BEV = 1, FD_OUTMAP_BEV_DMAJOR = 2 };
 /* FD_PREC_FP32: CUDA-core fp32 FMA (exact reference arithmetic).
  * FD_PREC_BF16X3: tcgen05 tensor cores, 3-term bf16 split (fp32-class accuracy).
  * FD_PREC_BF16: tcgen05 single pass bf16 (fast mode, outside the 1e-3 contract). */
