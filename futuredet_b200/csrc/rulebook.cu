@@ -151,11 +151,7 @@ neighbors_kernel(const int4* __restrict__ out_coords, const int32_t* __restrict_
             const int k = kz * gsz + q;
             int r = ok[q] ? coord_index_resolve(table, mask, key[q], h[q], e[q]) : -1;
             if (live) nbr[(size_t)k * nbr_stride + o] = r;
-            unsigned m = __ballot_sync(0xffffffffu, r >= 0);
-            if (m) {
-              if (lane == 0) atomicAdd(&pair_num[k], __popc(m));
-              my_mask |= 1u << (k & 31);
-            }
+            if (__any_sync(0xffffffffu, r >= 0)) my_mask |= 1u << (k & 31);
           }
         }
       } else {
@@ -169,11 +165,7 @@ neighbors_kernel(const int4* __restrict__ out_coords, const int32_t* __restrict_
             r = coord_index_resolve(table, mask, key, hh, table[hh]);
           }
           if (live) nbr[(size_t)k * nbr_stride + o] = r;
-          unsigned m = __ballot_sync(0xffffffffu, r >= 0);
-          if (m) {
-            if (lane == 0) atomicAdd(&pair_num[k], __popc(m));
-            my_mask |= 1u << (k & 31);
-          }
+          if (__any_sync(0xffffffffu, r >= 0)) my_mask |= 1u << (k & 31);
         }
       }
     }
@@ -223,15 +215,31 @@ neighbors_bitmap_kernel(const int4* __restrict__ out_coords, const int32_t* __re
             }
           }
           if (live) nbr[(size_t)k * nbr_stride + o] = r;
-          unsigned m = __ballot_sync(0xffffffffu, r >= 0);
-          if (m) {
-            if (lane == 0) atomicAdd(&pair_num[k], __popc(m));
-            my_mask |= 1u << (k & 31);
-          }
+          if (__any_sync(0xffffffffu, r >= 0)) my_mask |= 1u << (k & 31);
         }
       }
     }
     if (tile_mask && lane == 0 && my_mask) atomicOr(&tile_mask[o >> 7], my_mask);
+  }
+}
+
+// pairs per kernel offset (spconv `indice_pair_num`): one block per offset, deterministic
+__global__ void __launch_bounds__(256)
+count_pairs_kernel(const int* __restrict__ nbr, int nbr_stride, const int32_t* __restrict__ d_n, int n_cap,
+                   int* __restrict__ pair_num) {
+  __shared__ int ws[8];
+  const int n = d_n ? min(*d_n, n_cap) : n_cap;
+  const int* row = nbr + (size_t)blockIdx.x * nbr_stride;
+  int c = 0;
+  for (int o = threadIdx.x; o < n; o += blockDim.x) c += row[o] >= 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    pair_num[blockIdx.x] = t;
   }
 }
 
@@ -271,6 +279,15 @@ static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 }  // namespace fd
 
 extern "C" {
+
+int fd_rulebook_count_pairs(const int32_t* d_nbr, int nbr_stride, const int32_t* d_n_out, int n_out_cap, int K,
+                            int32_t* d_pair_num, void* stream) {
+  using namespace fd;
+  FD_REQUIRE(d_nbr && d_pair_num && K >= 1 && nbr_stride >= n_out_cap, "fd_rulebook_count_pairs: bad argument");
+  count_pairs_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(d_nbr, nbr_stride, d_n_out, n_out_cap, d_pair_num);
+  FD_LAUNCHED();
+  return 0;
+}
 
 int fd_coord_index_build(const int32_t* d_coords4, const int32_t* d_n, int n_cap, int B, const int32_t* shape3,
                          uint64_t* d_table, int64_t cap, void* stream_) {
@@ -337,7 +354,7 @@ int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, 
                           uint32_t* d_tile_mask, void* stream_) {
   using namespace fd;
   cudaStream_t stream = (cudaStream_t)stream_;
-  FD_REQUIRE(d_out_coords4 && d_in_table && in_shape3 && ksize3 && stride3 && pad3 && d_nbr && d_pair_num,
+  FD_REQUIRE(d_out_coords4 && d_in_table && in_shape3 && ksize3 && stride3 && pad3 && d_nbr,
              "fd_rulebook_neighbors: null argument");
   FD_REQUIRE(is_pow2(in_cap), "fd_rulebook_neighbors: in_cap must be a power of two");
   FD_REQUIRE(nbr_stride >= n_out_cap, "fd_rulebook_neighbors: nbr_stride < n_out_cap");
@@ -346,7 +363,7 @@ int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, 
   const int K = g.k[0] * g.k[1] * g.k[2];
   FD_REQUIRE(K >= 1 && K <= 343, "fd_rulebook_neighbors: kernel volume %d unsupported", K);
   FD_REQUIRE(!d_tile_mask || K <= 32, "fd_rulebook_neighbors: tile masks support at most 32 kernel offsets");
-  FD_CUDA(cudaMemsetAsync(d_pair_num, 0, sizeof(int32_t) * K, stream));
+  if (d_pair_num) FD_CUDA(cudaMemsetAsync(d_pair_num, 0, sizeof(int32_t) * K, stream));
   if (d_tile_mask) FD_CUDA(cudaMemsetAsync(d_tile_mask, 0, sizeof(uint32_t) * (size_t)ceil_div(n_out_cap > 0 ? n_out_cap : 1, 128), stream));
   if (n_out_cap <= 0) return 0;
   Shape3 ish{in_shape3[0], in_shape3[1], in_shape3[2]};
@@ -354,6 +371,7 @@ int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, 
       (const int4*)d_out_coords4, d_n_out, n_out_cap, (const unsigned long long*)d_in_table,
       (uint32_t)(in_cap - 1), ish, g, d_nbr, nbr_stride, d_pair_num, d_tile_mask);
   FD_LAUNCHED();
+  if (d_pair_num) return fd_rulebook_count_pairs(d_nbr, nbr_stride, d_n_out, n_out_cap, K, d_pair_num, stream_);
   return 0;
 }
 
@@ -363,8 +381,7 @@ int fd_rulebook_neighbors_bitmap(const int32_t* d_out_coords4, const int32_t* d_
                                  int nbr_stride, int32_t* d_pair_num, uint32_t* d_tile_mask, void* stream_) {
   using namespace fd;
   cudaStream_t stream = (cudaStream_t)stream_;
-  FD_REQUIRE(d_out_coords4 && d_in_bitmap && d_in_wordprefix && in_shape3 && ksize3 && stride3 && pad3 && d_nbr &&
-                 d_pair_num,
+  FD_REQUIRE(d_out_coords4 && d_in_bitmap && d_in_wordprefix && in_shape3 && ksize3 && stride3 && pad3 && d_nbr,
              "fd_rulebook_neighbors_bitmap: null argument");
   FD_REQUIRE(nbr_stride >= n_out_cap, "fd_rulebook_neighbors_bitmap: nbr_stride < n_out_cap");
   Conv3Geom g;
@@ -372,7 +389,7 @@ int fd_rulebook_neighbors_bitmap(const int32_t* d_out_coords4, const int32_t* d_
   const int K = g.k[0] * g.k[1] * g.k[2];
   FD_REQUIRE(K >= 1 && K <= 343, "fd_rulebook_neighbors_bitmap: kernel volume %d unsupported", K);
   FD_REQUIRE(!d_tile_mask || K <= 32, "fd_rulebook_neighbors_bitmap: tile masks support at most 32 kernel offsets");
-  FD_CUDA(cudaMemsetAsync(d_pair_num, 0, sizeof(int32_t) * K, stream));
+  if (d_pair_num) FD_CUDA(cudaMemsetAsync(d_pair_num, 0, sizeof(int32_t) * K, stream));
   if (d_tile_mask) FD_CUDA(cudaMemsetAsync(d_tile_mask, 0, sizeof(uint32_t) * (size_t)ceil_div(n_out_cap > 0 ? n_out_cap : 1, 128), stream));
   if (n_out_cap <= 0) return 0;
   Shape3 ish{in_shape3[0], in_shape3[1], in_shape3[2]};
@@ -380,6 +397,7 @@ int fd_rulebook_neighbors_bitmap(const int32_t* d_out_coords4, const int32_t* d_
       (const int4*)d_out_coords4, d_n_out, n_out_cap, d_in_bitmap, d_in_wordprefix, ish, g, d_nbr, nbr_stride,
       d_pair_num, d_tile_mask);
   FD_LAUNCHED();
+  if (d_pair_num) return fd_rulebook_count_pairs(d_nbr, nbr_stride, d_n_out, n_out_cap, K, d_pair_num, stream_);
   return 0;
 }
 

@@ -120,9 +120,20 @@ class Rulebook:
 
     def __init__(self, nbr, pair_num, K, out_coords, n_out_dev, n_out_cap, out_shape, ksize, stride, padding,
                  tile_mask=None):
-        self.nbr, self.pair_num, self.K, self.tile_mask = nbr, pair_num, K, tile_mask
+        self.nbr, self._pair_num, self.K, self.tile_mask = nbr, pair_num, K, tile_mask
         self.out_coords, self.n_out_dev, self.n_out_cap = out_coords, n_out_dev, n_out_cap
         self.out_shape, self.ksize, self.stride, self.padding = out_shape, ksize, stride, padding
+
+    @property
+    def pair_num(self):
+        """[K] int32 pairs per kernel offset (spconv `indice_pair_num`); counted on first use, off the hot path."""
+        if self._pair_num is None:
+            lib = L.load()
+            self._pair_num = torch.empty((self.K,), dtype=torch.int32, device=self.nbr.device)
+            rc = lib.fd_rulebook_count_pairs(_ptr(self.nbr), self.nbr.stride(0), _ptr(self.n_out_dev), self.n_out_cap,
+                                             self.K, _ptr(self._pair_num), _stream())
+            L.check(rc, "fd_rulebook_count_pairs")
+        return self._pair_num
 
     def to_pairs(self):
         """spconv-1.x layout: (indice_pairs [K,2,P] int32 padded with -1, indice_pair_num [K])."""
@@ -144,7 +155,7 @@ def _neighbors(out_coords, n_out_dev, n_out_cap, index, ksize, stride, padding):
     K = int(ksize[0] * ksize[1] * ksize[2])
     dev = out_coords.device
     nbr = torch.empty((K, max(n_out_cap, 1)), dtype=torch.int32, device=dev)
-    pair_num = torch.empty((K,), dtype=torch.int32, device=dev)
+    pair_num = None          # counted lazily (Rulebook.pair_num)
     tile_mask = torch.empty(((max(n_out_cap, 1) + 127) // 128,), dtype=torch.int32, device=dev) if K <= 32 else None
     if isinstance(index, BitmapIndex):
         rc = lib.fd_rulebook_neighbors_bitmap(_ptr(out_coords), _ptr(n_out_dev), n_out_cap, _ptr(index.bitmap),

@@ -98,8 +98,9 @@ int fd_rulebook_out_coords(const int32_t* d_in_coords4, const int32_t* d_n_in, i
                            int32_t* d_out_coords4, int n_out_cap, int32_t* d_n_out, void* stream);
 
 /* Neighbour table for SubMConv3d (out == in coords, stride 1, pad = k/2) and for
- * SparseConv3d (out coords from fd_rulebook_out_coords).  d_pair_num [K] int32
- * receives the number of pairs per kernel offset (spconv `indice_pair_num`).
+ * SparseConv3d (out coords from fd_rulebook_out_coords).  d_pair_num (optional, [K] int32)
+ * receives the number of pairs per kernel offset (spconv `indice_pair_num`); pass NULL on the hot path and call
+ * fd_rulebook_count_pairs() only when the counts are needed (export, flop accounting).
  * d_tile_mask (optional, [ceil(n_out_cap/128)] uint32, K <= 32): bit k of word t is set when some row of
  * the 128-row tile t has a neighbour through offset k; fd_conv_forward skips the other offsets.        */
 int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, int n_out_cap,
@@ -107,6 +108,9 @@ int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, 
                           const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
                           const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
                           uint32_t* d_tile_mask, void* stream);
+
+int fd_rulebook_count_pairs(const int32_t* d_nbr, int nbr_stride, const int32_t* d_n_out, int n_out_cap, int K,
+                            int32_t* d_pair_num, void* stream);
 
 /* Same search against the bitmap + per-word popcount prefix that fd_rulebook_out_coords left behind for a
  * strided conv's OUTPUT set (rows of that set are in ascending linear order, so row = rank): use it as the

@@ -2,7 +2,7 @@
 import ctypes as C, os, sys
 import numpy as np, torch
 os.environ["FD_TC_DEBUG"] = os.environ.get("FD_TC_DEBUG", "32")
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from futuredet_b200 import ops, lib
 dev = torch.device("cuda:0")
 rng = np.random.default_rng(0)
