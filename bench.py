@@ -206,6 +206,32 @@ def conv_profile(model, pts, off):
                 by_kind={k: dict(gflop=v[0] / 1e9, ms=v[1], tflops=v[0] / max(v[1], 1e-9) / 1e9) for k, v in by_kind.items()})
 
 
+def voxelize_roofline(model, dev, n_scenes=32):
+    """HBM roofline of the fused voxelize+VFE family on one batched launch of `n_scenes` scenes (a single 12.5 MB
+    scene is below launch latency, SURVEY.md hard part 1): algorithmic bytes 20*N + 40*M over the CUDA-event time."""
+    scenes = [synth_scene(N_TARGET, seed=5000 + i) for i in range(4)]
+    pts = torch.from_numpy(np.concatenate([scenes[i % 4] for i in range(n_scenes)])).to(dev)
+    off = torch.tensor(np.r_[0, np.cumsum([len(scenes[i % 4]) for i in range(n_scenes)])], dtype=torch.int32, device=dev)
+    for _ in range(3):
+        vox = model.voxelize(pts, off)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        vox = model.voxelize(pts, off)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    m = int(vox["total"].item())
+    nbytes = 20.0 * pts.shape[0] + 40.0 * m
+    pk = peaks()
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return dict(bound="hbm", kernel="fused voxelize+VFE family (7 launches), %d scenes per launch" % n_scenes,
+                achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=None,
+                algorithmic_bytes=nbytes, ms=ms, points=int(pts.shape[0]), voxels=m, peak_source=pk["src"] + " HBM copy")
+
+
 def run_gpu(args, rank, world, local):
     from futuredet_b200 import lib, neck, shard, sparse
     if not torch.cuda.is_available():
@@ -269,6 +295,7 @@ def run_gpu(args, rank, world, local):
         clocks = sampler.stop() if sampler else None
         ms_e2e, _ = timed(step_e2e)
         prof = conv_profile(model, *pool_dev[0]) if rank == 0 else None
+        vox_roof = voxelize_roofline(model, dev) if rank == 0 else None
     if rank != 0:
         return
     scenes = B * world * args.steps
@@ -300,7 +327,8 @@ def run_gpu(args, rank, world, local):
                             precision=args.precision, parallelism="scene replicas x%d, no collective" % world),
                 e2e=dict(value=e2e_value, unit="scenes/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),
-                gpu_launches=int(launches), clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline)
+                gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_voxelize=vox_roof,
+                cpu_baseline=cpu_baseline)
     print(json.dumps(line))
 
 

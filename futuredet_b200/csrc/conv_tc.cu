@@ -195,6 +195,26 @@ __device__ __forceinline__ uint32_t umma_stage(uint32_t tmem_d, uint64_t dA_hi, 
   }
   return ready;
 }
+// Spin on the non-suspending probe.  try_wait parks the thread and its wake-up after the phase flips was measured at
+// several hundred cycles; on the per-stage hand-shakes of the pipeline (MMA warp, producers, weight loader) that wake-up
+// latency lands on the critical path every time a role is even slightly ahead of its partner.
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_test(bar, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      if (*(volatile int*)&g_tc_abort) return;
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000LL) {
+        if (atomicAdd(&g_tc_abort, 1) < 8)
+          printf("futuredet_b200: mbarrier spin timed out (tag %d, block %d, thread %d, bar 0x%x, parity %u)\n", tag,
+                 (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        return;
+      }
+    }
+  }
+}
 // Warp-level wait: ONE lane polls, the rest of the warp parks at __syncwarp().  32 lanes polling the same mbarrier
 // word serialise in the shared-memory pipe (measured: ~450 cycles per already-completed wait vs ~100).
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int tag = 0, uint32_t backoff_ns = 0) {
@@ -533,7 +553,7 @@ conv_tc_kernel(const TcArgs t) {
         const int ch = ch_n;
         if (p + G < n_emit) fetch(p + G);                  // prefetch the next owned stage's indices (in flight during the wait)
         if (tid == 0) TC_TRACE(1, 4 * ptrace_i, clock64());
-        mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1, 2);
+        if (t.dbg & 128) mbar_spin(smem_u32(&a_empty[slot]), phase ^ 1, 2); else mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1, 2);
         if (tid == 0) { TC_TRACE(1, 4 * ptrace_i + 1, clock64()); TC_TRACE(1, 4 * ptrace_i + 3, (long long)(c_base + p)); }
         const uint32_t fbar = smem_u32(&a_full[slot]);
         const uint32_t dst0 = a_ring_u32 + slot * Cfg::A_BYTES + a_off0;
@@ -613,14 +633,14 @@ conv_tc_kernel(const TcArgs t) {
       tc_fence_after();
       uint32_t accumulate = 0;
       for (int ia = 0; ia < n_act; ++ia) {
-        if (!b_ready) mbar_wait(smem_u32(&b_full[b_slot]), b_phase, 4);
+        if (!b_ready) { if (t.dbg & 128) mbar_spin(smem_u32(&b_full[b_slot]), b_phase, 4); else mbar_wait(smem_u32(&b_full[b_slot]), b_phase, 4); }
         const uint32_t sB_hi = b_ring_u32 + b_slot * Cfg::B_BYTES, sB_lo = sB_hi + NT * 128;
         const uint64_t dB_hi = umma_desc_sw128(sB_hi), dB_lo = umma_desc_sw128(sB_lo);
         const uint32_t nb_slot = b_slot + 1 == SB ? 0 : b_slot + 1, nb_phase = b_slot + 1 == SB ? b_phase ^ 1 : b_phase;
         b_ready = mbar_test(smem_u32(&b_full[nb_slot]), nb_phase);   // consumed at the next K stage
         for (int ti = 0; ti < live; ++ti) {
           if (lane == 0) TC_TRACE(3, 4 * trace_i + 2, clock64());
-          if (!a_ready) mbar_wait(smem_u32(&a_full[a_slot]), a_phase, 5);
+          if (!a_ready) { if (t.dbg & 128) mbar_spin(smem_u32(&a_full[a_slot]), a_phase, 5); else mbar_wait(smem_u32(&a_full[a_slot]), a_phase, 5); }
           if (lane == 0) TC_TRACE(0, 2 * trace_i, clock64());
           tc_fence_after();
           if (lane == 0) TC_TRACE(3, 4 * trace_i + 3, clock64());
@@ -630,7 +650,8 @@ conv_tc_kernel(const TcArgs t) {
           const uint32_t tmem_d = tmem_base + (uint32_t)((acc * T + ti) * ACC);
           const uint32_t nbar = smem_u32(&a_full[na_slot]), cbar = smem_u32(&a_empty[a_slot]);
           if (t.dbg & 2) {
-            umma_commit_elect(cbar);
+            if (t.dbg & 256) { if (lane == 0) mbar_arrive(cbar); __syncwarp(); }   // triage: plain arrive instead of tcgen05.commit
+            else umma_commit_elect(cbar);
             a_ready = 0;
           } else if (!t.split) {
             a_ready = umma_stage<0>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, na_phase, cbar);
@@ -665,7 +686,7 @@ conv_tc_kernel(const TcArgs t) {
         for (int ia = 0; ia < n_act; ++ia, rem &= rem - 1) {
           const int ks = all_active ? ia : __ffsll((long long)rem) - 1;
           const uint32_t bbar = smem_u32(&b_full[b_slot]);
-          mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1);
+          if (t.dbg & 128) mbar_spin(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1); else mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1);
           if (!(t.dbg & 4)) {
             mbar_expect_tx(bbar, Cfg::B_BYTES);
             bulk_g2s(b_ring_u32 + b_slot * Cfg::B_BYTES, wtile + (size_t)ks * Cfg::B_BYTES, Cfg::B_BYTES, bbar);

@@ -39,7 +39,7 @@ __device__ __forceinline__ int find_scene(const int32_t* s_off, int B, int i) {
 __global__ void __launch_bounds__(256)
 vox_hash_points(const float* __restrict__ pts, int n, int pstride, const int32_t* __restrict__ boff,
                 int B, VoxGeom g, long long* __restrict__ keys, int* __restrict__ first,
-                uint32_t mask, int* __restrict__ pslot) {
+                uint32_t mask, uint32_t scene_cap, int* __restrict__ pslot) {
   extern __shared__ int32_t s_off[];
   for (int j = threadIdx.x; j <= B; j += blockDim.x) s_off[j] = boff[j];
   __syncthreads();
@@ -58,7 +58,9 @@ vox_hash_points(const float* __restrict__ pts, int n, int pstride, const int32_t
     if (ok) {
       int b = find_scene(s_off, B, i);
       long long key = (long long)b * cells + ((long long)c[2] * g.grid[1] + c[1]) * g.grid[0] + c[0];
-      uint32_t h = hash64((uint64_t)key) & mask;
+      // every scene hashes into its own region of the table (probing may spill into the next one): blocks run in
+      // launch order over scene-contiguous points, so the live part of the table stays L2 resident in a big batch
+      uint32_t h = ((uint32_t)b * scene_cap + (hash64((uint64_t)key) & (scene_cap - 1))) & mask;
       while (true) {
         long long prev = atomicCAS((unsigned long long*)&keys[h], (unsigned long long)kEmptyKey,
                                    (unsigned long long)key);
@@ -193,7 +195,7 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 static VoxWorkspace carve(void* base, int64_t n, int B, int max_voxels, int max_points) {
   VoxWorkspace w{};
   int64_t cap = 1024;
-  while (cap < 2 * n) cap <<= 1;
+  while (cap < 4 * n) cap <<= 1;      // load factor <= 0.25 overall, <= 0.5 inside a scene region for any B
   w.cap = cap;
   char* p = (char*)base;
   size_t off = 0;
@@ -283,10 +285,13 @@ int fd_voxelize_vfe(const float* d_points, int64_t total_points, int point_strid
   // first[] and slots[] are adjacent in the workspace: one memset covers both
   FD_CUDA(cudaMemsetAsync(w.first, 0x7f, (char*)w.pslot - (char*)w.first, stream));
   const int threads = 256;
-  const int grid_pts = persistent_grid(ceil_div(n, threads), 8);
+  const int grid_pts = ceil_div(n, threads) > 0 ? ceil_div(n, threads) : 1;   // one block per 256 consecutive points
+  uint32_t scene_cap = 1024;                                                   // per-scene region: pow2 >= 2 * mean scene size
+  while ((int64_t)scene_cap * B < w.cap) scene_cap <<= 1;
+  if ((int64_t)scene_cap * B > w.cap) scene_cap >>= 1;
   if (n > 0) {
     vox_hash_points<<<grid_pts, threads, (B + 1) * sizeof(int32_t), stream>>>(
-        d_points, n, point_stride, d_batch_offsets, B, g, w.keys, w.first, (uint32_t)(w.cap - 1), w.pslot);
+        d_points, n, point_stride, d_batch_offsets, B, g, w.keys, w.first, (uint32_t)(w.cap - 1), scene_cap, w.pslot);
     FD_LAUNCHED();
   }
   // rank[i] = number of voxel-first points before i
