@@ -364,8 +364,8 @@ struct TcArgs {
 };
 
 template <int NT> struct TcCfg {
-  static constexpr int SA = NT >= 128 ? 4 : 5;                 // A ring slots (32 KB each)
-  static constexpr int SB = NT >= 32 ? 2 : 3;                  // B ring slots
+  static constexpr int SA = NT >= 64 ? 4 : 5;                     // A ring slots (32 KB each)
+  static constexpr int SB = NT >= 128 ? 2 : 4;                    // B ring slots (weights are requested SB-1 K stages ahead)
   static constexpr int A_BYTES = 2 * TC_A_PLANE;
   static constexpr int B_BYTES = 2 * NT * 128;
   // NT <= 64: the split products A_hi*B_hi and A_hi*B_lo are issued as ONE MMA of width 2*NT against the adjacent
@@ -558,7 +558,7 @@ conv_tc_kernel(const TcArgs t) {
         const uint32_t fbar = smem_u32(&a_full[slot]);
         const uint32_t dst0 = a_ring_u32 + slot * Cfg::A_BYTES + a_off0;
         slot += G;
-        if (slot >= SA) { slot -= SA; phase ^= 1; }
+        while (slot >= SA) { slot -= SA; phase ^= 1; }
         // ---- A: gather 128 rows x 64 channels (this thread: chunk j of rows rbase + ROWS_PER_PASS q)
         if (t.dbg & 1) {
           mbar_arrive(fbar);
