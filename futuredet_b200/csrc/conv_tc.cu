@@ -29,7 +29,14 @@
 namespace fd {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;                 // bf16 elements per stage row (128 bytes, one swizzle atom)
+// K elements (bf16) per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B; twice the
+// stages in flight in the same shared memory).  Both are parity-green; measured on the 4-scene forward, 64 is faster
+// (14.6 ms vs 18.5 ms): the per-stage hand-shake cost outweighs the deeper ring.
+#define FD_TC_BK 64
+constexpr int TC_BK = FD_TC_BK;
+constexpr int TC_ROWB = TC_BK * 2;        // bytes of one stage row (one swizzle atom row)
+constexpr int TC_CHUNKS = TC_ROWB / 16;   // 16-byte chunks per row
+constexpr int TC_SWZ_SHIFT = TC_BK == 64 ? 0 : 1;   // chunk ^= (row >> shift) & (CHUNKS - 1): SWIZZLE_128B / SWIZZLE_64B
 constexpr int TC_MAXK = 32;               // max kernel offsets (27 for 3x3x3)
 constexpr int TC_DENSE_MAXK = 9;          // dense 2-D mode: up to 3x3 taps (row indices cached in shared memory)
 constexpr int TC_GROUPS = 4;              // producer groups (each fills whole A stages on its own)
@@ -39,7 +46,7 @@ constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;         // warp 8
 constexpr int TC_B_WARP = TC_PRODUCER_WARPS + 5;       // warp 13 (warps 9-12: epilogue, TMEM lane quarters 1,2,3,0)
 constexpr int TC_THREADS = TC_PRODUCERS + 32 + 128 + 32;
 constexpr int TC_SS_MAX = 512;                         // folded BN scale / shift cached in shared memory up to this Cout
-constexpr int TC_A_PLANE = TC_BM * 128;   // bytes of one A plane (hi or lo) per stage
+constexpr int TC_A_PLANE = TC_BM * TC_ROWB;   // bytes of one A plane (hi or lo) per stage
 
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -130,10 +137,12 @@ __device__ __forceinline__ uint32_t umma_stage(uint32_t tmem_d, uint64_t dA_hi, 
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, pa;\n\t"
         "add.u64 ah, %2, 2; add.u64 al, %3, 2; add.u64 bh, %4, 2; add.u64 bl, %5, 2;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
+#if FD_TC_BK == 64
         "add.u64 ah, %2, 4; add.u64 al, %3, 4; add.u64 bh, %4, 4; add.u64 bl, %5, 4;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
         "add.u64 ah, %2, 6; add.u64 al, %3, 6; add.u64 bh, %4, 6; add.u64 bl, %5, 6;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
+#endif
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
         "selp.u32 %0, 1, 0, pn;\n\t"
         "}"
@@ -153,12 +162,14 @@ __device__ __forceinline__ uint32_t umma_stage(uint32_t tmem_d, uint64_t dA_hi, 
         "add.u64 ah, %2, 2; add.u64 al, %3, 2; add.u64 bh, %4, 2; add.u64 bl, %5, 2;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %7, one;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+#if FD_TC_BK == 64
         "add.u64 ah, %2, 4; add.u64 al, %3, 4; add.u64 bh, %4, 4; add.u64 bl, %5, 4;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %7, one;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
         "add.u64 ah, %2, 6; add.u64 al, %3, 6; add.u64 bh, %4, 6; add.u64 bl, %5, 6;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %7, one;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+#endif
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
         "selp.u32 %0, 1, 0, pn;\n\t"
         "}"
@@ -180,6 +191,7 @@ __device__ __forceinline__ uint32_t umma_stage(uint32_t tmem_d, uint64_t dA_hi, 
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, one;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+#if FD_TC_BK == 64
         "add.u64 ah, %2, 4; add.u64 al, %3, 4; add.u64 bh, %4, 4; add.u64 bl, %5, 4;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, one;\n\t"
@@ -188,6 +200,7 @@ __device__ __forceinline__ uint32_t umma_stage(uint32_t tmem_d, uint64_t dA_hi, 
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bh, %6, one;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, one;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, one;\n\t"
+#endif
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
         "selp.u32 %0, 1, 0, pn;\n\t"
         "}"
@@ -274,9 +287,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), version 1.
+// UMMA shared-memory descriptor, K-major, one swizzle atom per row (SWIZZLE_128B for 64-element stages, SWIZZLE_64B
+// for 32): 8-row groups 8*TC_ROWB bytes apart (SBO), version 1, layout type 2 (128B) / 4 (64B).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t sbo = (8 * TC_ROWB) >> 4, layout = TC_BK == 64 ? 2 : 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
@@ -323,7 +338,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---- weight packing ------------------------------------------------------------------------------
 // W fp32 [K, Cin, Cout] -> for every (N tile tn, K stage ks) one contiguous block that is a byte-exact image of
-// the shared-memory B stage: [2 planes (hi, lo)][NT rows][64 bf16, 16-byte chunks XOR-swizzled by (row & 7)].
+// the shared-memory B stage: [2 planes (hi, lo)][NT rows][TC_BK bf16, 16-byte chunks XOR-swizzled by the row].
 // A stage's weights are then ONE cp.async.bulk (TMA bulk copy) instead of per-thread gathers.
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, int NT, int n_tiles_n, int n_kstages,
@@ -346,7 +361,7 @@ pack_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, int N
     __nv_bfloat16 hi = __float2bfloat16_rn(v);
     __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const long long blk = ((long long)tn * n_kstages + ks) * per_block;
-    const int off = nrow * TC_BK + ((((kc >> 3) ^ (nrow & 7)) << 3) | (kc & 7));
+    const int off = nrow * TC_BK + ((((kc >> 3) ^ ((nrow >> TC_SWZ_SHIFT) & (TC_CHUNKS - 1))) << 3) | (kc & 7));
     out[blk + off] = hi;
     out[blk + (long long)NT * TC_BK + off] = lo;
   }
@@ -364,10 +379,9 @@ struct TcArgs {
 };
 
 template <int NT> struct TcCfg {
-  static constexpr int SA = NT >= 64 ? 4 : 5;                     // A ring slots (32 KB each)
-  static constexpr int SB = NT >= 128 ? 2 : 4;                    // B ring slots (weights are requested SB-1 K stages ahead)
   static constexpr int A_BYTES = 2 * TC_A_PLANE;
-  static constexpr int B_BYTES = 2 * NT * 128;
+  static constexpr int B_BYTES = 2 * NT * TC_ROWB;
+  static constexpr int SB = (TC_BK == 64 && NT >= 128) ? 2 : 4;   // B ring slots (weights are requested SB-1 K stages ahead)
   // NT <= 64: the split products A_hi*B_hi and A_hi*B_lo are issued as ONE MMA of width 2*NT against the adjacent
   // [B_hi | B_lo] planes (each MMA re-reads its whole A tile from shared memory, which is what bounds narrow tiles),
   // so a tile owns two accumulator column blocks that the epilogue adds.
@@ -376,8 +390,14 @@ template <int NT> struct TcCfg {
   static constexpr int TMAX = 256 / ACC_COLS > 4 ? 4 : 256 / ACC_COLS;   // M tiles sharing one weight fetch
   static constexpr int TMEM_COLS = 2 * TMAX * ACC_COLS < 32 ? 32 : 2 * TMAX * ACC_COLS;
   static constexpr int IDX_BYTES = TMAX * TC_DENSE_MAXK * TC_BM * 4;   // dense-mode row index cache
+  // the A ring takes every byte that is left of the 227 KB a CTA may own
+  static constexpr int FIXED = 1024 + SB * B_BYTES + IDX_BYTES + 2 * TC_SS_MAX * 4 + (2 * 16 + 2 * SB + 4) * 8 + 64;
+  static constexpr int SA_FIT = (232448 - FIXED) / A_BYTES;
+  static constexpr int SA = SA_FIT > 12 ? 12 : SA_FIT;            // A ring slots
+  static_assert(SA >= TC_GROUPS, "every producer group needs a slot of its own");
   static constexpr int NBAR = 2 * SA + 2 * SB + 4;
   static constexpr size_t SMEM = 1024 + (size_t)SA * A_BYTES + (size_t)SB * B_BYTES + IDX_BYTES + 2 * TC_SS_MAX * 4 + NBAR * 8 + 64;
+  static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 template <int N>
@@ -406,7 +426,7 @@ conv_tc_kernel(const TcArgs t) {
   constexpr int ACC = Cfg::ACC_COLS;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B alignment
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms want 1024-B (128B) / 512-B (64B) alignment
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + SA * Cfg::A_BYTES;
   int* s_idx = (int*)(b_ring + SB * Cfg::B_BYTES);                // [TMAX][TC_DENSE_MAXK][128] (dense mode)
@@ -429,10 +449,13 @@ conv_tc_kernel(const TcArgs t) {
   const int n_super = (n_tiles_m + T - 1) / T;
   const int n_units = n_super * t.n_tiles_n;
   const int ktot = a.K * a.cin;
-  const int n_kstages = (ktot + TC_BK - 1) / TC_BK;      // <= 64 (checked on the host)
+  const int n_kstages = (ktot + TC_BK - 1) / TC_BK;
   const bool wide = a.cin >= TC_BK;
-  const int spo = wide ? a.cin / TC_BK : 1;      // stages per kernel offset   (wide:   Cin multiple of 64)
-  const int opk = wide ? 1 : TC_BK / a.cin;      // kernel offsets per stage   (narrow: Cin divides 64)
+  const int spo = wide ? a.cin / TC_BK : 1;      // stages per kernel offset   (wide:   Cin multiple of TC_BK)
+  const int opk = wide ? 1 : TC_BK / a.cin;      // kernel offsets per stage   (narrow: Cin divides TC_BK)
+  // K stages come in groups: a kernel offset's `spo` stages (wide) or one stage covering `opk` offsets (narrow)
+  const int n_groups = wide ? a.K : n_kstages;   // <= 32
+  const int spg = spo;                           // stages per group (narrow: 1)
   constexpr int G = TC_GROUPS, GT = TC_PRODUCERS / G;
   const bool ss_smem = t.cout_pad <= TC_SS_MAX;
 
@@ -456,39 +479,39 @@ conv_tc_kernel(const TcArgs t) {
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  // K stages of a super-tile that touch an active kernel offset, as a bit mask over ks (ks = 0 is forced for an
-  // all-empty unit so that the accumulator is always defined).  Identical in every role.
-  // Without a rulebook mask (dense 2-D convolutions) every stage is active and ks == position; the bit mask is only
-  // built for masked launches (n_kstages <= 64 is checked on the host for those).
-  const bool all_active = t.tile_mask == nullptr;
-  auto unit_ksmask = [&](int st) -> unsigned long long {
-    if (all_active) return ~0ull;
+  // Groups of a super-tile that touch an active kernel offset, as a bit mask (group 0 is forced for an all-empty
+  // unit so that the accumulator is always defined).  Identical in every role; the unit's stage list is the stages
+  // of its active groups in ascending order.  Without a rulebook mask (dense 2-D convolutions) every group is active.
+  const uint32_t all_groups = n_groups >= 32 ? 0xffffffffu : ((1u << n_groups) - 1u);
+  auto unit_gmask = [&](int st) -> uint32_t {
+    if (t.tile_mask == nullptr) return all_groups;
     uint32_t m = 0;
-    {
-      for (int i = 0; i < T; ++i) {
-        const int tm = st * T + i;
-        if (tm < n_tiles_m) m |= __ldg(t.tile_mask + tm);
-      }
+    for (int i = 0; i < T; ++i) {
+      const int tm = st * T + i;
+      if (tm < n_tiles_m) m |= __ldg(t.tile_mask + tm);
     }
-    unsigned long long ksm = 0;
-    for (int ks = 0; ks < n_kstages; ++ks) {
-      const uint32_t km = wide ? (1u << (ks / spo)) : (((1u << opk) - 1u) << (ks * opk));
-      if (m & km) ksm |= 1ull << ks;
+    uint32_t gm = m;
+    if (!wide) {
+      gm = 0;
+      for (int ks = 0; ks < n_kstages; ++ks)
+        if (m & (((1u << opk) - 1u) << (ks * opk))) gm |= 1u << ks;
     }
-    return ksm ? ksm : 1ull;
+    gm &= all_groups;
+    return gm ? gm : 1u;
   };
 
   if (warp < TC_PRODUCER_WARPS) {
     // ===================================== PRODUCERS (A gather) =====================================
     // 4 groups of 64 threads; group g fills emitted A stages g, g+4, ... on its own, so several stages are being
     // issued concurrently, and the rulebook indices of a group's next stage are prefetched while it waits for a slot.
-    constexpr int ROWS_PER_PASS = GT / 8;
+    constexpr int ROWS_PER_PASS = GT / TC_CHUNKS;
     constexpr int PASSES = TC_BM / ROWS_PER_PASS;
+    static_assert(ROWS_PER_PASS % 8 == 0 && PASSES % 4 == 0, "swizzle phase must not change between passes");
     const int tid = threadIdx.x;                 // 0..TC_PRODUCERS-1
     const int grp = tid / GT, gt = tid % GT;
-    const int j = gt & 7, rbase = gt >> 3;       // 16-byte chunk column, first row (rows rbase + p*ROWS_PER_PASS)
+    const int j = gt % TC_CHUNKS, rbase = gt / TC_CHUNKS;   // 16-byte chunk column, first row (rows rbase + p*ROWS_PER_PASS)
     const uint32_t a_ring_u32 = smem_u32(a_ring), idx_u32 = smem_u32(s_idx);
-    const uint32_t a_off0 = rbase * 128 + ((j ^ (rbase & 7)) << 4);   // (row & 7) is the same for every pass
+    const uint32_t a_off0 = rbase * TC_ROWB + ((j ^ ((rbase >> TC_SWZ_SHIFT) & (TC_CHUNKS - 1))) << 4);   // swizzle phase is the same for every pass
     const int jk = wide ? 0 : (j * 8) / a.cin;   // which of the stage's offsets this thread's chunk belongs to
     const int jc = wide ? j * 8 : (j * 8) % a.cin;
     const uint32_t row_bytes = (uint32_t)a.in_stride * 4;
@@ -512,26 +535,23 @@ conv_tc_kernel(const TcArgs t) {
         }
         named_bar_sync(1, TC_PRODUCERS);
       }
-      const unsigned long long ksmask = unit_ksmask(st);
-      const int n_emit = (all_active ? n_kstages : __popcll(ksmask)) * live;
+      const uint32_t gmask = unit_gmask(st);
+      const int n_emit = __popc(gmask) * spg * live;
       // this group's positions in the unit's emitted-stage list: p = p0, p0 + G, ...
       int p = (int)((grp + G - (c_base % G)) % G);
       uint32_t slot = (c_base + p) % SA, phase = ((c_base + p) / SA) & 1;
-      unsigned long long rem = ksmask;             // active stages not yet passed
-      int act_idx = 0;                              // index (among active stages) of the lowest bit of `rem`
+      uint32_t rem = gmask;                         // active groups not yet passed
+      int act_idx = 0;                              // index (among active groups) of the lowest bit of `rem`
       int src[PASSES], kk_n = 0, ch_n = 0, ti_n = 0;
       // (ks, ti) of position p, this thread's kernel offset / channel, and the 16 gathered row indices
       auto fetch = [&](int pos) {
         const int want = pos / live;
         ti_n = pos - want * live;
-        int ks = want;
-        if (!all_active) {
-          while (act_idx < want) { rem &= rem - 1; ++act_idx; }
-          ks = __ffsll((long long)rem) - 1;
-        }
-        const int kq = wide ? ks / spo : 0;
-        kk_n = wide ? kq : ks * opk + jk;
-        ch_n = wide ? (ks - kq * spo) * TC_BK + jc : jc;
+        const int gi = want / spg, sub = want - gi * spg;
+        while (act_idx < gi) { rem &= rem - 1; ++act_idx; }
+        const int g = __ffs((int)rem) - 1;
+        kk_n = wide ? g : g * opk + jk;
+        ch_n = wide ? sub * TC_BK + jc : jc;
         const bool kvalid = kk_n < a.K;
         const int row0 = (st * T + ti_n) * TC_BM + rbase;
         if (table) {
@@ -559,7 +579,7 @@ conv_tc_kernel(const TcArgs t) {
         const uint32_t dst0 = a_ring_u32 + slot * Cfg::A_BYTES + a_off0;
         slot += G;
         while (slot >= SA) { slot -= SA; phase ^= 1; }
-        // ---- A: gather 128 rows x 64 channels (this thread: chunk j of rows rbase + ROWS_PER_PASS q)
+        // ---- A: gather 128 rows x TC_BK channels (this thread: chunk j of rows rbase + ROWS_PER_PASS q)
         if (t.dbg & 1) {
           mbar_arrive(fbar);
         } else if (a.in_fmt == FD_FMT_SPLIT_BF16) {
@@ -571,8 +591,8 @@ conv_tc_kernel(const TcArgs t) {
           for (int q = 0; q < PASSES; ++q) {
             const uint32_t sz = cur[q] >= 0 ? 16u : 0u;
             const size_t goff = (size_t)(uint32_t)max(cur[q], 0) * row_bytes;
-            cp_async16_sz(dst0 + q * ROWS_PER_PASS * 128, gh + goff, sz);
-            cp_async16_sz(dst0 + q * ROWS_PER_PASS * 128 + TC_A_PLANE, gl + goff, sz);
+            cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB, gh + goff, sz);
+            cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB + TC_A_PLANE, gl + goff, sz);
           }
           cp_async_mbar_arrive_noinc(fbar);
         } else {
@@ -602,8 +622,8 @@ conv_tc_kernel(const TcArgs t) {
                 hi[e] = *reinterpret_cast<uint32_t*>(&h);
                 lo[e] = *reinterpret_cast<uint32_t*>(&l);
               }
-              sts_u128(dst0 + (p0 + q) * ROWS_PER_PASS * 128, hi[0], hi[1], hi[2], hi[3]);
-              sts_u128(dst0 + (p0 + q) * ROWS_PER_PASS * 128 + TC_A_PLANE, lo[0], lo[1], lo[2], lo[3]);
+              sts_u128(dst0 + (p0 + q) * ROWS_PER_PASS * TC_ROWB, hi[0], hi[1], hi[2], hi[3]);
+              sts_u128(dst0 + (p0 + q) * ROWS_PER_PASS * TC_ROWB + TC_A_PLANE, lo[0], lo[1], lo[2], lo[3]);
             }
           }
           fence_proxy_async();                             // generic-proxy smem writes -> visible to the tensor core
@@ -628,13 +648,13 @@ conv_tc_kernel(const TcArgs t) {
       const int live = min(T, n_tiles_m - st * T);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int n_act = all_active ? n_kstages : __popcll(unit_ksmask(st));
+      const int n_act = __popc(unit_gmask(st)) * spg;
       mbar_wait(smem_u32(&t_empty[acc]), acc_phase ^ 1, 3);        // epilogue has drained this accumulator buffer
       tc_fence_after();
       uint32_t accumulate = 0;
       for (int ia = 0; ia < n_act; ++ia) {
         if (!b_ready) { if (t.dbg & 128) mbar_spin(smem_u32(&b_full[b_slot]), b_phase, 4); else mbar_wait(smem_u32(&b_full[b_slot]), b_phase, 4); }
-        const uint32_t sB_hi = b_ring_u32 + b_slot * Cfg::B_BYTES, sB_lo = sB_hi + NT * 128;
+        const uint32_t sB_hi = b_ring_u32 + b_slot * Cfg::B_BYTES, sB_lo = sB_hi + NT * TC_ROWB;
         const uint64_t dB_hi = umma_desc_sw128(sB_hi), dB_lo = umma_desc_sw128(sB_lo);
         const uint32_t nb_slot = b_slot + 1 == SB ? 0 : b_slot + 1, nb_phase = b_slot + 1 == SB ? b_phase ^ 1 : b_phase;
         b_ready = mbar_test(smem_u32(&b_full[nb_slot]), nb_phase);   // consumed at the next K stage
@@ -681,10 +701,11 @@ conv_tc_kernel(const TcArgs t) {
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int st = unit / t.n_tiles_n, tn = unit - st * t.n_tiles_n;
         const char* wtile = wblocks + (size_t)tn * n_kstages * Cfg::B_BYTES;
-        unsigned long long rem = unit_ksmask(st);
-        const int n_act = all_active ? n_kstages : __popcll(rem);
-        for (int ia = 0; ia < n_act; ++ia, rem &= rem - 1) {
-          const int ks = all_active ? ia : __ffsll((long long)rem) - 1;
+        uint32_t rem = unit_gmask(st);
+        const int n_act = __popc(rem) * spg;
+        for (int ia = 0, sub = 0; ia < n_act; ++ia) {
+          const int ks = (__ffs((int)rem) - 1) * spg + sub;
+          if (++sub == spg) { sub = 0; rem &= rem - 1; }
           const uint32_t bbar = smem_u32(&b_full[b_slot]);
           if (t.dbg & 128) mbar_spin(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1); else mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1);
           if (!(t.dbg & 4)) {
@@ -844,10 +865,8 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
   if (a.n_cap <= 0) return 0;
   FD_REQUIRE(a.wp != nullptr, "fd_conv_forward: tensor-core precision needs d_w_packed (fd_conv_pack_weights)");
   FD_REQUIRE(a.cin % 8 == 0 && (a.cin % TC_BK == 0 || TC_BK % a.cin == 0),
-             "fd_conv_forward: tensor-core arm needs Cin in {8,16,32} or a multiple of 64 (got %d)", a.cin);
+             "fd_conv_forward: tensor-core arm needs Cin in {8,16} or a multiple of %d (got %d)", TC_BK, a.cin);
   FD_REQUIRE(a.K <= TC_MAXK, "fd_conv_forward: tensor-core arm supports at most %d kernel offsets", TC_MAXK);
-  FD_REQUIRE(a.mode != FD_GATHER_TABLE || !a.tile_mask || (a.K * a.cin + TC_BK - 1) / TC_BK <= 64,
-             "fd_conv_forward: tensor-core arm supports K*Cin <= 4096 with a rulebook tile mask");
   FD_REQUIRE(a.mode == FD_GATHER_TABLE || a.K <= TC_DENSE_MAXK,
              "fd_conv_forward: tensor-core arm supports dense 2-D kernels of at most %d taps", TC_DENSE_MAXK);
   FD_REQUIRE(a.in_stride % 4 == 0 && (((uintptr_t)a.in) & 15) == 0 && (a.in_fmt != FD_FMT_SPLIT_BF16 || a.in_ctot % 8 == 0),

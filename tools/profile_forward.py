@@ -14,9 +14,10 @@ prec = os.environ.get("FD_PRECISION", "bf16x3")
 sparse.DEFAULT_PRECISION = neck.DEFAULT_PRECISION = prec
 dev = torch.device("cuda:0")
 model = bench.build_model().to(dev).configure_voxelizer(bench.VOXEL_CFG)
-scene = synth_scene(bench.N_TARGET, seed=0)
-pts = torch.from_numpy(scene).to(dev)
-off = torch.tensor([0, len(scene)], dtype=torch.int32, device=dev)
+nb = int(os.environ.get("FD_BATCH", "1"))
+scenes = [synth_scene(bench.N_TARGET, seed=i) for i in range(nb)]
+pts = torch.from_numpy(np.concatenate(scenes)).to(dev)
+off = torch.tensor(np.concatenate([[0], np.cumsum([len(s) for s in scenes])]), dtype=torch.int32, device=dev)
 n = int(os.environ.get("FD_ITERS", "3"))
 with torch.no_grad():
     for i in range(n):
