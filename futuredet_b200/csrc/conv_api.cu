@@ -100,6 +100,16 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
       FD_REQUIRE(d->n_out_cap == d->B * d->Hout * d->Wout && !d->d_n_out, "fd_conv_forward: conv2d rows must be B*Hout*Wout");
       return run(a);
     }
+    case FD_GATHER_CONV2D_DGRAD: {
+      // training: data gradient of a Conv2d; rows = pixels of the conv's input grid (Hout x Wout of this descriptor)
+      FD_REQUIRE(d->B >= 1 && d->Hin >= 1 && d->Win >= 1 && d->Hout >= 1 && d->Wout >= 1 && d->kh >= 1 && d->kw >= 1 &&
+                     d->sh >= 1 && d->sw >= 1 && d->ph >= 0 && d->pw >= 0, "fd_conv_forward: bad conv2d-dgrad geometry");
+      FD_REQUIRE(d->K == d->kh * d->kw, "fd_conv_forward: K != kh*kw");
+      FD_REQUIRE(d->Hin == (d->Hout + 2 * d->ph - d->kh) / d->sh + 1 && d->Win == (d->Wout + 2 * d->pw - d->kw) / d->sw + 1,
+                 "fd_conv_forward: conv2d-dgrad: dy grid inconsistent with the conv geometry");
+      FD_REQUIRE(d->n_out_cap == d->B * d->Hout * d->Wout && !d->d_n_out, "fd_conv_forward: conv2d-dgrad rows must be B*H*W of the conv input");
+      return run(a);
+    }
     case FD_GATHER_CONVT2D: {
       // ConvTranspose2d with kernel == stride, no padding: each output pixel receives exactly one
       // (input pixel, kernel offset) product -> kh*kw independent 1x1 GEMMs with interleaved stores.

@@ -34,6 +34,15 @@ __device__ __forceinline__ int gather_row(const ConvArgs& a, int o, int k) {
   int r = o - b * hw;
   int oy = r / a.Wout, ox = r - oy * a.Wout;
   int ky = k / a.kw, kx = k - ky * a.kw;
+  if (a.mode == FD_GATHER_CONV2D_DGRAD) {
+    // data gradient of Conv2d: rows are pixels of the conv's INPUT grid (Hout x Wout here), the gathered tensor is
+    // dL/dy on the conv's OUTPUT grid (Hin x Win here); (y,x) receives dy[(y+p-ky)/s, (x+p-kx)/s] @ W[k]^T
+    int ty = oy + a.ph - ky, tx = ox + a.pw - kx;
+    if (ty < 0 || tx < 0 || ty % a.sh != 0 || tx % a.sw != 0) return -1;
+    int gy = ty / a.sh, gx = tx / a.sw;
+    if (gy >= a.Hin || gx >= a.Win) return -1;
+    return (b * a.Hin + gy) * a.Win + gx;
+  }
   int iy = oy * a.sh - a.ph + ky, ix = ox * a.sw - a.pw + kx;
   if (iy < 0 || iy >= a.Hin || ix < 0 || ix >= a.Win) return -1;
   return (b * a.Hin + iy) * a.Win + ix;

@@ -87,7 +87,26 @@ class VoxelNet(SingleStageDetector):
             x = self.neck(x, out_fmt=fmt)
         return x, voxel_feature
 
+    def native_trainer(self, precision=None, attach_grads=True):
+        """The NativeTrainer of this model (train-mode forward + hand-written backward), created on first use."""
+        from . import train
+        key = (precision or self.train_precision, attach_grads)
+        tr = self.__dict__.get("_trainer")
+        if tr is None or tr[0] != key:
+            tr = (key, train.NativeTrainer(self, precision=key[0], attach_grads=attach_grads))
+            self.__dict__["_trainer"] = tr
+        return tr[1]
+
+    train_precision = "fp32"
+
     def forward(self, example, return_loss=True, **kwargs):
+        if self.training and return_loss:
+            # training mode (trainer.py:317-344): native train-mode forward now, native backward when the caller runs
+            # `sum(losses["loss"]).backward()`
+            from . import train
+            tr = self.native_trainer(attach_grads=False)
+            losses = tr.forward(example)
+            return train.bridged_losses(tr, losses) if torch.is_grad_enabled() else losses
         num_voxels = example["num_voxels"]
         data = dict(features=example["voxels"], num_voxels=example["num_points"], coors=example["coordinates"],
                     batch_size=len(num_voxels), input_shape=example["shape"][0])

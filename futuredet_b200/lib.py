@@ -40,7 +40,7 @@ class ConvDesc(C.Structure):
     ]
 
 
-GATHER_TABLE, GATHER_CONV2D, GATHER_CONVT2D = 0, 1, 2
+GATHER_TABLE, GATHER_CONV2D, GATHER_CONVT2D, GATHER_CONV2D_DGRAD = 0, 1, 2, 3
 OUTMAP_IDENTITY, OUTMAP_BEV, OUTMAP_BEV_DMAJOR = 0, 1, 2
 PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
@@ -83,6 +83,30 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_fill_i32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    # ---- training
+    "fd_rulebook_transpose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p]),
+    "fd_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]),
+    "fd_bn_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "fd_bn_train_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_affine_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fd_bn_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_col_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_add_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fd_rows_to_bev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "fd_bev_to_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "fd_center_head_loss_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_float, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -1,10 +1,11 @@
-"""CenterHead.loss (standard branch) on the native loss kernels.
+"""CenterHead.loss (standard branch) on the native loss kernels, forward and backward.
 
 Mirrors det3d/models/bbox_heads/center_head.py:396-539 for the standard mode used by the n0 / n3 configs:
 per task  hm_loss = FastFocalLoss(sigmoid-clamped hm, targets of timestep 0),  box_loss_t = RegLoss(cat(reg, height,
 dim, vel[2t:2t+2], rot), mask/ind of timestep 0, anno_box_t[..., [0..7,-2,-1]]),  loc_loss_t = sum(box_loss_t *
 code_weights (t = 0) | code_weights_forecast (t > 0)),  loss = hm_loss + weight * sum_t loc_loss_t.
-Returns the reference's dict of per-task lists.  Forward only in this round (no autograd graph).
+Returns the reference's dict of per-task lists.  `center_head_loss_backward` is the hand-written gradient of the same
+expression w.r.t. every head tensor (what autograd computes under the reference's `loss.backward()`).
 """
 import ctypes as C
 from collections import defaultdict
@@ -25,26 +26,29 @@ def _plane(v, c):
     return v.data_ptr() + 4 * c * v.stride(1), v.stride(0), v.stride(3)
 
 
-def center_head_loss(head, example, preds_dicts):
-    lib = L.load()
-    rets = []
-    for task_id, p in enumerate(preds_dicts):
+class _TaskArgs:
+    """Device-side argument tables of one task (shared by the forward and backward kernels)."""
+
+    def __init__(self, head, example, p, task_id):
         hm = p["hm"]
         dev = hm.device
-        B, Cc, H, W = hm.shape
-        T = head.timesteps
+        self.dev = dev
+        self.B, self.Cc, self.H, self.W = hm.shape
+        self.T = T = head.timesteps
         if not all(k in p for k in ("reg", "height", "dim", "vel", "rot")):
             raise NotImplementedError("CenterHead.loss: only the vel+rot box encoding of the n0/n3 configs is implemented")
-        hm_t = example["hm"][0][task_id].to(dev, torch.float32).contiguous()
-        ind = example["ind"][0][task_id].to(dev, torch.int64).contiguous()
-        mask = example["mask"][0][task_id].to(dev, torch.uint8).contiguous()
-        cat = example["cat"][0][task_id].to(dev, torch.int64).contiguous()
-        masks_t = [example["mask"][i][task_id].to(dev, torch.uint8).contiguous() for i in range(T)]
-        tgts = [example["anno_box"][i][task_id].to(dev, torch.float32).contiguous() for i in range(T)]
-        M = ind.shape[1]
-        tgt_dim = tgts[0].shape[-1]
-        sel = torch.tensor([s % tgt_dim for s in TGT_SEL], dtype=torch.int32, device=dev)
-        NC = len(TGT_SEL)
+        self.hm = hm
+        self.hm_t = example["hm"][0][task_id].to(dev, torch.float32).contiguous()
+        self.ind = example["ind"][0][task_id].to(dev, torch.int64).contiguous()
+        self.mask = example["mask"][0][task_id].to(dev, torch.uint8).contiguous()
+        self.cat = example["cat"][0][task_id].to(dev, torch.int64).contiguous()
+        self.masks_t = [example["mask"][i][task_id].to(dev, torch.uint8).contiguous() for i in range(T)]
+        self.tgts = [example["anno_box"][i][task_id].to(dev, torch.float32).contiguous() for i in range(T)]
+        self.M = self.ind.shape[1]
+        self.tgt_dim = self.tgts[0].shape[-1]
+        self.sel = torch.tensor([s % self.tgt_dim for s in TGT_SEL], dtype=torch.int32, device=dev)
+        self.NC = len(TGT_SEL)
+        self.planes = []            # (tensor, channel) per (t, c)
         ptrs, sbs, ssps = [], [], []
         for t in range(T):
             planes = ([(p["reg"], 0), (p["reg"], 1), (p["height"], 0), (p["dim"], 0), (p["dim"], 1), (p["dim"], 2),
@@ -52,25 +56,60 @@ def center_head_loss(head, example, preds_dicts):
             for v, c in planes:
                 a, sb, ssp = _plane(v, c)
                 ptrs.append(a); sbs.append(sb); ssps.append(ssp)
+            self.planes += planes
         i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=dev)
-        d_ptr, d_sb, d_ssp = i64(ptrs), i64(sbs), i64(ssps)
-        d_tgt = i64([t_.data_ptr() for t_ in tgts])
-        d_mask_t = i64([m.data_ptr() for m in masks_t])
-        cw = torch.tensor(head.code_weights, dtype=torch.float32, device=dev)
-        cwf = torch.tensor([float(x) for x in head.code_weights_forecast], dtype=torch.float32, device=dev)
-        out = torch.empty((3 + T + T * NC,), dtype=torch.float32, device=dev)
-        ws = torch.empty((lib.fd_center_loss_workspace_bytes(),), dtype=torch.uint8, device=dev)
-        hm_addr, hm_sb, hm_ssp = _plane(hm, 0)
-        rc = lib.fd_center_head_loss(C.c_void_p(hm_addr), hm_sb, hm.stride(1), hm_ssp, _ptr(hm_t), B, Cc, H, W, _ptr(ind),
-                                     _ptr(mask), _ptr(cat), _ptr(d_mask_t), M, T, NC, _ptr(d_ptr), _ptr(d_sb), _ptr(d_ssp),
-                                     _ptr(d_tgt), tgt_dim, _ptr(sel), _ptr(cw), _ptr(cwf), float(head.weight), _ptr(out),
-                                     _ptr(ws), _stream())
+        self.ptrs = ptrs
+        self.d_ptr, self.d_sb, self.d_ssp = i64(ptrs), i64(sbs), i64(ssps)
+        self.d_tgt = i64([t_.data_ptr() for t_ in self.tgts])
+        self.d_mask_t = i64([m.data_ptr() for m in self.masks_t])
+        self.cw = torch.tensor(head.code_weights, dtype=torch.float32, device=dev)
+        self.cwf = torch.tensor([float(x) for x in head.code_weights_forecast], dtype=torch.float32, device=dev)
+        self.weight = float(head.weight)
+        self.hm_addr, self.hm_sb, self.hm_ssp = _plane(hm, 0)
+
+
+def center_head_loss(head, example, preds_dicts, return_ctx=False):
+    lib = L.load()
+    rets, ctxs = [], []
+    for task_id, p in enumerate(preds_dicts):
+        a = _TaskArgs(head, example, p, task_id)
+        T, NC = a.T, a.NC
+        out = torch.empty((3 + T + T * NC,), dtype=torch.float32, device=a.dev)
+        ws = torch.empty((lib.fd_center_loss_workspace_bytes(),), dtype=torch.uint8, device=a.dev)
+        rc = lib.fd_center_head_loss(C.c_void_p(a.hm_addr), a.hm_sb, a.hm.stride(1), a.hm_ssp, _ptr(a.hm_t), a.B, a.Cc,
+                                     a.H, a.W, _ptr(a.ind), _ptr(a.mask), _ptr(a.cat), _ptr(a.d_mask_t), a.M, T, NC,
+                                     _ptr(a.d_ptr), _ptr(a.d_sb), _ptr(a.d_ssp), _ptr(a.d_tgt), a.tgt_dim, _ptr(a.sel),
+                                     _ptr(a.cw), _ptr(a.cwf), a.weight, _ptr(out), _ptr(ws), _stream())
         L.check(rc, "fd_center_head_loss")
         elem = out[3 + T:].view(T, NC)
-        rets.append({"loss": out[0], "hm_loss": out[1].detach().cpu(), "loc_loss": [out[3 + t] for t in range(T)],
-                     "loc_loss_elem": [elem[t].detach().cpu() for t in range(T)], "num_positive": out[2]})
+        rets.append({"loss": out[0], "hm_loss": out[1].detach().cpu() if not return_ctx else out[1],
+                     "loc_loss": [out[3 + t] for t in range(T)],
+                     "loc_loss_elem": [elem[t].detach().cpu() if not return_ctx else elem[t] for t in range(T)],
+                     "num_positive": out[2]})
+        ctxs.append(a)
     merged = defaultdict(list)
     for r in rets:
         for k, v in r.items():
             merged[k].append(v)
-    return merged
+    return (merged, ctxs) if return_ctx else merged
+
+
+def center_head_loss_backward(ctx, out_base, gout_base, gscale=None):
+    """Gradient of one task's loss w.r.t. its head tensors.  `ctx`: the _TaskArgs of the forward call (its `hm` now holds
+    the clamped probabilities); every head tensor must be a view of `out_base`; the gradients are written into the
+    same positions of `gout_base` (same shape/strides as out_base, zero-filled by the caller)."""
+    lib = L.load()
+    a = ctx
+    delta = gout_base.data_ptr() - out_base.data_ptr()
+    lo, hi = out_base.data_ptr(), out_base.data_ptr() + out_base.numel() * 4
+    for ptr in a.ptrs + [a.hm_addr]:
+        if not (lo <= ptr < hi):
+            raise RuntimeError("center_head_loss_backward: head tensors must be views of the given output buffer")
+    d_gptr = torch.tensor([q + delta for q in a.ptrs], dtype=torch.int64, device=a.dev)
+    rc = lib.fd_center_head_loss_backward(C.c_void_p(a.hm_addr), C.c_void_p(a.hm_addr + delta), a.hm_sb, a.hm.stride(1),
+                                          a.hm_ssp, _ptr(a.hm_t), a.B, a.Cc, a.H, a.W, _ptr(a.ind), _ptr(a.mask),
+                                          _ptr(a.cat), a.M, a.T, a.NC, _ptr(a.d_ptr), _ptr(d_gptr), _ptr(a.d_sb),
+                                          _ptr(a.d_ssp), _ptr(a.d_tgt), a.tgt_dim, _ptr(a.sel), _ptr(a.cw), _ptr(a.cwf),
+                                          a.weight, _ptr(gscale), _stream())
+    L.check(rc, "fd_center_head_loss_backward")
+    return gout_base

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 1
+#define FD_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------ */
 int         fd_version(void);
@@ -173,7 +173,11 @@ typedef struct fd_conv_desc {
   int32_t        precision;   /* FD_PREC_* */
 } fd_conv_desc;
 
-enum { FD_GATHER_TABLE = 0, FD_GATHER_CONV2D = 1, FD_GATHER_CONVT2D = 2 };
+enum { FD_GATHER_TABLE = 0, FD_GATHER_CONV2D = 1, FD_GATHER_CONVT2D = 2,
+       /* data gradient of a Conv2d (training): rows = pixels of the conv's input grid (given as Hout x Wout), gathered
+        * tensor = dL/dy on the conv's output grid (given as Hin x Win), kh/kw/sh/sw/ph/pw = the conv's own geometry,
+        * weights = W[k]^T ([K, Cout, Cin]).                                                                      */
+       FD_GATHER_CONV2D_DGRAD = 3 };
 /* FD_OUTMAP_BEV: channel = c*D + z (the reference's dense().view() order).  FD_OUTMAP_BEV_DMAJOR: channel = z*C + c
  * (contiguous per row -> vector stores); only for consumers that permute their input channels accordingly. */
 enum { FD_OUTMAP_IDENTITY = 0, FD_OUTMAP_BEV = 1, FD_OUTMAP_BEV_DMAJOR = 2 };
@@ -221,6 +225,73 @@ int fd_center_head_loss(float* d_hm, int64_t hm_sb, int64_t hm_sc, int64_t hm_ss
                         const float* const* d_tgt_ptr, int tgt_dim, const int32_t* d_tgt_sel,
                         const float* d_code_w, const float* d_code_w_forecast, float weight, float* d_out,
                         void* d_workspace, void* stream);
+
+/* ---- training: backward kernels -----------------------------------------------------------------------
+ * The reference trains through torch autograd over spconv's `indice_conv_backward`, cuDNN and ATen batch-norm
+ * (det3d/torchie/trainer/trainer.py:317-344 -> loss.backward(); det3d/models/backbones/scn.py:37-176,
+ * det3d/models/necks/rpn.py:124-159, det3d/models/bbox_heads/center_head.py:129-174,396-539).  Here every backward
+ * op is an explicit kernel; all operands are FD_FMT_FP32 rows ("channels last") with explicit row strides.
+ *
+ * Data gradient of a sparse conv = fd_conv_forward over the TRANSPOSED rulebook with W[k]^T:
+ *   SubMConv3d : the table is its own transpose with the offsets mirrored (nbrT[k] = nbr[K-1-k]);
+ *   SparseConv3d: fd_rulebook_transpose builds nbrT[k][i] = o for every pair (i = nbr[k][o]).
+ * Data gradient of Conv2d = fd_conv_forward in FD_GATHER_CONV2D_DGRAD mode; of ConvTranspose2d(k == s) = a
+ * k x k stride-k FD_GATHER_CONV2D over dL/dy.                                                                */
+int fd_rulebook_transpose(const int32_t* d_nbr, int nbr_stride, const int32_t* d_n_out, int n_out_cap, int K,
+                          int32_t* d_nbr_t, int nbr_t_stride, int n_in_cap, void* stream);
+
+/* Weight gradient of any convolution fd_conv_forward can run: dW[k] += gather_k(in)^T @ dy  (spconv
+ * `indice_conv_backward` filter gradient / cuDNN wgrad).  `desc` describes the FORWARD convolution with
+ * d_in = the layer input, d_out = dL/dy (read only) laid out as the forward output (out_map / out_stride honoured);
+ * scale/shift/residual/relu/d_w are ignored.  Accumulates with fp32 atomics into d_dw [K,Cin,Cout]: the caller
+ * zeroes it.  fp32 rows only.                                                                                */
+int fd_conv_wgrad(const fd_conv_desc* desc, float* d_dw, void* stream);
+
+/* BatchNorm1d/2d in training mode over the first n rows of x [n, C] (det3d/models/utils/norm.py:59-64 ->
+ * torch.nn.BatchNorm*: biased batch variance for normalisation, unbiased for the running estimate).
+ * fd_bn_train_stats writes mean / invstd (saved for backward) and the folded scale = gamma*invstd,
+ * shift = beta - mean*scale consumed by fd_affine_act (or by a fused conv epilogue), and updates the running
+ * statistics with `momentum` (pass NULL to skip).  Deterministic two-stage reduction in fp64.               */
+size_t fd_bn_workspace_bytes(int C);
+int fd_bn_train_stats(const float* d_x, int x_stride, int C, const int32_t* d_n, int64_t n_cap, float eps,
+                      float momentum, const float* d_gamma, const float* d_beta, float* d_running_mean,
+                      float* d_running_var, float* d_mean, float* d_invstd, float* d_scale, float* d_shift,
+                      void* d_workspace, void* stream);
+/* y = act(x * scale[c] + shift[c] (+ res)), rows < n; scale/shift/res may be NULL (1 / 0 / none). */
+int fd_affine_act(const float* d_x, int x_stride, int C, const float* d_scale, const float* d_shift,
+                  const float* d_res, int res_stride, int relu, float* d_y, int y_stride, const int32_t* d_n,
+                  int64_t n_cap, void* stream);
+/* Backward of y = act(bn(x) (+ res)):  dz = dy * [y > 0] (relu) ;  dgamma = sum dz*xhat ; dbeta = sum dz ;
+ * dx = gamma*invstd*(dz - dbeta/n - xhat*dgamma/n) ;  dres = dz (d_dres may be NULL).                        */
+int fd_bn_backward(const float* d_dy, int dy_stride, const float* d_y, int y_stride, int relu, const float* d_x,
+                   int x_stride, int C, const int32_t* d_n, int64_t n_cap, const float* d_mean,
+                   const float* d_invstd, const float* d_gamma, float* d_dx, int dx_stride, float* d_dres,
+                   int dres_stride, float* d_dgamma, float* d_dbeta, void* d_workspace, void* stream);
+/* out[c] = sum_rows x[r, c]  (conv bias gradient). */
+int fd_col_sum(const float* d_x, int x_stride, int C, const int32_t* d_n, int64_t n_cap, float* d_out,
+               void* d_workspace, void* stream);
+/* dst[r, c] += src[r, c]  (gradient accumulation where an activation feeds two consumers). */
+int fd_add_rows(float* d_dst, int dst_stride, const float* d_src, int src_stride, int C, const int32_t* d_n,
+                int64_t n_cap, void* stream);
+/* SparseConvTensor.dense().view(N, C*D, H, W) (scn.py:165-168) as channels-last [B,H,W,C*D] (channel = c*D + z)
+ * and its backward (gather of the BEV gradient back to the active rows).  d_bev is zero-filled by the call.  */
+int fd_rows_to_bev(const float* d_rows, int row_stride, int C, const int32_t* d_coords4, const int32_t* d_n,
+                   int n_cap, int B, int D, int H, int W, float* d_bev, void* stream);
+int fd_bev_to_rows(const float* d_bev, int C, const int32_t* d_coords4, const int32_t* d_n, int n_cap, int B,
+                   int D, int H, int W, float* d_rows, int row_stride, void* stream);
+
+/* Backward of fd_center_head_loss (same argument meaning; d_hm holds the clamped probabilities the forward left
+ * in place).  Writes dL/d(hm logits) densely into d_ghm (same strides as d_hm) and ADDS the masked-L1 gradients
+ * at the object centres into the planes d_gpred_ptr [T*NC] (same strides as the predictions; the caller zeroes
+ * them).  d_gscale: optional device scalar multiplying every gradient (upstream dL), NULL = 1.               */
+int fd_center_head_loss_backward(const float* d_hm, float* d_ghm, int64_t hm_sb, int64_t hm_sc, int64_t hm_ssp,
+                                 const float* d_hm_target, int B, int C, int H, int W, const int64_t* d_ind,
+                                 const uint8_t* d_mask, const int64_t* d_cat, int M, int T, int NC,
+                                 const float* const* d_pred_ptr, float* const* d_gpred_ptr,
+                                 const int64_t* d_pred_sb, const int64_t* d_pred_ssp,
+                                 const float* const* d_tgt_ptr, int tgt_dim, const int32_t* d_tgt_sel,
+                                 const float* d_code_w, const float* d_code_w_forecast, float weight,
+                                 const float* d_gscale, void* stream);
 
 /* small helpers used by the host layer */
 int fd_fill_i32(int32_t* d_ptr, int64_t n, int32_t value, void* stream);

@@ -13,23 +13,27 @@ import torch
 import torch.nn.functional as F
 
 
-def _bn(x, sd, p, eps):
+def _bn(x, sd, p, eps, train=None):
+    """train=None: eval mode; train=momentum: training mode (batch statistics, running stats of sd updated in place)."""
+    if train is None:
+        return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
+                            False, 0.0, eps)
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
-                        False, 0.0, eps)
+                        True, train, eps)
 
 
-def rpn_forward(sd, x, layer_nums, ds_layer_strides, us_layer_strides, prefix="", eps=1e-3):
+def rpn_forward(sd, x, layer_nums, ds_layer_strides, us_layer_strides, prefix="", eps=1e-3, train=None):
     """RPN.forward (rpn.py:150-159), eval mode.  us stride > 1 -> ConvTranspose2d, else Conv2d (rpn.py:78-110)."""
     ups = []
     start = len(layer_nums) - len(us_layer_strides)
     for i, n in enumerate(layer_nums):
         b = "%sblocks.%d." % (prefix, i)
         x = F.conv2d(F.pad(x, (1, 1, 1, 1)), sd[b + "1.weight"], None, stride=ds_layer_strides[i])   # ZeroPad2d(1)+conv
-        x = F.relu(_bn(x, sd, b + "2.", eps))
+        x = F.relu(_bn(x, sd, b + "2.", eps, train))
         for j in range(n):
             k = 4 + 3 * j
             x = F.conv2d(x, sd[b + "%d.weight" % k], None, padding=1)
-            x = F.relu(_bn(x, sd, b + "%d." % (k + 1), eps))
+            x = F.relu(_bn(x, sd, b + "%d." % (k + 1), eps, train))
         if i - start >= 0:
             d = "%sdeblocks.%d." % (prefix, i - start)
             s = us_layer_strides[i - start]
@@ -38,23 +42,23 @@ def rpn_forward(sd, x, layer_nums, ds_layer_strides, us_layer_strides, prefix=""
             else:
                 s = int(round(1 / s))
                 y = F.conv2d(x, sd[d + "0.weight"], None, stride=s)
-            ups.append(F.relu(_bn(y, sd, d + "1.", eps)))
+            ups.append(F.relu(_bn(y, sd, d + "1.", eps, train)))
     return torch.cat(ups, dim=1) if ups else x
 
 
-def center_head_forward(sd, x, head_names_per_task, prefix=""):
+def center_head_forward(sd, x, head_names_per_task, prefix="", train=None):
     """CenterHead.forward in standard mode (center_head.py:375-390): list over tasks of {head: [B,c,H,W]}.
     BatchNorm2d in the head uses the torch default eps 1e-5 (center_head.py:347,136)."""
     p = prefix + "shared_conv."
     x = F.conv2d(x, sd[p + "0.weight"], sd[p + "0.bias"], padding=1)
-    x = F.relu(_bn(x, sd, p + "1.", 1e-5))
+    x = F.relu(_bn(x, sd, p + "1.", 1e-5, train))
     rets = []
     for t, names in enumerate(head_names_per_task):
         ret = {}
         for h in names:
             q = "%stasks.%d.%s." % (prefix, t, h)
             y = F.conv2d(x, sd[q + "0.weight"], sd[q + "0.bias"], padding=1)
-            y = F.relu(_bn(y, sd, q + "1.", 1e-5))
+            y = F.relu(_bn(y, sd, q + "1.", 1e-5, train))
             ret[h] = F.conv2d(y, sd[q + "3.weight"], sd[q + "3.bias"], padding=1)
         rets.append(ret)
     return rets

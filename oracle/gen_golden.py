@@ -7,6 +7,9 @@ that nothing on the GPU box needs the reference.  Usage:  python oracle/gen_gold
                      + reference VoxelFeatureExtractorV3 (det3d/models/readers/voxel_encoder.py:17-24)
   neck_head.pt       reference RPN (det3d/models/necks/rpn.py) + CenterHead forward & loss
                      (det3d/models/bbox_heads/center_head.py:375-539) at reduced widths, random BN statistics
+  neck_head_train.pt the same reference classes in TRAINING mode: loss dict, every parameter gradient after
+                     `sum(loss["loss"]).backward()` (trainer.py:85,317-344), the input gradient and the updated
+                     BatchNorm running statistics  (`python oracle/gen_golden.py train` regenerates only this file)
 """
 import importlib.util
 import logging
@@ -104,8 +107,42 @@ def make_targets(B, H, W, timesteps, gen, max_objs=20):
     return ex
 
 
+def gen_train(M):
+    """Reference RPN + CenterHead in training mode: forward, loss, backward."""
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(7)
+    neck = M.build_neck(dict(NECK_CFG, logger=logging.getLogger("RPN")))
+    head = M.build_head(dict(HEAD_CFG))
+    randomise_bn(neck, gen)
+    randomise_bn(head, gen)
+    neck.train()
+    head.train()
+    init = dict(neck_state={k: v.clone() for k, v in neck.state_dict().items()},
+                head_state={k: v.clone() for k, v in head.state_dict().items()})
+    x = torch.randn((2, 8, 12, 12), generator=gen).requires_grad_(True)
+    feat = neck(x)
+    preds = head(feat)
+    example = make_targets(2, feat.shape[2], feat.shape[3], 3, gen)
+    loss = head.loss(example, preds)
+    total = sum(loss["loss"])
+    total.backward()
+    grads = {"neck." + k: p.grad.clone() for k, p in neck.named_parameters()}
+    grads.update({"head." + k: p.grad.clone() for k, p in head.named_parameters()})
+    torch.save(dict(neck_cfg=NECK_CFG, head_cfg=HEAD_CFG, x=x.detach(), x_grad=x.grad.clone(), example=example,
+                    total=total.detach(), grads=grads,
+                    loss={k: [t.detach() if torch.is_tensor(t) else t for t in v] if isinstance(v, list) else v
+                          for k, v in loss.items()},
+                    neck_state_after={k: v.clone() for k, v in neck.state_dict().items()},
+                    head_state_after={k: v.clone() for k, v in head.state_dict().items()}, **init),
+               os.path.join(OUT, "neck_head_train.pt"))
+    print("neck_head_train: total loss %.6f, %d parameter gradients" % (float(total), len(grads)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "train" in sys.argv[1:]:
+        gen_train(import_ref_models())
+        return
     pco = load_ref_voxelizer()
     M = import_ref_models()
     from det3d.models.readers.voxel_encoder import VoxelFeatureExtractorV3
@@ -141,6 +178,7 @@ def main():
                os.path.join(OUT, "neck_head.pt"))
     print("neck_head: neck_out", tuple(feat.shape), {k: tuple(v.shape) for k, v in preds[0].items()})
     print("loss keys", {k: (v[0] if isinstance(v, list) else v) for k, v in loss.items()})
+    gen_train(M)
 
 
 if __name__ == "__main__":

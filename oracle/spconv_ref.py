@@ -103,7 +103,7 @@ def indice_conv(features, weight, nbr, n_out):
     """spconv-1.x indice_conv forward: per offset gather -> mm -> index_add_, fp32.
     features [N_in,Cin] torch fp32; weight [kD,kH,kW,Cin,Cout] or [K,Cin,Cout]."""
     w = weight.reshape(-1, weight.shape[-2], weight.shape[-1])
-    out = torch.zeros((n_out, w.shape[-1]), dtype=torch.float32)
+    out = torch.zeros((n_out, w.shape[-1]), dtype=features.dtype)
     for k, (i, o) in enumerate(nbr_to_pairs(nbr)):
         if len(i) == 0:
             continue
@@ -116,13 +116,24 @@ def bn_eval(x, sd, prefix, eps):
                         sd[prefix + "bias"], False, 0.0, eps)
 
 
-def backbone_forward(sd, voxel_features, coors, batch_size, input_shape, prefix="", eps=1e-3, return_stages=False):
+def bn_train(momentum):
+    """Training-mode BatchNorm1d (batch statistics; updates sd's running statistics in place, as nn.BatchNorm1d)."""
+    def fn(x, sd, prefix, eps):
+        return F.batch_norm(x, sd[prefix + "running_mean"], sd[prefix + "running_var"], sd[prefix + "weight"],
+                            sd[prefix + "bias"], True, momentum, eps)
+    return fn
+
+
+def backbone_forward(sd, voxel_features, coors, batch_size, input_shape, prefix="", eps=1e-3, return_stages=False,
+                     bn_eval=bn_eval):
     """SpMiddleResNetFHD.forward (scn.py:148-176) in eval mode, state_dict `sd` in the reference key layout.
     voxel_features [M,5] fp32 torch, coors [M,4] int (b,z,y,x), input_shape = grid (x,y,z).
-    Returns dense [B, C*D, H, W] (and per-stage dicts when return_stages)."""
+    Returns dense [B, C*D, H, W] (and per-stage dicts when return_stages).
+    bn_eval=bn_train(momentum) switches every BatchNorm1d to training mode (torch-autograd differentiable: the
+    oracle of the native backward pass).  Differentiable w.r.t. every tensor of `sd` that requires grad."""
     shape = [int(input_shape[2]) + 1, int(input_shape[1]), int(input_shape[0])]          # scn.py:151
     coords = np.asarray(coors, np.int32)
-    x = voxel_features.float()
+    x = voxel_features if voxel_features.dtype == torch.float64 else voxel_features.float()
     stages = {}
     rb_cache = {}
 
@@ -162,7 +173,7 @@ def backbone_forward(sd, voxel_features, coors, batch_size, input_shape, prefix=
     stages["extra_conv"] = (x, coords, shape)
     stages["subm_rulebooks"] = rb_cache
     C = x.shape[1]
-    dense = torch.zeros((batch_size, C, shape[0], shape[1], shape[2]), dtype=torch.float32)      # .dense()
+    dense = torch.zeros((batch_size, C, shape[0], shape[1], shape[2]), dtype=x.dtype)             # .dense()
     ci = torch.from_numpy(coords.astype(np.int64))
     dense[ci[:, 0], :, ci[:, 1], ci[:, 2], ci[:, 3]] = x
     dense = dense.view(batch_size, C * shape[0], shape[1], shape[2])                              # scn.py:167-168

@@ -65,3 +65,53 @@ def test_bench_reference_arm_contract_two_ranks():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["higher_is_better"] is True and line["n_gpus"] == 2
+
+
+def _grad_worker(rank, world, port, q):
+    from torch import nn
+    from futuredet_b200 import train
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)                                   # ranks start with DIFFERENT parameters ...
+    model = nn.Sequential(nn.Linear(5, 7), nn.BatchNorm1d(7), nn.Linear(7, 3))
+    shard.broadcast_parameters(model)                         # ... and leave with rank 0's
+    buckets = train.GradBuckets(list(model.parameters()), bucket_bytes=64)      # tiny buckets -> several all-reduces
+    sync = shard.GradSync(buckets)
+    launched = []
+    orig = sync._launch
+    sync._launch = lambda i, flat: (launched.append(i), orig(i, flat))[1]
+    buckets.on_bucket_ready = sync._launch
+    buckets.zero()
+    params = [p for p in model.parameters()]
+    for j, p in enumerate(reversed(params)):                  # backward order
+        buckets.grad(p).fill_(float(rank + 1) * (j + 1))
+        buckets.done(p)
+    buckets.flush()
+    sync.finish()
+    got = [float(p.grad.flatten()[0]) for p in reversed(params)]
+    psum = float(sum(p.detach().sum() for p in model.parameters()))
+    q.put((rank, got, launched, len(buckets.buckets), psum, sync.bytes_reduced))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_allreduce_world2():
+    """The training exchange: bucketed all-reduce(sum)/world of the parameter gradients, launched as
+    buckets complete in backward order; parameters broadcast from rank 0 first."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, g0, l0, nb0, ps0, by0), (_, g1, l1, nb1, ps1, by1) = res
+    want = [1.5 * (j + 1) for j in range(len(g0))]            # mean of (1, 2) * (j + 1)
+    assert g0 == want and g1 == want
+    assert nb0 == nb1 and nb0 >= 2 and l0 == list(range(nb0)) and l1 == l0      # every bucket once, in backward order
+    assert abs(ps0 - ps1) < 1e-6                                                 # same parameters after the broadcast
+    n_params = 5 * 7 + 7 + 7 + 7 + 7 * 3 + 3
+    assert by0 == by1 == 4 * n_params                                            # one exchange of every gradient byte
