@@ -232,6 +232,59 @@ def voxelize_roofline(model, dev, n_scenes=32):
                 algorithmic_bytes=nbytes, ms=ms, points=int(pts.shape[0]), voxels=m, peak_source=pk["src"] + " HBM copy")
 
 
+def train_bench(args, rank, world, dev):
+    """BASELINE configs[2]/[3]: forecast_n3 (7-timestep heads) forward + backward (+ AdamW step) per sample, one
+    305k-point scene per GPU per step; for world > 1 the parameter gradients are all-reduced over NCCL (bucketed,
+    overlapped with backward: shard.GradSync).  Auxiliary measurement, reported under "train" in the JSON line."""
+    import futuredet_b200 as fb
+    from futuredet_b200 import lib, shard, train
+    from futuredet_b200.synth import synth_targets
+    torch.manual_seed(0)
+    m = fb.build_detector(model_cfg(timesteps=7)).to(dev).train()
+    m.configure_voxelizer(VOXEL_CFG, training=True)
+    shard.broadcast_parameters(m)
+    tr = train.NativeTrainer(m, precision=args.train_precision)
+    sync = shard.GradSync(tr.grads)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
+    B = 1
+    scene = synth_scene(N_TARGET, seed=shard.scene_seed(rank, 7, 0, B))
+    pts = torch.from_numpy(scene).to(dev)
+    off = torch.tensor([0, len(scene)], dtype=torch.int32, device=dev)
+    ex = synth_targets(B, 180, 180, 7, seed=rank)
+    ex = {k: [[t.to(dev) for t in ts] for ts in v] for k, v in ex.items()}
+    losses = None
+
+    def step():
+        nonlocal losses
+        losses = tr.step(ex, points=pts, batch_offsets=off)
+        sync.finish()
+        opt.step()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    n0 = lib.launch_count()
+    sync.bytes_reduced = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = barrier_max(e0.elapsed_time(e1), world, dev) / args.train_steps
+    loss = float(sum(losses["loss"]))
+    return dict(workload="forecast_n3 (7-timestep heads) car, fwd+bwd+AdamW, 1 x 305k-pt scene per GPU per step "
+                         "(BASELINE configs[2]; configs[3] for n_gpus > 1)", ms_per_step=ms,
+                samples_per_s=B * world / (ms / 1e3), precision=args.train_precision, steps=args.train_steps,
+                gpu_launches_per_step=(lib.launch_count() - n0) // args.train_steps, loss=loss,
+                params=sum(p.numel() for p in m.parameters()),
+                allreduce_bytes_per_step=sync.bytes_reduced // max(args.train_steps, 1),
+                exchange="bucketed all-reduce(sum)/world of the parameter gradients, %s" %
+                         ("NCCL over NVLink, overlapped with backward" if world > 1 else "single rank: none"))
+
+
 def run_gpu(args, rank, world, local):
     from futuredet_b200 import lib, neck, shard, sparse
     if not torch.cuda.is_available():
@@ -296,6 +349,12 @@ def run_gpu(args, rank, world, local):
         ms_e2e, _ = timed(step_e2e)
         prof = conv_profile(model, *pool_dev[0]) if rank == 0 else None
         vox_roof = voxelize_roofline(model, dev) if rank == 0 else None
+    train_info = None
+    if args.train_steps > 0:
+        pool_dev.clear()
+        flush = None
+        torch.cuda.empty_cache()
+        train_info = train_bench(args, rank, world, dev)
     if rank != 0:
         return
     scenes = B * world * args.steps
@@ -329,6 +388,8 @@ def run_gpu(args, rank, world, local):
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_voxelize=vox_roof,
                 cpu_baseline=cpu_baseline)
+    if train_info is not None:
+        line["train"] = train_info
     print(json.dumps(line))
 
 
@@ -342,6 +403,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("FD_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="bf16x3 (default): tcgen05 tensor cores with a 3-term bf16 split, holds the 1e-3 parity contract; "
                          "fp32: CUDA-core exact arm; bf16: single pass, outside the parity contract")
+    ap.add_argument("--train-steps", type=int, default=3, help="timed forecast_n3 fwd+bwd steps reported under 'train' (0: skip)")
+    ap.add_argument("--train-precision", default="bf16x3", choices=["fp32", "bf16x3"],
+                    help="forward / data-gradient convolutions of the training step (weight gradients are always fp32)")
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus, init=args.impl != "reference")
     if args.impl == "reference":

@@ -49,3 +49,34 @@ def random_points(n=50_000, seed=0, snap_frac=0.0, pile=0):
         sel = rng.integers(0, n, pile)
         p[sel, :3] = centres[rng.integers(0, 50, pile)] + rng.uniform(-0.03, 0.03, (pile, 3)).astype(np.float32)
     return p
+
+
+def synth_targets(batch, H, W, timesteps, n_obj=50, max_objs=500, seed=0, sigma=2.0):
+    """Seeded CenterPoint training targets in the collate layout `example[key][timestep][task] -> Tensor[B, ...]`
+    (det3d/torchie/parallel/collate.py:208-232; produced in the reference by AssignLabel,
+    det3d/datasets/pipelines/preprocess.py:464-546): `n_obj` random object centres per scene splatted as Gaussians
+    into `hm [B,1,H,W]`, `ind / cat [B,max_objs] int64`, `mask [B,max_objs] uint8`, `anno_box [B,max_objs,14]`."""
+    import torch
+    rng = np.random.default_rng(seed)
+    ys, xs = np.mgrid[0:H, 0:W]
+    ex = {k: [] for k in ("hm", "anno_box", "ind", "mask", "cat")}
+    cy = rng.integers(0, H, (batch, n_obj))
+    cx = rng.integers(0, W, (batch, n_obj))
+    for t in range(timesteps):
+        hm = np.zeros((batch, 1, H, W), np.float32)
+        ind = np.zeros((batch, max_objs), np.int64)
+        mask = np.zeros((batch, max_objs), np.uint8)
+        box = np.zeros((batch, max_objs, 14), np.float32)
+        for b in range(batch):
+            for j in range(n_obj):
+                g = np.exp(-((ys - cy[b, j]) ** 2 + (xs - cx[b, j]) ** 2) / (2 * sigma * sigma)).astype(np.float32)
+                hm[b, 0] = np.maximum(hm[b, 0], g)
+            ind[b, :n_obj] = cy[b] * W + cx[b]
+            mask[b, :n_obj] = 1
+            box[b, :n_obj] = rng.standard_normal((n_obj, 14)).astype(np.float32)
+        ex["hm"].append([torch.from_numpy(hm)])
+        ex["anno_box"].append([torch.from_numpy(box)])
+        ex["ind"].append([torch.from_numpy(ind)])
+        ex["mask"].append([torch.from_numpy(mask)])
+        ex["cat"].append([torch.zeros((batch, max_objs), dtype=torch.int64)])
+    return ex

@@ -392,6 +392,7 @@ class NativeTrainer:
         losses, ctxs = center_head_loss(m.bbox_head, example, preds, return_ctx=True)
         self.tape, self._loss_ctx = tape, (ctxs, outs)
         self.preds = preds
+        self.activations = dict(bev=bev, neck_out=x, head_out=outs)      # Vars (value + gradient after backward)
         return losses
 
     def backward(self, gscales=None):
