@@ -222,6 +222,9 @@ class CenterHead(nn.Module):
         from .loss import center_head_loss
         return center_head_loss(self, example, preds_dicts)
 
+    @torch.no_grad()
     def predict(self, example, preds_dicts, test_cfg, **kwargs):
-        raise NotImplementedError("CenterHead.predict (decode + rotated NMS) is the first 'next' row of "
-                                  "SURVEY.md section 8f; not built in this round")
+        """decode + score/range masks + rotated NMS per forecast timestep (center_head.py:541-747) -> list over samples
+        of {box3d_lidar [n,9], scores [n], label_preds [n], metadata}."""
+        from .predict import center_head_predict
+        return center_head_predict(self, example, preds_dicts, test_cfg)

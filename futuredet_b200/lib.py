@@ -83,6 +83,13 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_fill_i32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    # ---- predict
+    "fd_center_predict_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "fd_center_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_float, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_boxes_iou_bev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     # ---- training
     "fd_rulebook_transpose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p]),

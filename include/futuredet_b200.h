@@ -293,6 +293,30 @@ int fd_center_head_loss_backward(const float* d_hm, float* d_ghm, int64_t hm_sb,
                                  const float* d_code_w, const float* d_code_w_forecast, float weight,
                                  const float* d_gscale, void* stream);
 
+/* ---- CenterHead.predict: decode + masks + top-k + rotated BEV NMS, all on device ---------------------------
+ * Replaces det3d/models/bbox_heads/center_head.py:541-747 (predict / post_processing, standard mode),
+ * det3d/core/bbox/box_torch_ops.py:248-276 (rotate_nms_pcdet) and det3d/ops/iou3d_nms (nms_gpu:
+ * src/iou3d_nms.cpp:90-136 + src/iou3d_nms_kernel.cu:264-311, which copies a bit mask to the host, sweeps it there
+ * and cudaMalloc/cudaFrees per call).
+ *   d_out       head output of one task, channels last [B, H*W, row_stride]; c_* = first channel of each head
+ *               (reg 2, height 1, dim 3, rot 2 (sin, cos), hm num_cls); c_vel [T] = first velocity channel of every
+ *               emitted forecast timestep (center_head.py:561-570: the timesteps share everything but `vel`, so
+ *               selection and NMS run once per sample and the kept boxes are emitted T times)
+ *   candidates  cells with sigmoid(hm).max > score_threshold and (x, y, z) inside post_center_range6; ordered by
+ *               score (descending, ties by cell index), first pre_max (<= 1024) enter the NMS, first post_max kept
+ *   outputs     d_boxes [B,T,post_max,9] (x,y,z,w,l,h,vx,vy,rot), d_scores / d_labels [B,T,post_max],
+ *               d_cells [B,post_max] (BEV cell index of every kept box), d_count [B]                         */
+size_t fd_center_predict_workspace_bytes(int B, int H, int W);
+int fd_center_predict(const float* d_out, int row_stride, int c_reg, int c_height, int c_dim, int c_rot,
+                      const int32_t* c_vel, int T, int c_hm, int num_cls, int B, int H, int W, float score_threshold,
+                      const float* post_center_range6, float out_size_factor, float voxel_x, float voxel_y,
+                      float pc_x0, float pc_y0, float nms_iou_threshold, int pre_max, int post_max, float* d_boxes,
+                      float* d_scores, int32_t* d_labels, int32_t* d_cells, int32_t* d_count, void* d_workspace,
+                      void* stream);
+/* Pairwise rotated BEV IoU of boxes [n,7] (x,y,z,dx,dy,dz,heading) -> d_iou [na,nb]; replaces boxes_iou_bev_gpu
+ * (det3d/ops/iou3d_nms/src/iou3d_nms.cpp:61-88, iou3d_nms_kernel.cu:230-262).                               */
+int fd_boxes_iou_bev(const float* d_boxes_a, int na, const float* d_boxes_b, int nb, float* d_iou, void* stream);
+
 /* small helpers used by the host layer */
 int fd_fill_i32(int32_t* d_ptr, int64_t n, int32_t value, void* stream);
 

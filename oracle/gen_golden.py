@@ -7,6 +7,10 @@ that nothing on the GPU box needs the reference.  Usage:  python oracle/gen_gold
                      + reference VoxelFeatureExtractorV3 (det3d/models/readers/voxel_encoder.py:17-24)
   neck_head.pt       reference RPN (det3d/models/necks/rpn.py) + CenterHead forward & loss
                      (det3d/models/bbox_heads/center_head.py:375-539) at reduced widths, random BN statistics
+  predict.pt         reference `CenterHead.predict` (center_head.py:541-770: decode, masks, per-timestep merge) on
+                     object-like head tensors, for a 1-timestep head (replicated 7x) and a 7-timestep head; only the
+                     CUDA call inside rotate_nms_pcdet is replaced (oracle.predict_ref.rotate_nms_ref + float64 IoU)
+                     (`python oracle/gen_golden.py predict` regenerates only this file)
   neck_head_train.pt the same reference classes in TRAINING mode: loss dict, every parameter gradient after
                      `sum(loss["loss"]).backward()` (trainer.py:85,317-344), the input gradient and the updated
                      BatchNorm running statistics  (`python oracle/gen_golden.py train` regenerates only this file)
@@ -138,10 +142,37 @@ def gen_train(M):
     print("neck_head_train: total loss %.6f, %d parameter gradients" % (float(total), len(grads)))
 
 
+TEST_CFG = dict(post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], max_per_img=500,
+                nms=dict(use_rotate_nms=True, use_multi_class_nms=False, nms_pre_max_size=1000, nms_post_max_size=83,
+                         nms_iou_threshold=0.2),
+                score_threshold=0.1, pc_range=[-54, -54], out_size_factor=8, voxel_size=[0.075, 0.075])
+
+
+def gen_predict(M):
+    """Reference CenterHead.predict with the CUDA NMS call swapped for the oracle's (same box convention / ordering)."""
+    from det3d.core import box_torch_ops
+    from oracle import predict_ref as PR
+    box_torch_ops.rotate_nms_pcdet = lambda boxes, scores, thresh, pre_maxsize=None, post_max_size=None: \
+        PR.rotate_nms_ref(boxes, scores, thresh, pre_maxsize, post_max_size, PR.nms_np)
+    AttrDict = sys.modules["addict"].Dict
+    cases = {}
+    for name, T, H, W in (("t1", 1, 40, 40), ("t7", 7, 36, 44)):   # the reference merge (:693-713) only works for T in {1, 7}
+        head = M.build_head(dict(HEAD_CFG, timesteps=T))
+        preds = PR.synth_preds(2, H, W, T, seed=10 + T, n_obj=12)
+        ret = head.predict({}, [{k: v.clone() for k, v in preds.items()}], AttrDict(TEST_CFG))
+        cases[name] = dict(timesteps=T, preds=preds,
+                           ret=[{k: v for k, v in r.items() if k != "metadata"} for r in ret])
+        print("predict %s: %s boxes per sample" % (name, [len(r["scores"]) for r in ret]))
+    torch.save(dict(test_cfg=TEST_CFG, cases=cases), os.path.join(OUT, "predict.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "train" in sys.argv[1:]:
         gen_train(import_ref_models())
+        return
+    if "predict" in sys.argv[1:]:
+        gen_predict(import_ref_models())
         return
     pco = load_ref_voxelizer()
     M = import_ref_models()
@@ -179,6 +210,7 @@ def main():
     print("neck_head: neck_out", tuple(feat.shape), {k: tuple(v.shape) for k, v in preds[0].items()})
     print("loss keys", {k: (v[0] if isinstance(v, list) else v) for k, v in loss.items()})
     gen_train(M)
+    gen_predict(M)
 
 
 if __name__ == "__main__":

@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
 export PYTHONPATH=$GRAFT_REPO_ROOT
-nvidia-smi topo -m 2>&1 | head -8
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 2000 gpurun_out/bench_n2.err; cat gpurun_out/bench_n2.json
+timeout 900 python -m pytest tests/test_gpu_predict.py -q -x 2>&1 | tail -40 | cut -c1-1200
