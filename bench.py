@@ -260,26 +260,28 @@ def train_bench(args, rank, world, dev):
         sync.finish()
         opt.step()
 
-    for _ in range(2):
+    for _ in range(3):
         step()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     n0 = lib.launch_count()
     sync.bytes_reduced = 0
+    sampler = ClockSampler(dev.index) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.train_steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
     ms = barrier_max(e0.elapsed_time(e1), world, dev) / args.train_steps
     loss = float(sum(losses["loss"]))
     return dict(workload="forecast_n3 (7-timestep heads) car, fwd+bwd+AdamW, 1 x 305k-pt scene per GPU per step "
                          "(BASELINE configs[2]; configs[3] for n_gpus > 1)", ms_per_step=ms,
                 samples_per_s=B * world / (ms / 1e3), precision=args.train_precision, steps=args.train_steps,
                 gpu_launches_per_step=(lib.launch_count() - n0) // args.train_steps, loss=loss,
-                params=sum(p.numel() for p in m.parameters()),
+                params=sum(p.numel() for p in m.parameters()), clocks=clocks,
                 allreduce_bytes_per_step=sync.bytes_reduced // max(args.train_steps, 1),
                 exchange="bucketed all-reduce(sum)/world of the parameter gradients, %s" %
                          ("NCCL over NVLink, overlapped with backward" if world > 1 else "single rank: none"))
@@ -403,7 +405,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("FD_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="bf16x3 (default): tcgen05 tensor cores with a 3-term bf16 split, holds the 1e-3 parity contract; "
                          "fp32: CUDA-core exact arm; bf16: single pass, outside the parity contract")
-    ap.add_argument("--train-steps", type=int, default=3, help="timed forecast_n3 fwd+bwd steps reported under 'train' (0: skip)")
+    ap.add_argument("--train-steps", type=int, default=8, help="timed forecast_n3 fwd+bwd steps reported under 'train' (0: skip)")
     ap.add_argument("--train-precision", default="bf16x3", choices=["fp32", "bf16x3"],
                     help="forward / data-gradient convolutions of the training step (weight gradients are always fp32)")
     args = ap.parse_args()

@@ -27,102 +27,193 @@ nbr_transpose_kernel(const int* __restrict__ nbr, int nbr_stride, const int32_t*
 }
 
 // ---------------------------------------------------------------------------------------------- wgrad
-// dW[k][ci][co] += sum_o in[gather(o,k)][ci] * dy[o][co].  One CTA = one kernel offset x one 64x64 (ci,co) tile x one
-// chunk of output rows; 256 threads, 4x4 register block each; rows streamed through shared memory 32 at a time.
-constexpr int WG_T = 64;
+// dW[k][ci][co] += sum_o in[gather(o,k)][ci] * dy[o][co].  One CTA = one kernel offset x one TI x TO (ci,co) tile x one
+// chunk of output rows.  The 256 threads form G groups; every group owns the whole tile with an RI x RO register block
+// per thread (8 x 8 for tile sides >= 64, else 4 x 4) and takes every G-th row of a 32-row batch staged in shared
+// memory (128-bit gathers when the rows allow it), so narrow layers keep all threads busy.
 constexpr int WG_R = 32;
 constexpr int WG_THREADS = 256;
+constexpr int WG_Q = 512;          // pair ring: holds < WG_R leftovers + one batch of WG_THREADS rows
 
+// output-channel owned by register j of thread column tx: groups of 4 consecutive channels, interleaved across the 16
+// thread columns so that the 128-bit shared-memory reads of a warp are conflict free
+constexpr int wg_rows(int width) {      // rows per shared-memory batch: 32 (larger batches measured slower: occupancy)
+  int r = 32;
+  while (r * width > 8192) r >>= 1;
+  return r;
+}
+
+template <int RO, int TXN>
+__device__ __forceinline__ int wg_col(int tx, int j) {
+  return (j >> 2) * (TXN * 4) + tx * 4 + (j & 3);
+}
+
+template <int TI, int TO>
 __global__ void __launch_bounds__(WG_THREADS)
 conv_wgrad_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta, int tiles_ci, int tiles_co) {
-  __shared__ __align__(16) float As[WG_R][WG_T];
-  __shared__ __align__(16) float Bs[WG_R][WG_T];
-  __shared__ int s_idx[WG_R];
+  constexpr int RI = TI >= 64 ? 8 : 4, RO = TO >= 64 ? 8 : 4;
+  constexpr int TXN = TO / RO, TYN = TI / RI, GS = TXN * TYN, G = WG_THREADS / GS;
+  // rows per shared-memory batch: 32 KB of operands in flight per CTA whatever the tile width
+  constexpr int R = wg_rows(TI + TO);
+  static_assert(GS <= WG_THREADS && WG_THREADS % GS == 0 && R % G == 0 && R - 1 + WG_THREADS <= WG_Q, "bad wgrad tiling");
+  __shared__ __align__(16) float As[R][TI];
+  __shared__ __align__(16) float Bs[R][TO];
+  __shared__ int q_in[WG_Q], q_out[WG_Q];
+  __shared__ int s_wcnt[WG_THREADS / 32];
   const int tid = threadIdx.x;
   const int n = a.d_n ? min(*a.d_n, a.n_cap) : a.n_cap;
   int t = blockIdx.y;
   const int to = t % tiles_co; t /= tiles_co;
   const int ti = t % tiles_ci;
   const int k = t / tiles_ci;
-  const int ci0 = ti * WG_T, co0 = to * WG_T;
+  const int ci0 = ti * TI, co0 = to * TO;
   const long long rb = (long long)blockIdx.x * rows_per_cta;
   if (rb >= n) return;
   const int row_begin = (int)rb;
   const int row_end = (int)min((long long)n, rb + rows_per_cta);
-  const int tx = tid & 15, ty = tid >> 4;     // tx -> 4 output channels, ty -> 4 input channels
-  float acc[4][4];
+  const int grp = tid / GS, tx = (tid % GS) % TXN, ty = (tid % GS) / TXN;   // tx -> RO output, ty -> RI input channels
+  const bool vec_a = (a.cin % 4 == 0) && (a.in_stride % 4 == 0) && ((((uintptr_t)a.in) & 15) == 0);
+  const bool vec_b = a.out_map == FD_OUTMAP_IDENTITY && (a.cout % 4 == 0) && (a.out_stride % 4 == 0) &&
+                     ((((uintptr_t)a.out) & 15) == 0);
+  float acc[RI][RO];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < RO; ++j) acc[i][j] = 0.f;
 
-  for (int r0 = row_begin; r0 < row_end; r0 += WG_R) {
-    __syncthreads();
-    int any = 0;
-    if (tid < WG_R) {
-      const int o = r0 + tid;
+  // (input row, output row) pairs of this offset are compacted on the fly into a ring and consumed 32 at a time, so the
+  // GEMM only ever sees rows that have a neighbour (about 20 % of the rows per offset on the first sparse levels)
+  const int lane = tid & 31, warp = tid >> 5;
+  int q_head = 0, q_cnt = 0;                  // uniform across the CTA
+  for (int base = row_begin; base < row_end || q_cnt > 0; base += WG_THREADS) {
+    if (base < row_end) {
+      const int o = base + tid;
       const int src = o < row_end ? gather_row(a, o, k) : -1;
-      s_idx[tid] = src;
-      any = src >= 0;
-    }
-    if (!__syncthreads_or(any)) continue;
+      const unsigned ballot = __ballot_sync(0xffffffffu, src >= 0);
+      if (lane == 0) s_wcnt[warp] = __popc(ballot);
+      __syncthreads();
+      int woff = 0, total = 0;
 #pragma unroll
-    for (int it = 0; it < (WG_R * WG_T) / WG_THREADS; ++it) {
-      const int e = it * WG_THREADS + tid;
-      const int r = e / WG_T, c = e % WG_T;
-      const int src = s_idx[r];
-      float va = 0.f, vb = 0.f;
+      for (int w = 0; w < WG_THREADS / 32; ++w) {
+        const int c = s_wcnt[w];
+        if (w < warp) woff += c;
+        total += c;
+      }
       if (src >= 0) {
-        if (ci0 + c < a.cin) va = __ldg(a.in + (size_t)src * a.in_stride + ci0 + c);
-        if (co0 + c < a.cout) {
-          const OutRow orow = map_out_row(a, r0 + r);
-          vb = orow.base[orow.coff + (co0 + c) * orow.cstride];
+        const int pos = (q_head + q_cnt + woff + __popc(ballot & ((1u << lane) - 1u))) & (WG_Q - 1);
+        q_in[pos] = src;
+        q_out[pos] = o;
+      }
+      q_cnt += total;
+      __syncthreads();
+    }
+    const bool last = base + WG_THREADS >= row_end;
+    while (q_cnt >= R || (last && q_cnt > 0)) {
+      const int take = min(q_cnt, R);
+      // ---- A: gathered input rows
+      if (vec_a) {
+        for (int e = tid; e < R * TI / 4; e += WG_THREADS) {
+          const int r = e / (TI / 4), c = (e % (TI / 4)) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < take && ci0 + c < a.cin)
+            v = __ldg(reinterpret_cast<const float4*>(a.in + (size_t)q_in[(q_head + r) & (WG_Q - 1)] * a.in_stride + ci0 + c));
+          *reinterpret_cast<float4*>(&As[r][c]) = v;
+        }
+      } else {
+        for (int e = tid; e < R * TI; e += WG_THREADS) {
+          const int r = e / TI, c = e % TI;
+          As[r][c] = (r < take && ci0 + c < a.cin)
+                         ? __ldg(a.in + (size_t)q_in[(q_head + r) & (WG_Q - 1)] * a.in_stride + ci0 + c) : 0.f;
         }
       }
-      As[r][c] = va;
-      Bs[r][c] = vb;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < WG_R; ++r) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[r][tx * 4]);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+      // ---- B: dL/dy rows of the same pairs
+      if (vec_b) {
+        for (int e = tid; e < R * TO / 4; e += WG_THREADS) {
+          const int r = e / (TO / 4), c = (e % (TO / 4)) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < take && co0 + c < a.cout)
+            v = *reinterpret_cast<const float4*>(a.out + (size_t)q_out[(q_head + r) & (WG_Q - 1)] * a.out_stride + co0 + c);
+          *reinterpret_cast<float4*>(&Bs[r][c]) = v;
+        }
+      } else {
+        for (int e = tid; e < R * TO; e += WG_THREADS) {
+          const int r = e / TO, c = e % TO;
+          float v = 0.f;
+          if (r < take && co0 + c < a.cout) {
+            const OutRow orow = map_out_row(a, q_out[(q_head + r) & (WG_Q - 1)]);
+            v = orow.base[orow.coff + (co0 + c) * orow.cstride];
+          }
+          Bs[r][c] = v;
+        }
+      }
+      __syncthreads();
+#pragma unroll 2
+      for (int r = grp; r < R; r += G) {
+        float av[RI], bv[RO];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < RI; ++i) av[i] = As[r][ty * RI + i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < RO; ++j) bv[j] = Bs[r][wg_col<RO, TXN>(tx, j)];
+#pragma unroll
+        for (int i = 0; i < RI; ++i)
+#pragma unroll
+          for (int j = 0; j < RO; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+      q_head = (q_head + take) & (WG_Q - 1);
+      q_cnt -= take;
     }
   }
   float* dwk = dw + (size_t)k * a.cin * a.cout;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ci = ci0 + ty * 4 + i;
+  for (int i = 0; i < RI; ++i) {
+    const int ci = ci0 + ty * RI + i;
     if (ci >= a.cin) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + tx * 4 + j;
+    for (int j = 0; j < RO; ++j) {
+      const int co = co0 + wg_col<RO, TXN>(tx, j);
       if (co < a.cout && acc[i][j] != 0.f) atomicAdd(dwk + (size_t)ci * a.cout + co, acc[i][j]);
     }
   }
 }
 
-static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream) {
-  if (a.n_cap <= 0) return 0;
-  const int tiles_ci = ceil_div(a.cin, WG_T), tiles_co = ceil_div(a.cout, WG_T);
+static int wg_tile(int c) { return c >= 96 ? 128 : c >= 48 ? 64 : c >= 24 ? 32 : 16; }
+
+template <int TI, int TO>
+static int launch_wgrad_t(const ConvArgs& a, float* dw, cudaStream_t stream) {
+  const int tiles_ci = ceil_div(a.cin, TI), tiles_co = ceil_div(a.cout, TO);
   const int tiles = a.K * tiles_ci * tiles_co;
   FD_REQUIRE(tiles <= 65535, "fd_conv_wgrad: K*tiles = %d exceeds the grid limit", tiles);
-  int chunks = ceil_div((int64_t)kNumSMs * 16, tiles);
+  int chunks = ceil_div((int64_t)kNumSMs * 8, tiles);
   const int max_chunks = ceil_div(a.n_cap, 8 * WG_R);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   int rows_per_cta = ceil_div(a.n_cap, chunks);
   rows_per_cta = ceil_div(rows_per_cta, WG_R) * WG_R;
   chunks = ceil_div(a.n_cap, rows_per_cta);
-  conv_wgrad_kernel<<<dim3(chunks, tiles), WG_THREADS, 0, stream>>>(a, dw, rows_per_cta, tiles_ci, tiles_co);
+  conv_wgrad_kernel<TI, TO><<<dim3(chunks, tiles), WG_THREADS, 0, stream>>>(a, dw, rows_per_cta, tiles_ci, tiles_co);
   FD_LAUNCHED();
   return 0;
+}
+
+template <int TI>
+static int launch_wgrad_i(const ConvArgs& a, float* dw, cudaStream_t stream) {
+  switch (wg_tile(a.cout)) {
+    case 128: return launch_wgrad_t<TI, 128>(a, dw, stream);
+    case 64: return launch_wgrad_t<TI, 64>(a, dw, stream);
+    case 32: return launch_wgrad_t<TI, 32>(a, dw, stream);
+    default: return launch_wgrad_t<TI, 16>(a, dw, stream);
+  }
+}
+
+static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream) {
+  if (a.n_cap <= 0) return 0;
+  switch (wg_tile(a.cin)) {
+    case 128: return launch_wgrad_i<128>(a, dw, stream);
+    case 64: return launch_wgrad_i<64>(a, dw, stream);
+    case 32: return launch_wgrad_i<32>(a, dw, stream);
+    default: return launch_wgrad_i<16>(a, dw, stream);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- reductions
@@ -196,16 +287,23 @@ struct FinArgs {
   float* out;                                                    // RED_COLSUM output
 };
 
+// One warp per channel: lane l sums partials l, l+32, ... in order, then a fixed-order butterfly -> deterministic.
 __global__ void __launch_bounds__(RED_THREADS)
 red_finalize_kernel(const FinArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= a.C) return;
   const long long n = a.d_n ? min((long long)*a.d_n, a.n_cap) : a.n_cap;
   double s1 = 0.0, s2 = 0.0;
-  for (int g = 0; g < a.G; ++g) {
+  for (int g = lane; g < a.G; g += 32) {
     s1 += a.partial[((size_t)g * 2 + 0) * a.C + c];
     s2 += a.partial[((size_t)g * 2 + 1) * a.C + c];
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane != 0) return;
   const double dn = n > 0 ? (double)n : 1.0;
   if (a.mode == RED_STATS) {
     const double mu = s1 / dn;
@@ -496,7 +594,7 @@ int fd_bn_train_stats(const float* d_x, int x_stride, int C, const int32_t* d_n,
   f.eps = eps; f.momentum = momentum; f.gamma = d_gamma; f.beta = d_beta;
   f.running_mean = d_running_mean; f.running_var = d_running_var;
   f.mean = d_mean; f.invstd = d_invstd; f.scale = d_scale; f.shift = d_shift;
-  red_finalize_kernel<<<ceil_div(C, RED_THREADS), RED_THREADS, 0, stream>>>(f);
+  red_finalize_kernel<<<ceil_div((int64_t)C * 32, RED_THREADS), RED_THREADS, 0, stream>>>(f);
   FD_LAUNCHED();
   return 0;
 }
@@ -537,7 +635,7 @@ int fd_bn_backward(const float* d_dy, int dy_stride, const float* d_y, int y_str
   FinArgs f{};
   f.mode = RED_BN_BWD; f.C = C; f.G = G; f.partial = r.partial; f.d_n = d_n; f.n_cap = n_cap;
   f.dgamma = d_dgamma; f.dbeta = d_dbeta; f.c1 = c1; f.c2 = c2;
-  red_finalize_kernel<<<ceil_div(C, RED_THREADS), RED_THREADS, 0, stream>>>(f);
+  red_finalize_kernel<<<ceil_div((int64_t)C * 32, RED_THREADS), RED_THREADS, 0, stream>>>(f);
   FD_LAUNCHED();
   bn_bwd_apply_kernel<<<persistent_grid(ceil_div(n_cap * C, 256), 8), 256, 0, stream>>>(
       d_dy, dy_stride, d_y, y_stride, relu, d_x, x_stride, C, d_mean, d_invstd, d_gamma, c1, c2, d_dx, dx_stride,
@@ -559,7 +657,7 @@ int fd_col_sum(const float* d_x, int x_stride, int C, const int32_t* d_n, int64_
   FD_LAUNCHED();
   FinArgs f{};
   f.mode = RED_COLSUM; f.C = C; f.G = G; f.partial = r.partial; f.d_n = d_n; f.n_cap = n_cap; f.out = d_out;
-  red_finalize_kernel<<<ceil_div(C, RED_THREADS), RED_THREADS, 0, stream>>>(f);
+  red_finalize_kernel<<<ceil_div((int64_t)C * 32, RED_THREADS), RED_THREADS, 0, stream>>>(f);
   FD_LAUNCHED();
   return 0;
 }
