@@ -83,6 +83,16 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_fill_i32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    # ---- multi-sweep assembly
+    "fd_sweeps_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "fd_assemble_sweeps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    # ---- target assignment
+    "fd_assign_center_targets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                            C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     # ---- predict
     "fd_center_predict_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "fd_center_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, C.c_int, C.c_int,

@@ -317,6 +317,39 @@ int fd_center_predict(const float* d_out, int row_stride, int c_reg, int c_heigh
  * (det3d/ops/iou3d_nms/src/iou3d_nms.cpp:61-88, iou3d_nms_kernel.cu:230-262).                               */
 int fd_boxes_iou_bev(const float* d_boxes_a, int na, const float* d_boxes_b, int nb, float* d_iou, void* stream);
 
+/* ---- multi-sweep assembly (the step in front of the voxelizer) ------------------------------------------
+ * Replaces det3d/datasets/pipelines/loading.py:24-60 (read_file column selection, remove_close, read_sweep) and
+ * :120-140 (key frame + sweeps concatenation, `combined = hstack([points, times])`).
+ *   d_raw            [total_records, raw_stride] fp32: the untouched .bin payloads of every sweep of every scene,
+ *                    concatenated in output order (nuScenes: raw_stride 5 = x,y,z,intensity,ring; num_feat 4)
+ *   d_sweep_offsets  [S+1] int32 record offsets;  d_sweep_scene [S] int32 scene of every sweep (non-decreasing)
+ *   d_transforms     [S,16] float64 row-major 4x4 sweep-to-keyframe transforms, applied when d_flags[s] & 1
+ *                    (float64 product stored as float32, as numpy does);  d_flags[s] & 2: remove_close with
+ *                    |x| < close_radius and |y| < close_radius;  d_time_lag [S] -> last output column
+ * outputs: d_points [total_records, num_feat+1] (kept rows first, reference order; rows >= count are NaN so that
+ *          fd_voxelize_vfe rejects them), d_batch_offsets [B+1] int32 rows of every scene, d_count [1].            */
+size_t fd_sweeps_workspace_bytes(int64_t total_records);
+int fd_assemble_sweeps(const float* d_raw, int64_t total_records, int raw_stride, int num_feat,
+                       const int32_t* d_sweep_offsets, const double* d_transforms, const int32_t* d_flags,
+                       const float* d_time_lag, const int32_t* d_sweep_scene, int S, int B, float close_radius,
+                       float* d_points, int32_t* d_batch_offsets, int32_t* d_count, void* d_workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- CenterPoint target assignment (the step that feeds CenterHead.loss) -----------------------------------
+ * Replaces det3d/datasets/pipelines/preprocess.py:464-546 (AssignLabel, one task, one timestep) with
+ * det3d/core/utils/center_utils.py:17-64 (gaussian_radius, gaussian2D, draw_umich_gaussian).
+ *   d_boxes   [B, n_max, box_dim = 12] fp32 (x,y,z,w,l,h,vx,vy,rvx,rvy,rot,rrot: the last two columns are
+ *             wrapped to [-pi, pi) as preprocess.py:449-456 does), d_classes [B, n_max] 1-based class within the task
+ *             (<= 0: skip), d_num [B] objects per sample (at most max_objs are used, object k -> slot k)
+ *   outputs (zero-filled by the call): d_hm [B,num_cls,H,W], d_anno_box [B,max_objs,14] (dx,dy,z,log w,log l,log h,
+ *             vx,vy,rvx,rvy,sin rot,cos rot,sin rrot,cos rrot), d_ind / d_cat [B,max_objs] int64, d_mask uint8.
+ *   radius_mult / timestep: mult = clamp(|v| * (1 + timestep) / 2, 1, 4) on the Gaussian radius (:487-491).       */
+int fd_assign_center_targets(const float* d_boxes, const int32_t* d_classes, const int32_t* d_num, int B, int n_max,
+                             int box_dim, int num_cls, int W, int H, float pc_x0, float pc_y0, float voxel_x,
+                             float voxel_y, float out_size_factor, float gaussian_overlap, int min_radius,
+                             int radius_mult, int timestep, int max_objs, float* d_hm, float* d_anno_box,
+                             int64_t* d_ind, uint8_t* d_mask, int64_t* d_cat, void* stream);
+
 /* small helpers used by the host layer */
 int fd_fill_i32(int32_t* d_ptr, int64_t n, int32_t value, void* stream);
 

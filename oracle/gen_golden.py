@@ -11,6 +11,10 @@ that nothing on the GPU box needs the reference.  Usage:  python oracle/gen_gold
                      object-like head tensors, for a 1-timestep head (replicated 7x) and a 7-timestep head; only the
                      CUDA call inside rotate_nms_pcdet is replaced (oracle.predict_ref.rotate_nms_ref + float64 IoU)
                      (`python oracle/gen_golden.py predict` regenerates only this file)
+  loader.npz         reference `LoadPointCloudFromFile.__call__` (det3d/datasets/pipelines/loading.py:102-147) on synthetic
+                     nuScenes-format .bin sweeps written to a temp dir (`python oracle/gen_golden.py loader`)
+  assign.npz         reference `AssignLabel.__call__` (det3d/datasets/pipelines/preprocess.py:336-909, standard sampler)
+                     on synthetic car annotations, 3 timesteps (`python oracle/gen_golden.py assign`)
   neck_head_train.pt the same reference classes in TRAINING mode: loss dict, every parameter gradient after
                      `sum(loss["loss"]).backward()` (trainer.py:85,317-344), the input gradient and the updated
                      BatchNorm running statistics  (`python oracle/gen_golden.py train` regenerates only this file)
@@ -166,8 +170,117 @@ def gen_predict(M):
     torch.save(dict(test_cfg=TEST_CFG, cases=cases), os.path.join(OUT, "predict.pt"))
 
 
+def gen_loader():
+    """Run the reference loader on synthetic .bin files.  det3d.datasets pulls the nuscenes devkit at import time, so
+    loading.py is executed inside stub packages (only its own code runs: read_file / remove_close / read_sweep /
+    LoadPointCloudFromFile)."""
+    import tempfile
+    from oracle import loader_ref as LR
+    import_ref_models()
+    for name in ("det3d.datasets", "det3d.datasets.pipelines"):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [REF + "/" + name.replace(".", "/")]
+        sys.modules[name] = pkg
+    reg = types.ModuleType("det3d.datasets.registry")
+
+    class _Reg:
+        def register_module(self, cls):
+            return cls
+    reg.PIPELINES = _Reg()
+    sys.modules["det3d.datasets.registry"] = reg
+    spec = importlib.util.spec_from_file_location("det3d.datasets.pipelines.loading",
+                                                  REF + "/det3d/datasets/pipelines/loading.py")
+    LD = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = LD
+    spec.loader.exec_module(LD)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for case, seed in (("a", 0), ("b", 1)):
+            key, sweeps = LR.synth_sweeps(seed)
+            kp = os.path.join(tmp, "key_%s.bin" % case)
+            key.tofile(kp)
+            infos = []
+            for i, (rec, T, lag) in enumerate(sweeps):
+                sp = os.path.join(tmp, "sweep_%s_%d.bin" % (case, i))
+                rec.tofile(sp)
+                infos.append(dict(lidar_path=sp, transform_matrix=T, time_lag=lag))
+            res = dict(lidar=dict(nsweeps=len(sweeps) + 1), painted=False)
+            LD.LoadPointCloudFromFile(dataset="NuScenesDataset")(res, dict(lidar_path=kp, sweeps=infos))
+            # the reference visits the sweeps in rng.choice order (loading.py:121-122): record it so the oracle and
+            # the native path can be fed the same order
+            order = np.random.default_rng(0).choice(len(infos), len(infos), replace=False)
+            out["combined_" + case] = res["lidar"]["combined"]
+            out["order_" + case] = order
+            out["seed_" + case] = np.int64(seed)
+            print("loader %s: %d points" % (case, len(res["lidar"]["combined"])))
+    np.savez_compressed(os.path.join(OUT, "loader.npz"), **out)
+
+
+def _stub_dataset_packages():
+    import_ref_models()
+    for name in ("det3d.datasets", "det3d.datasets.pipelines"):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [REF + "/" + name.replace(".", "/")]
+        sys.modules[name] = pkg
+    reg = types.ModuleType("det3d.datasets.registry")
+
+    class _Reg:
+        def register_module(self, cls):
+            return cls
+    reg.PIPELINES = _Reg()
+    sys.modules["det3d.datasets.registry"] = reg
+    b = types.ModuleType("det3d.builder")           # det3d.builder drags det3d.solver (py3.12-incompatible import)
+    b.build_dbsampler = None
+    sys.modules["det3d.builder"] = b
+
+
+ASSIGN_CFG = dict(out_size_factor=8, gaussian_overlap=0.1, max_objs=500, min_radius=2, radius_mult=False,
+                  sampler_type="standard")
+
+
+def gen_assign():
+    """Run the reference AssignLabel on synthetic annotations (2 samples x 3 timesteps, one car task)."""
+    from oracle import assign_ref as AR
+    _stub_dataset_packages()
+    spec = importlib.util.spec_from_file_location("det3d.datasets.pipelines.preprocess",
+                                                  REF + "/det3d/datasets/pipelines/preprocess.py")
+    PP = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = PP
+    spec.loader.exec_module(PP)
+    AttrDict = sys.modules["addict"].Dict
+    out = {}
+    for radius_mult in (False, True):
+        cfg = AttrDict(dict(ASSIGN_CFG, radius_mult=radius_mult))
+        cfg.target_assigner = AttrDict(tasks=None)
+        cfg.target_assigner.tasks = [AttrDict(num_class=1, class_names=["car"])]
+        al = PP.AssignLabel(cfg=cfg)
+        for sample, seed in enumerate((0, 1)):
+            boxes = AR.synth_annotations(seed)
+            n = len(boxes[0])
+            res = dict(mode="train", type="NuScenesDataset", lidar=dict(
+                voxels=dict(shape=np.array([1440, 1440, 40]), range=np.array(NUSC_RANGE, np.float32),
+                            size=np.array(NUSC_VOXEL, np.float32)),
+                annotations=dict(gt_boxes=[b.copy() for b in boxes], gt_names=[np.array(["car"] * n)] * 3,
+                                 gt_classes=[np.ones(n, np.int32) for _ in range(3)],
+                                 gt_trajectory=[np.array(["static"] * n)] * 3)))
+            res, _ = al(res, {})
+            tg = res["lidar"]["targets"]
+            tag = "%d_%d" % (int(radius_mult), sample)
+            for key in ("hm", "anno_box", "ind", "mask", "cat"):
+                out[key + "_" + tag] = np.stack([tg[key][t][0] for t in range(3)])
+            print("assign rm=%d sample %d: %d objects placed at t0" % (radius_mult, sample, int(tg["mask"][0][0].sum())))
+    # heat maps are sparse: store them compressed
+    np.savez_compressed(os.path.join(OUT, "assign.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "assign" in sys.argv[1:]:
+        gen_assign()
+        return
+    if "loader" in sys.argv[1:]:
+        gen_loader()
+        return
     if "train" in sys.argv[1:]:
         gen_train(import_ref_models())
         return
@@ -211,6 +324,8 @@ def main():
     print("loss keys", {k: (v[0] if isinstance(v, list) else v) for k, v in loss.items()})
     gen_train(M)
     gen_predict(M)
+    gen_loader()
+    gen_assign()
 
 
 if __name__ == "__main__":
