@@ -9,10 +9,12 @@
 //                                                              cudaMalloc/cudaFree per call).
 // Design: in the standard mode every forecast timestep shares hm / reg / height / dim / rot (only `vel` differs,
 // center_head.py:561-570) and the NMS boxes carry no velocity, so candidate selection and NMS run ONCE per sample and
-// the kept boxes are emitted once per timestep.  Kernel 1 decodes every BEV cell into a sortable 64-bit key
-// (score bits | inverted cell index; 0 = rejected).  Kernel 2 is one 1024-thread CTA per sample: exact radix select of
-// the `pre_max` largest keys, bitonic sort in shared memory, box decode, the full upper-triangular IoU bit matrix in
-// shared memory (128 KB for 1024 candidates), and the greedy sweep by one warp -- no host round trip, no allocation.
+// the kept boxes are emitted once per timestep.  Four launches per batch: (1) every BEV cell -> a sortable 64-bit key
+// (score bits | inverted cell index; 0 = rejected); (2) one 1024-thread CTA per sample: exact radix select of the
+// `pre_max` largest keys, bitonic sort in shared memory, decode of the NMS boxes; (3) the upper-triangular IoU bit
+// matrix in 64 x 64 tiles over the whole GPU, far-apart pairs decided by a circumscribed-circle test; (4) one warp per
+// sample sweeps greedily in score order with the suppressed set in registers, then the CTA emits -- no host round trip,
+// no allocation.
 // The polygon-clipping arithmetic follows the reference kernel operation by operation (fp32, same evaluation order),
 // so the keep / suppress decisions agree with it.
 #include "common.cuh"
@@ -32,6 +34,8 @@ struct PredictArgs {
   float osf, vx, vy, x0, y0;                    // out_size_factor, voxel size, pc_range origin
   float iou_thr; int pre_max, post_max;
   unsigned long long* keys;                     // [B, H*W]
+  float* cand_box; unsigned long long* cand_key; int* cand_n;   // [B,1024,8] NMS boxes (+half diagonal), [B,1024], [B]
+  unsigned long long* mask;                     // [B, 1024, 16] IoU bit matrix (upper triangle)
   float* boxes; float* scores; int* labels; int* cells; int* count;   // [B,T,post_max,9] [B,T,post_max] x2, [B,post_max], [B]
 };
 
@@ -167,26 +171,20 @@ iou_bev_pairs_kernel(const float* __restrict__ a, int na, const float* __restric
   }
 }
 
-// ---- one CTA per sample: select, sort, NMS, emit ----------------------------------------------------------------
-struct PredSmem {
-  unsigned long long mask[PRED_MAX_PRE][PRED_WORDS];   // 128 KB: bit j of row i = IoU(i, j) > thr, j > i
+// ---- stage A: one CTA per sample -- exact top-k selection, sort, decode of the NMS boxes ---------------------------
+struct SelSmem {
   unsigned long long key[PRED_MAX_PRE];
-  float box[PRED_MAX_PRE][7];                          // pcdet convention (x, y, z, dy, dx, dz, -rot - pi/2)
   int hist[256];
-  int keep[PRED_MAX_PRE];
-  unsigned long long prefix; int remaining; int n_valid; int n_sel; int n_keep;
+  unsigned long long prefix; int remaining; int n_valid; int n_sel;
 };
 
 __global__ void __launch_bounds__(PRED_THREADS)
-predict_nms_kernel(const PredictArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  PredSmem& s = *reinterpret_cast<PredSmem*>(smem_raw);
+predict_select_kernel(const PredictArgs a) {
+  __shared__ SelSmem s;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int HW = a.H * a.W;
   const unsigned long long* keys = a.keys + (size_t)b * HW;
-
-  // ---- number of surviving cells
-  if (tid == 0) { s.n_valid = 0; s.n_sel = 0; s.n_keep = 0; s.prefix = 0ULL; }
+  if (tid == 0) { s.n_valid = 0; s.n_sel = 0; s.prefix = 0ULL; }
   __syncthreads();
   int local = 0;
   for (int i = tid; i < HW; i += PRED_THREADS) local += keys[i] != 0ULL;
@@ -194,11 +192,9 @@ predict_nms_kernel(const PredictArgs a) {
   if ((tid & 31) == 0 && local) atomicAdd(&s.n_valid, local);
   __syncthreads();
   const int k = min(min(a.pre_max, PRED_MAX_PRE), s.n_valid);
-  if (k == 0) {
-    if (tid == 0) a.count[b] = 0;
-    return;
-  }
-  // ---- exact k-th largest key: 8 passes of an 8-bit radix select (keys are unique)
+  if (tid == 0) a.cand_n[b] = k;
+  if (k == 0) return;
+  // exact k-th largest key: 8 passes of an 8-bit radix select (keys are unique)
   if (tid == 0) s.remaining = k;
   for (int pass = 7; pass >= 0; --pass) {
     if (tid < 256) s.hist[tid] = 0;
@@ -219,7 +215,7 @@ predict_nms_kernel(const PredictArgs a) {
     __syncthreads();
   }
   const unsigned long long kth = s.prefix;
-  // ---- gather the k winners, pad to a power of two, bitonic sort (descending)
+  // gather the k winners, pad to a power of two, bitonic sort (descending)
   for (int i = tid; i < PRED_MAX_PRE; i += PRED_THREADS) s.key[i] = 0ULL;
   __syncthreads();
   for (int i = tid; i < HW; i += PRED_THREADS) {
@@ -237,49 +233,90 @@ predict_nms_kernel(const PredictArgs a) {
       }
       __syncthreads();
     }
-  // ---- boxes of the sorted candidates in the NMS convention (box_torch_ops.py:256-257)
+  // boxes of the sorted candidates in the NMS convention (box_torch_ops.py:256-257)
   const float* out_b = a.out + (size_t)b * HW * a.row_stride;
   for (int i = tid; i < k; i += PRED_THREADS) {
-    const int cell = (int)(0xffffffffu - (unsigned)(s.key[i] & 0xffffffffULL));
+    const unsigned long long key = s.key[i];
+    const int cell = (int)(0xffffffffu - (unsigned)(key & 0xffffffffULL));
     float b7[7];
     decode_cell(a, out_b + (size_t)cell * a.row_stride, cell, b7);
-    s.box[i][0] = b7[0]; s.box[i][1] = b7[1]; s.box[i][2] = b7[2];
-    s.box[i][3] = b7[4]; s.box[i][4] = b7[3]; s.box[i][5] = b7[5];
-    s.box[i][6] = __fsub_rn(-b7[6], 1.5707963267948966f);
+    float* cb = a.cand_box + ((size_t)b * PRED_MAX_PRE + i) * 8;
+    cb[0] = b7[0]; cb[1] = b7[1]; cb[2] = b7[2];
+    cb[3] = b7[4]; cb[4] = b7[3]; cb[5] = b7[5];
+    cb[6] = __fsub_rn(-b7[6], 1.5707963267948966f);
+    cb[7] = 0.5f * sqrtf(b7[3] * b7[3] + b7[4] * b7[4]);          // half diagonal: cheap far-apart test in stage B
+    a.cand_key[(size_t)b * PRED_MAX_PRE + i] = key;
+  }
+}
+
+// ---- stage B: the IoU bit matrix, one 64 x 64 tile per CTA (same tiling as iou3d_nms_kernel.cu:264-311) -------------
+// Pairs whose circumscribed circles (plus the kernel's 1e-2 containment margin) do not touch have an empty
+// intersection in the reference arithmetic too (no edge crossing, no contained corner -> area 0), so they are decided
+// without running the polygon clip.
+__global__ void __launch_bounds__(64)
+predict_mask_kernel(const PredictArgs a) {
+  __shared__ float cbox[64][8];
+  const int b = blockIdx.z, rb = blockIdx.y, cw = blockIdx.x, tid = threadIdx.x;
+  const int k = a.cand_n[b];
+  if (rb * 64 >= k || cw * 64 >= k || cw < rb) return;            // outside / strictly lower triangle
+  const float* boxes = a.cand_box + (size_t)b * PRED_MAX_PRE * 8;
+  const int j0 = cw * 64;
+  if (j0 + tid < k) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cbox[tid][c] = boxes[(size_t)(j0 + tid) * 8 + c];
   }
   __syncthreads();
-  // ---- upper-triangular IoU bit matrix (iou3d_nms_kernel.cu:264-311 computes the same bits tile by tile)
+  const int i = rb * 64 + tid;
+  if (i >= k) return;
+  float mine[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) mine[c] = boxes[(size_t)i * 8 + c];
+  unsigned long long bits = 0ULL;
+  const int jbeg = max(j0, i + 1), jend = min(j0 + 64, k);
+  for (int j = jbeg; j < jend; ++j) {
+    const float* o = cbox[j - j0];
+    const float dx = mine[0] - o[0], dy = mine[1] - o[1], reach = mine[7] + o[7] + 0.05f;
+    if (dx * dx + dy * dy > reach * reach) continue;
+    if (iou_bev_ref(mine, o) > a.iou_thr) bits |= 1ULL << (j & 63);
+  }
+  a.mask[((size_t)b * PRED_MAX_PRE + i) * PRED_WORDS + cw] = bits;
+}
+
+// ---- stage C: greedy sweep in score order (iou3d_nms.cpp:116-131) by one warp, then emit -------------------------------
+__global__ void __launch_bounds__(256)
+predict_sweep_emit_kernel(const PredictArgs a) {
+  __shared__ int keep[PRED_MAX_PRE];
+  __shared__ int n_keep;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int HW = a.H * a.W;
+  const int k = a.cand_n[b];
+  if (k == 0) {
+    if (tid == 0) a.count[b] = 0;
+    return;
+  }
   const int words = (k + 63) / 64;
-  for (int item = tid; item < k * words; item += PRED_THREADS) {
-    const int i = item / words, w = item - i * words;
-    unsigned long long bits = 0ULL;
-    const int j0 = max(w * 64, i + 1), j1 = min(w * 64 + 64, k);
-    for (int j = j0; j < j1; ++j)
-      if (iou_bev_ref(s.box[i], s.box[j]) > a.iou_thr) bits |= 1ULL << (j & 63);
-    s.mask[i][w] = bits;
-  }
-  __syncthreads();
-  // ---- greedy sweep in score order (iou3d_nms.cpp:116-131), one warp, suppressed set in registers
+  const unsigned long long* mask = a.mask + (size_t)b * PRED_MAX_PRE * PRED_WORDS;
   if (tid < 32) {
-    unsigned long long remv = 0ULL;      // lane w holds word w
+    unsigned long long remv = 0ULL;      // lane w holds word w of the suppressed set
     int nk = 0;
     for (int i = 0; i < k && nk < a.post_max; ++i) {
       const unsigned long long word = __shfl_sync(0xffffffffu, remv, i >> 6);
       if (!((word >> (i & 63)) & 1ULL)) {
-        if (tid == 0) s.keep[nk] = i;
+        if (tid == 0) keep[nk] = i;
         ++nk;
-        if (tid < words) remv |= s.mask[i][tid];
+        // words left of the diagonal tile were never written (lower triangle): only read w >= i / 64
+        if (tid < words && tid >= (i >> 6)) remv |= mask[(size_t)i * PRED_WORDS + tid];
       }
     }
-    if (tid == 0) { s.n_keep = nk; a.count[b] = nk; }
+    if (tid == 0) { n_keep = nk; a.count[b] = nk; }
   }
   __syncthreads();
-  // ---- emit: box3d_lidar (x, y, z, w, l, h, vx, vy, rot), score, label for every forecast timestep
-  const int nk = s.n_keep;
-  for (int e = tid; e < nk * a.T; e += PRED_THREADS) {
+  // emit: box3d_lidar (x, y, z, w, l, h, vx, vy, rot), score, label for every forecast timestep
+  const int nk = n_keep;
+  const float* out_b = a.out + (size_t)b * HW * a.row_stride;
+  for (int e = tid; e < nk * a.T; e += blockDim.x) {
     const int t = e / nk, q = e - t * nk;
-    const int i = s.keep[q];
-    const unsigned long long key = s.key[i];
+    const unsigned long long key = a.cand_key[(size_t)b * PRED_MAX_PRE + keep[q]];
     const int cell = (int)(0xffffffffu - (unsigned)(key & 0xffffffffULL));
     const float* row = out_b + (size_t)cell * a.row_stride;
     float b7[7];
@@ -301,9 +338,14 @@ predict_nms_kernel(const PredictArgs a) {
 
 extern "C" {
 
+static size_t pred_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
 size_t fd_center_predict_workspace_bytes(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1) return 0;
-  return sizeof(unsigned long long) * (size_t)B * H * W;
+  return pred_align(sizeof(unsigned long long) * (size_t)B * H * W) +
+         pred_align(sizeof(float) * (size_t)B * fd::PRED_MAX_PRE * 8) +
+         pred_align(sizeof(unsigned long long) * (size_t)B * fd::PRED_MAX_PRE) + pred_align(sizeof(int) * (size_t)B) +
+         pred_align(sizeof(unsigned long long) * (size_t)B * fd::PRED_MAX_PRE * fd::PRED_WORDS);
 }
 
 int fd_center_predict(const float* d_out, int row_stride, int c_reg, int c_height, int c_dim, int c_rot,
@@ -316,11 +358,12 @@ int fd_center_predict(const float* d_out, int row_stride, int c_reg, int c_heigh
   cudaStream_t stream = (cudaStream_t)stream_;
   FD_REQUIRE(d_out && c_vel && post_center_range6 && d_boxes && d_scores && d_labels && d_cells && d_count && d_workspace,
              "fd_center_predict: null argument");
-  FD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && T >= 1 && T <= 16 && num_cls >= 1 && row_stride >= 1,
+  FD_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && W >= 1 && T >= 1 && T <= 16 && num_cls >= 1 && row_stride >= 1,
              "fd_center_predict: bad shape (T must be <= 16)");
   FD_REQUIRE(pre_max >= 1 && pre_max <= PRED_MAX_PRE && post_max >= 1 && post_max <= pre_max,
              "fd_center_predict: need 1 <= post_max <= pre_max <= %d", PRED_MAX_PRE);
   FD_REQUIRE((long long)H * W < 0x7fffffffLL, "fd_center_predict: grid too large");
+  FD_REQUIRE(nms_iou_threshold >= 0.f, "fd_center_predict: negative IoU threshold");
   PredictArgs a{};
   a.out = d_out; a.row_stride = row_stride;
   a.c_reg = c_reg; a.c_height = c_height; a.c_dim = c_dim; a.c_rot = c_rot; a.c_hm = c_hm; a.num_cls = num_cls;
@@ -330,16 +373,21 @@ int fd_center_predict(const float* d_out, int row_stride, int c_reg, int c_heigh
   for (int j = 0; j < 6; ++j) a.range[j] = post_center_range6[j];
   a.osf = out_size_factor; a.vx = voxel_x; a.vy = voxel_y; a.x0 = pc_x0; a.y0 = pc_y0;
   a.iou_thr = nms_iou_threshold; a.pre_max = pre_max; a.post_max = post_max;
-  a.keys = (unsigned long long*)d_workspace;
+  char* ws = (char*)d_workspace;
+  a.keys = (unsigned long long*)ws;      ws += pred_align(sizeof(unsigned long long) * (size_t)B * H * W);
+  a.cand_box = (float*)ws;               ws += pred_align(sizeof(float) * (size_t)B * PRED_MAX_PRE * 8);
+  a.cand_key = (unsigned long long*)ws;  ws += pred_align(sizeof(unsigned long long) * (size_t)B * PRED_MAX_PRE);
+  a.cand_n = (int*)ws;                   ws += pred_align(sizeof(int) * (size_t)B);
+  a.mask = (unsigned long long*)ws;
   a.boxes = d_boxes; a.scores = d_scores; a.labels = d_labels; a.cells = d_cells; a.count = d_count;
   predict_keys_kernel<<<persistent_grid(ceil_div((int64_t)B * H * W, 256), 8), 256, 0, stream>>>(a);
   FD_LAUNCHED();
-  static bool configured = false;
-  if (!configured) {
-    FD_CUDA(cudaFuncSetAttribute(predict_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PredSmem)));
-    configured = true;
-  }
-  predict_nms_kernel<<<B, PRED_THREADS, sizeof(PredSmem), stream>>>(a);
+  predict_select_kernel<<<B, PRED_THREADS, 0, stream>>>(a);
+  FD_LAUNCHED();
+  const int tiles = ceil_div(pre_max, 64);
+  predict_mask_kernel<<<dim3(tiles, tiles, B), 64, 0, stream>>>(a);
+  FD_LAUNCHED();
+  predict_sweep_emit_kernel<<<B, 256, 0, stream>>>(a);
   FD_LAUNCHED();
   return 0;
 }
