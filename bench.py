@@ -31,6 +31,10 @@ METRIC = "scenes/sec fwd (300k-pt, 10-sweep synth)"
 N_TARGET = 360_000           # synth_scene(360000) -> 305,677 points, the 160k-voxel val cap is hit
 VOXEL_CFG = dict(range=NUSC_RANGE, voxel_size=NUSC_VOXEL, max_points_in_voxel=10, max_voxel_num=[120000, 160000])
 HEADS = ["reg", "height", "dim", "rot", "vel", "hm"]
+TEST_CFG = dict(post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], max_per_img=500,
+                nms=dict(use_rotate_nms=True, use_multi_class_nms=False, nms_pre_max_size=1000, nms_post_max_size=83,
+                         nms_iou_threshold=0.2),
+                score_threshold=0.1, pc_range=[-54, -54], out_size_factor=8, voxel_size=[0.075, 0.075])   # configs/...n0...:88-103
 
 
 def model_cfg(timesteps=1):
@@ -324,6 +328,19 @@ def run_gpu(args, rank, world, local):
         out_host, _ = model.forward_host(p, o, out_host)
         return out_host
 
+    det_bytes = [0]
+
+    def step_detect(i):
+        # inference as the reference runs it (voxelnet.py:51-56): forward + CenterHead.predict; only the detections
+        # (boxes, scores, labels of the kept objects) travel back to the host
+        flush.zero_()
+        p, o = pool_host[i % n_pool]
+        preds = model.forward_points(p.to(dev, non_blocking=True), o.to(dev, non_blocking=True))
+        dets = model.bbox_head.predict({}, preds, TEST_CFG)
+        host = [(d["box3d_lidar"].cpu(), d["scores"].cpu(), d["label_preds"].cpu()) for d in dets]
+        det_bytes[0] = sum(t.numel() * t.element_size() for h in host for t in h)
+        return host
+
     def timed(step_fn):
         for i in range(args.warmup):
             step_fn(i)
@@ -349,6 +366,7 @@ def run_gpu(args, rank, world, local):
         ms_res, launches = timed(step_resident)
         clocks = sampler.stop() if sampler else None
         ms_e2e, _ = timed(step_e2e)
+        ms_det, _ = timed(step_detect)
         prof = conv_profile(model, *pool_dev[0]) if rank == 0 else None
         vox_roof = voxelize_roofline(model, dev) if rank == 0 else None
     train_info = None
@@ -388,6 +406,9 @@ def run_gpu(args, rank, world, local):
                             precision=args.precision, parallelism="scene replicas x%d, no collective" % world),
                 e2e=dict(value=e2e_value, unit="scenes/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),
+                detect=dict(value=scenes / (ms_det / 1e3), unit="scenes/s", ms_per_step=ms_det / args.steps,
+                            what="host points -> H2D -> forward -> CenterHead.predict (decode + rotated NMS on device) -> "
+                                 "detections D2H", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(det_bytes[0])),
                 gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_voxelize=vox_roof,
                 cpu_baseline=cpu_baseline)
     if train_info is not None:

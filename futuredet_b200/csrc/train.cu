@@ -67,6 +67,9 @@ conv_wgrad_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta, in
   const int ti = t % tiles_ci;
   const int k = t / tiles_ci;
   const int ci0 = ti * TI, co0 = to * TO;
+  // the row chunks are cut from the DEVICE-side row count: capacities of strided levels are several times the number
+  // of active sites, and chunks cut from the capacity would leave most CTAs without rows
+  rows_per_cta = ((n + (int)gridDim.x - 1) / (int)gridDim.x + 63) & ~63;
   const long long rb = (long long)blockIdx.x * rows_per_cta;
   if (rb >= n) return;
   const int row_begin = (int)rb;
@@ -206,8 +209,9 @@ static int launch_wgrad_i(const ConvArgs& a, float* dw, cudaStream_t stream) {
   }
 }
 
-static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream) {
+static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream, int precision = FD_PREC_FP32) {
   if (a.n_cap <= 0) return 0;
+  if (precision == FD_PREC_BF16X3 && wgrad_tc_supported(a)) return conv_wgrad_tc(a, dw, stream);
   switch (wg_tile(a.cin)) {
     case 128: return launch_wgrad_i<128>(a, dw, stream);
     case 64: return launch_wgrad_i<64>(a, dw, stream);
@@ -542,12 +546,12 @@ int fd_conv_wgrad(const fd_conv_desc* d, float* d_dw, void* stream_) {
     case FD_GATHER_TABLE:
       FD_REQUIRE(d->d_nbr && d->nbr_stride >= d->n_out_cap, "fd_conv_wgrad: bad neighbour table");
       FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY && d->out_stride >= d->cout, "fd_conv_wgrad: identity out rows only");
-      return launch_wgrad(a, d_dw, stream);
+      return launch_wgrad(a, d_dw, stream, d->precision);
     case FD_GATHER_CONV2D:
       FD_REQUIRE(d->K == d->kh * d->kw && d->sh >= 1 && d->sw >= 1, "fd_conv_wgrad: bad conv2d geometry");
       FD_REQUIRE(d->n_out_cap == d->B * d->Hout * d->Wout && !d->d_n_out, "fd_conv_wgrad: conv2d rows must be B*Hout*Wout");
       FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY && d->out_stride >= d->cout, "fd_conv_wgrad: identity out rows only");
-      return launch_wgrad(a, d_dw, stream);
+      return launch_wgrad(a, d_dw, stream, d->precision);
     case FD_GATHER_CONVT2D: {
       FD_REQUIRE(d->kh == d->sh && d->kw == d->sw && d->kh == d->kw && d->ph == 0 && d->pw == 0 && d->K == d->kh * d->kw,
                  "fd_conv_wgrad: convT2d supports kernel == stride, pad 0 only");

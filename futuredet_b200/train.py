@@ -13,8 +13,9 @@ reverse: loss gradient -> ConvT/Conv2d dgrad+wgrad -> BEV gather -> sparse dgrad
 Parameter gradients are written straight into flat bucket buffers (`GradBuckets`) so the data-parallel all-reduce
 (`shard.GradSync`) needs no packing copy; `param.grad` are views of those buckets, so any torch optimizer applies.
 
-Arithmetic is fp32 (CUDA-core kernels for wgrad; `precision="bf16x3"` moves forward / data-gradient convolutions with
-tensor-core friendly shapes to the tcgen05 kernel).
+Arithmetic is fp32 (`precision="fp32"`: exact CUDA-core kernels) or, with `precision="bf16x3"`, fp32-class on the
+tensor cores: forward, data-gradient and weight-gradient convolutions with tensor-core friendly shapes run on tcgen05
+with a 3-term bf16 split and fp32 accumulation in TMEM.
 """
 import numpy as np
 import torch
@@ -167,7 +168,7 @@ def sparse_conv_train(tape, x, conv, xt, grads, prec):
         gy = y.grad
         if gy is None:
             return
-        T.sparse_conv_wgrad(xin, gy, rb, grads.grad(conv.weight).view(K, cin, cout))
+        T.sparse_conv_wgrad(xin, gy, rb, grads.grad(conv.weight).view(K, cin, cout), precision=prec)
         grads.done(conv.weight)
         if conv.bias is not None:
             T.col_sum(gy, grads.grad(conv.bias), rb.n_out_dev, rb.n_out_cap)
@@ -229,7 +230,7 @@ def conv2d_train(tape, x, conv, grads, prec, pad=None, out=None):
         if gy is None:
             return
         gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=w.device)
-        T.conv2d_wgrad(x.t, gy, gw, ksize, stride, padding, transposed)
+        T.conv2d_wgrad(x.t, gy, gw, ksize, stride, padding, transposed, precision=prec)
         g4 = gw.view(ksize[0], ksize[1], cin, cout)
         # back to the parameter layout: Conv2d [Cout,Cin,kh,kw], ConvTranspose2d [Cin,Cout,kh,kw]
         grads.grad(conv.weight).copy_(g4.permute(2, 3, 0, 1) if transposed else g4.permute(3, 2, 0, 1))

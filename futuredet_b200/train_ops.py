@@ -75,7 +75,7 @@ def Rulebook_pair_num(rb):
 
 
 # ------------------------------------------------------------------------------------------ weight gradients
-def sparse_conv_wgrad(x, dy, rb, dw):
+def sparse_conv_wgrad(x, dy, rb, dw, precision="fp32"):
     """dw [K,Cin,Cout] += sum over rulebook pairs of x[i]^T dy[o] (dw must be zeroed by the caller)."""
     lib = L.load()
     x, xs, cin = _rows(x)
@@ -91,11 +91,12 @@ def sparse_conv_wgrad(x, dy, rb, dw):
     d.mode = L.GATHER_TABLE
     d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
     d.out_map = L.OUTMAP_IDENTITY
+    d.precision = L.PRECISIONS[precision]
     L.check(lib.fd_conv_wgrad(C.byref(d), _ptr(dw), _stream()), "fd_conv_wgrad(sparse)")
     return dw
 
 
-def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False):
+def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False, precision="fp32"):
     """Weight gradient of conv2d_nhwc / its ConvTranspose2d(k == s) form.  x [B,H,W,Cin], dy [B,Ho,Wo,Cout] (channel
     slices allowed), dw [kh*kw, Cin, Cout] zeroed by the caller."""
     lib = L.load()
@@ -113,6 +114,7 @@ def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False):
     d.kh, d.kw, d.sh, d.sw, d.ph, d.pw = kh, kw, stride[0], stride[1], padding[0], padding[1]
     d.out_map = L.OUTMAP_IDENTITY
     d.n_out_cap = B * H * W if transposed else B * Ho * Wo
+    d.precision = L.PRECISIONS[precision]
     L.check(lib.fd_conv_wgrad(C.byref(d), _ptr(dw), _stream()), "fd_conv_wgrad(conv2d)")
     return dw
 

@@ -244,7 +244,9 @@ int fd_rulebook_transpose(const int32_t* d_nbr, int nbr_stride, const int32_t* d
  * `indice_conv_backward` filter gradient / cuDNN wgrad).  `desc` describes the FORWARD convolution with
  * d_in = the layer input, d_out = dL/dy (read only) laid out as the forward output (out_map / out_stride honoured);
  * scale/shift/residual/relu/d_w are ignored.  Accumulates with fp32 atomics into d_dw [K,Cin,Cout]: the caller
- * zeroes it.  fp32 rows only.                                                                                */
+ * zeroes it.  fp32 rows only.  desc->precision: FD_PREC_FP32 = exact fp32 on CUDA cores; FD_PREC_BF16X3 = tcgen05
+ * (both operands MN-major, 3-term bf16 split, fp32 accumulation in TMEM) where the rows allow it (Cin, Cout multiples
+ * of 8, 16-byte aligned rows, identity output map), the CUDA-core kernel otherwise.                            */
 int fd_conv_wgrad(const fd_conv_desc* desc, float* d_dw, void* stream);
 
 /* BatchNorm1d/2d in training mode over the first n rows of x [n, C] (det3d/models/utils/norm.py:59-64 ->

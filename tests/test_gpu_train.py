@@ -125,6 +125,9 @@ def test_sparse_conv_backward(cuda, cin, cout, strided):
     dw = torch.zeros((27, cin, cout), device=cuda)
     T.sparse_conv_wgrad(xg, gg, rb, dw)
     close(dw, wr.grad, 2e-4, "wgrad")
+    dw3 = torch.zeros((27, cin, cout), device=cuda)            # tcgen05 arm (CUDA-core kernel when Cin % 8 != 0)
+    T.sparse_conv_wgrad(xg, gg, rb, dw3, precision="bf16x3")
+    close(dw3, wr.grad, 3e-4, "wgrad bf16x3")
     wg = w.to(cuda)
     if strided:
         nbr_t = T.rulebook_transpose(rb, cap)
@@ -181,6 +184,9 @@ def test_conv2d_backward(cuda, kind):
     g4 = dw.view(conv.kernel_size[0], conv.kernel_size[1], cin, cout)
     got_w = g4.permute(2, 3, 0, 1) if transposed else g4.permute(3, 2, 0, 1)
     close(got_w, conv.weight.grad, 2e-4, "wgrad " + kind)
+    dw3 = torch.zeros((K, cin, cout), device=cuda)
+    T.conv2d_wgrad(xg, gyg, dw3, tuple(conv.kernel_size), tuple(conv.stride), pad, transposed, precision="bf16x3")
+    close(dw3, dw, 3e-4, "wgrad bf16x3 " + kind)
     wt = w.transpose(1, 2).contiguous()
     if transposed:
         dx = ops.conv2d_nhwc(gyg, wt, (2, 2), (2, 2), (0, 0), precision="fp32")
@@ -190,6 +196,21 @@ def test_conv2d_backward(cuda, kind):
     if conv.bias is not None:
         db = torch.empty(cout, device=cuda)
         close(T.col_sum(gyg, db), conv.bias.grad, 1e-4, "bias grad")
+
+
+@pytest.mark.parametrize("cin,cout", [(256, 256), (128, 256), (512, 64), (64, 8)])
+def test_conv2d_wgrad_tensor_core_wide(cuda, cin, cout):
+    """Neck / head sized weight gradients (several 128-wide ci / co tiles, partial N) on the tcgen05 arm vs the exact
+    CUDA-core arm."""
+    rng = np.random.default_rng(cin + cout)
+    B, H, W = 2, 20, 18
+    x = torch.from_numpy(rng.standard_normal((B, H, W, cin)).astype(np.float32)).to(cuda)
+    gy = torch.from_numpy(rng.standard_normal((B, H, W, cout)).astype(np.float32)).to(cuda)
+    dw32 = torch.zeros((9, cin, cout), device=cuda)
+    dw3 = torch.zeros((9, cin, cout), device=cuda)
+    T.conv2d_wgrad(x, gy, dw32, (3, 3), (1, 1), (1, 1))
+    T.conv2d_wgrad(x, gy, dw3, (3, 3), (1, 1), (1, 1), precision="bf16x3")
+    close(dw3, dw32, 2e-4, "wide wgrad")
 
 
 def test_bev_scatter_gather(cuda):
