@@ -140,10 +140,24 @@ class VoxelNet(SingleStageDetector):
         """End-to-end entry for host-resident inputs: pinned `points_host [sum N, >=5]` fp32 and `batch_offsets_host
         [B+1]` int32 are copied to the module's device, the fused forward runs, and every head tensor of every task is
         copied back into one pinned host tensor `[B, H, W, sum c]` (returned with the per-head channel ranges).
-        Nothing synchronises until the caller touches the result (`torch.cuda.current_stream().synchronize()`)."""
+        The H2D copy, the kernels and the D2H copy run on three streams chained by events, so consecutive calls
+        pipeline (the upload of batch i+1 overlaps the kernels of batch i, the download of batch i overlaps the kernels
+        of batch i+1).  Nothing synchronises with the host: wait on `self.host_result_ready` (a CUDA event) or
+        `torch.cuda.synchronize()` before reading the returned tensors."""
         dev = next(self.parameters()).device
-        pts = points_host.to(dev, non_blocking=True)
-        off = batch_offsets_host.to(dev, non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
+        streams = self.__dict__.setdefault("_io_streams", {})
+        if dev not in streams:
+            streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = streams[dev]
+        with torch.cuda.stream(s_in):
+            pts = points_host.to(dev, non_blocking=True)
+            off = batch_offsets_host.to(dev, non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(s_in)
+        cur.wait_event(uploaded)
+        pts.record_stream(cur)
+        off.record_stream(cur)
         preds = self.forward_points(pts, off)
         outs, layout = [], []
         for t_id, p in enumerate(preds):
@@ -163,8 +177,15 @@ class VoxelNet(SingleStageDetector):
                                          v.storage_offset() - v.storage_offset() % v.stride(2)))
         if out_host is None:
             out_host = [torch.empty(b.shape, dtype=b.dtype).pin_memory() for b in bufs]
-        for h, b in zip(out_host, bufs):
-            h.copy_(b, non_blocking=True)
+        computed = torch.cuda.Event()
+        computed.record(cur)
+        s_out.wait_event(computed)
+        with torch.cuda.stream(s_out):
+            for h, b in zip(out_host, bufs):
+                h.copy_(b, non_blocking=True)
+                b.record_stream(s_out)
+            self.host_result_ready = torch.cuda.Event()
+            self.host_result_ready.record(s_out)
         return out_host, layout
 
     def forward_points(self, points, batch_offsets, return_voxels=False):

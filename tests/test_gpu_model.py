@@ -164,3 +164,11 @@ def test_forward_host_matches_forward_points(cuda):
         torch.testing.assert_close(outs[0][..., col:col + c], want, rtol=0, atol=0)
         col += c
     assert [n for _, n, _ in layout] == ["reg", "height", "dim", "rot", "vel", "hm"]
+    # pipelined calls (upload / kernels / download on three streams): every result belongs to its own input
+    scenes = [synth_scene(15000 + 2000 * i, seed=20 + i) for i in range(3)]
+    hosts = [(torch.from_numpy(sc).pin_memory(), torch.tensor([0, len(sc)], dtype=torch.int32).pin_memory()) for sc in scenes]
+    results = [m.forward_host(p, o)[0] for p, o in hosts]
+    m.host_result_ready.synchronize()
+    for (p, o), res in zip(hosts, results):
+        want = m.forward_points(p.to(cuda), o.to(cuda))[0]["hm"].permute(0, 2, 3, 1).cpu()
+        torch.testing.assert_close(res[0][..., -1:], want, rtol=0, atol=0)

@@ -338,18 +338,67 @@ def test_rpn_center_head_training_matches_reference_golden(cuda, golden_dir):
 
 
 # ------------------------------------------------------------------------------------------------ whole model
-def build_model(timesteps, dev):
+def build_model(timesteps, dev, tasks=None):
     torch.manual_seed(0)
+    tasks = tasks or [dict(num_class=1, class_names=["car"])]
     cfg = dict(
         type="VoxelNet", pretrained=None, reader=dict(type="VoxelFeatureExtractorV3", num_input_features=5),
         backbone=dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8),
         neck=dict(type="RPN", layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256],
                   us_layer_strides=[1, 2], us_num_filters=[256, 256], num_input_features=256),
-        bbox_head=dict(type="CenterHead", in_channels=512, tasks=[dict(num_class=1, class_names=["car"])],
+        bbox_head=dict(type="CenterHead", in_channels=512, tasks=tasks,
                        dataset="nuscenes", weight=0.25, code_weights=[1.0] * 6 + [0.2, 0.2, 1.0, 1.0],
                        common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
                        share_conv_channel=64, dcn_head=False, timesteps=timesteps, classify=False))
     return fb.build_detector(cfg)
+
+
+def test_two_task_head_train_step_matches_oracle(cuda):
+    """BASELINE configs[4] shape: mixed car + pedestrian heads (two SepHeads on the shared feature, per-task targets and
+    losses, trainer.py:85 sums them): loss per task and every gradient vs autograd over the oracle."""
+    from oracle.gen_golden import make_targets
+    rng = np.random.default_rng(8)
+    tasks = [dict(num_class=1, class_names=["car"]), dict(num_class=1, class_names=["pedestrian"])]
+    model = build_model(3, cuda, tasks=tasks)
+    g0 = torch.Generator().manual_seed(21)
+    for m in model.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.weight.data.copy_(0.4 + 0.2 * torch.rand(m.weight.shape, generator=g0))
+            m.bias.data.copy_(1.5 + 0.3 * torch.rand(m.bias.shape, generator=g0))
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    B, grid = 1, [64, 64, 40]
+    c = random_sites(rng, B, [40, 64, 64], 4000)
+    n = len(c)
+    feats = rng.standard_normal((n, 5)).astype(np.float32)
+    voxels = np.zeros((n, 10, 5), np.float32); voxels[:, 0] = feats
+    ta = make_targets(B, 8, 8, 3, torch.Generator().manual_seed(1), max_objs=10)
+    tb = make_targets(B, 8, 8, 3, torch.Generator().manual_seed(2), max_objs=10)
+    example = {k: [[ta[k][t][0], tb[k][t][0]] for t in range(3)] for k in ta}            # [timestep][task]
+    example.update(voxels=torch.from_numpy(voxels).to(cuda), num_points=torch.ones(n, dtype=torch.int32, device=cuda),
+                   coordinates=torch.from_numpy(c).to(cuda), num_voxels=torch.tensor([0] * B), shape=[np.array(grid)] * B)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    sub = lambda p: {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
+    bev = S.backbone_forward(sub("backbone."), torch.from_numpy(feats), c, B, grid, bn_eval=S.bn_train(0.01))
+    feat = D.rpn_forward(sub("neck."), bev, [5, 5], [1, 2], [1, 2], train=0.01)
+    preds = D.center_head_forward(sub("bbox_head."), feat, [HEADS, HEADS], train=0.1)
+    ref = center_head_loss_ref(preds, example, 3, [1.0] * 6 + [0.2, 0.2, 1.0, 1.0], 0.25)
+    sum(ref["loss"]).backward()
+    model.to(cuda).train()
+    tr = train.NativeTrainer(model, precision="bf16x3")
+    losses = tr.step(example)
+    assert len(losses["loss"]) == 2
+    for t_id in range(2):
+        close(losses["loss"][t_id], ref["loss"][t_id], 1e-3, "loss task %d" % t_id)
+    bad = []
+    for k, p in model.named_parameters():
+        want = sd[k].grad
+        err, refmax = float((p.grad.cpu() - want).abs().max()), float(want.abs().max())
+        if err > 5e-3 * refmax + 2e-6:
+            bad.append((k, "%.1e" % (err / max(refmax, 1e-30))))
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("timesteps,precision,init", [(3, "fp32", "smooth"), (7, "bf16x3", "smooth"),
