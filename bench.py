@@ -64,11 +64,31 @@ def build_model(seed=0):
 
 
 def peaks():
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json when present (HBM copy GB/s, dense bf16 TFLOP/s burst
+    and sustained), else the fallback of /opt/skills/guides/B200_PROFILING.md; `src` says which."""
+    fb = dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    if not os.path.exists(p):
+        return fb
+    try:
         d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+        def pick(*names):
+            for n in names:
+                v = d.get(n)
+                if isinstance(v, dict):
+                    v = v.get("value")
+                if isinstance(v, (int, float)) and v > 0:
+                    return float(v)
+            return None
+        hbm = pick("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs", "hbm")
+        burst = pick("bf16_tflops", "bf16_tflops_burst", "bf16_dense_tflops")
+        sust = pick("bf16_tflops_sustained", "bf16_sustained_tflops") or burst
+        if hbm and burst:
+            return dict(hbm=hbm, tf_burst=burst, tf_sustained=sust, src="measured")
+    except (OSError, ValueError):
+        pass
+    return fb
 
 
 class ClockSampler:

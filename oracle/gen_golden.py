@@ -15,6 +15,10 @@ that nothing on the GPU box needs the reference.  Usage:  python oracle/gen_gold
                      nuScenes-format .bin sweeps written to a temp dir (`python oracle/gen_golden.py loader`)
   assign.npz         reference `AssignLabel.__call__` (det3d/datasets/pipelines/preprocess.py:336-909, standard sampler)
                      on synthetic car annotations, 3 timesteps (`python oracle/gen_golden.py assign`)
+  state_keys.json    parameter / buffer names and shapes of the REFERENCE modules: RPN, CenterHead (n0 and n3 heads) built
+                     from det3d.models, and SpMiddleResNetFHD built by executing the reference's own
+                     det3d/models/backbones/scn.py with `spconv` bound to the spconv-1.x-shaped classes of this repo
+                     (checkpoint compatibility; `python oracle/gen_golden.py keys`)
   neck_head_train.pt the same reference classes in TRAINING mode: loss dict, every parameter gradient after
                      `sum(loss["loss"]).backward()` (trainer.py:85,317-344), the input gradient and the updated
                      BatchNorm running statistics  (`python oracle/gen_golden.py train` regenerates only this file)
@@ -273,8 +277,38 @@ def gen_assign():
     np.savez_compressed(os.path.join(OUT, "assign.npz"), **out)
 
 
+def gen_state_keys():
+    import json
+    M = import_ref_models()
+    from futuredet_b200 import sparse as fsp
+    sp = types.ModuleType("spconv")
+    for n in ("SparseConvTensor", "SubMConv3d", "SparseConv3d", "SparseSequential", "SparseModule"):
+        setattr(sp, n, getattr(fsp, n))
+    sys.modules["spconv"] = sp
+    spec = importlib.util.spec_from_file_location("det3d.models.backbones.scn_ref", REF + "/det3d/models/backbones/scn.py")
+    scn = importlib.util.module_from_spec(spec)
+    scn.__package__ = "det3d.models.backbones"
+    sys.modules[spec.name] = scn
+    spec.loader.exec_module(scn)
+    out = {}
+    bb = scn.SpMiddleResNetFHD(num_input_features=5, ds_factor=8)
+    out["backbone"] = {k: list(v.shape) for k, v in bb.state_dict().items()}
+    neck = M.build_neck(dict(type="RPN", layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256],
+                             us_layer_strides=[1, 2], us_num_filters=[256, 256], num_input_features=256,
+                             logger=logging.getLogger("RPN")))
+    out["neck"] = {k: list(v.shape) for k, v in neck.state_dict().items()}
+    for name, T in (("head_n0", 1), ("head_n3", 7)):
+        head = M.build_head(dict(HEAD_CFG, in_channels=512, timesteps=T))
+        out[name] = {k: list(v.shape) for k, v in head.state_dict().items()}
+    json.dump(out, open(os.path.join(OUT, "state_keys.json"), "w"), indent=0, sort_keys=True)
+    print("state keys:", {k: len(v) for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "keys" in sys.argv[1:]:
+        gen_state_keys()
+        return
     if "assign" in sys.argv[1:]:
         gen_assign()
         return
@@ -326,6 +360,7 @@ def main():
     gen_predict(M)
     gen_loader()
     gen_assign()
+    gen_state_keys()
 
 
 if __name__ == "__main__":
