@@ -278,10 +278,20 @@ def train_bench(args, rank, world, dev):
     ex = {k: [[t.to(dev) for t in ts] for ts in v] for k, v in ex.items()}
     losses = None
 
+    # single rank: the sync-free step (764 launches) is replayed as ONE CUDA graph; several ranks keep the eager step so
+    # that the bucket all-reduces interleave with backward
+    graphed = None
+    if world == 1 and not args.train_eager:
+        from futuredet_b200 import graphs
+        graphed = graphs.GraphedTrainStep(tr, max_points=pts.shape[0], batch_size=B)
+
     def step():
         nonlocal losses
-        losses = tr.step(ex, points=pts, batch_offsets=off)
-        sync.finish()
+        if graphed is not None:
+            losses = graphed(ex, pts, off)
+        else:
+            losses = tr.step(ex, points=pts, batch_offsets=off)
+            sync.finish()
         opt.step()
 
     for _ in range(3):
@@ -304,6 +314,7 @@ def train_bench(args, rank, world, dev):
     return dict(workload="forecast_n3 (7-timestep heads) car, fwd+bwd+AdamW, 1 x 305k-pt scene per GPU per step "
                          "(BASELINE configs[2]; configs[3] for n_gpus > 1)", ms_per_step=ms,
                 samples_per_s=B * world / (ms / 1e3), precision=args.train_precision, steps=args.train_steps,
+                launch_mode="cuda graph replay" if graphed is not None else "eager",
                 gpu_launches_per_step=(lib.launch_count() - n0) // args.train_steps, loss=loss,
                 params=sum(p.numel() for p in m.parameters()), clocks=clocks,
                 allreduce_bytes_per_step=sync.bytes_reduced // max(args.train_steps, 1),
@@ -449,6 +460,7 @@ def main():
                     help="bf16x3 (default): tcgen05 tensor cores with a 3-term bf16 split, holds the 1e-3 parity contract; "
                          "fp32: CUDA-core exact arm; bf16: single pass, outside the parity contract")
     ap.add_argument("--train-steps", type=int, default=8, help="timed forecast_n3 fwd+bwd steps reported under 'train' (0: skip)")
+    ap.add_argument("--train-eager", action="store_true", help="do not replay the training step as a CUDA graph")
     ap.add_argument("--train-precision", default="bf16x3", choices=["fp32", "bf16x3"],
                     help="forward / data-gradient convolutions of the training step (weight gradients are always fp32)")
     args = ap.parse_args()

@@ -18,6 +18,15 @@ from .ops import _ptr, _stream
 TGT_SEL = [0, 1, 2, 3, 4, 5, 6, 7, -2, -1]       # drop the velocity targets (center_head.py:468)
 
 
+def _table(values, dtype, dev, keep):
+    """Small host table -> device through pinned memory with an asynchronous copy (a memcpy node when the step is
+    being captured into a CUDA graph; a pageable copy would synchronise and cannot be captured).  `keep` holds the
+    pinned source alive for as long as the copy (or the graph) may read it."""
+    host = torch.tensor(values, dtype=dtype).pin_memory()
+    keep.append(host)
+    return host.to(dev, non_blocking=True)
+
+
 def _plane(v, c):
     """channel c of a logical [B,C,H,W] view -> (address, batch stride, spatial stride); needs y*W+x addressing."""
     B, Cc, H, W = v.shape
@@ -46,7 +55,8 @@ class _TaskArgs:
         self.tgts = [example["anno_box"][i][task_id].to(dev, torch.float32).contiguous() for i in range(T)]
         self.M = self.ind.shape[1]
         self.tgt_dim = self.tgts[0].shape[-1]
-        self.sel = torch.tensor([s % self.tgt_dim for s in TGT_SEL], dtype=torch.int32, device=dev)
+        self.keep = []
+        self.sel = _table([s % self.tgt_dim for s in TGT_SEL], torch.int32, dev, self.keep)
         self.NC = len(TGT_SEL)
         self.planes = []            # (tensor, channel) per (t, c)
         ptrs, sbs, ssps = [], [], []
@@ -57,13 +67,13 @@ class _TaskArgs:
                 a, sb, ssp = _plane(v, c)
                 ptrs.append(a); sbs.append(sb); ssps.append(ssp)
             self.planes += planes
-        i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=dev)
+        i64 = lambda xs: _table(xs, torch.int64, dev, self.keep)
         self.ptrs = ptrs
         self.d_ptr, self.d_sb, self.d_ssp = i64(ptrs), i64(sbs), i64(ssps)
         self.d_tgt = i64([t_.data_ptr() for t_ in self.tgts])
         self.d_mask_t = i64([m.data_ptr() for m in self.masks_t])
-        self.cw = torch.tensor(head.code_weights, dtype=torch.float32, device=dev)
-        self.cwf = torch.tensor([float(x) for x in head.code_weights_forecast], dtype=torch.float32, device=dev)
+        self.cw = _table([float(x) for x in head.code_weights], torch.float32, dev, self.keep)
+        self.cwf = _table([float(x) for x in head.code_weights_forecast], torch.float32, dev, self.keep)
         self.weight = float(head.weight)
         self.hm_addr, self.hm_sb, self.hm_ssp = _plane(hm, 0)
 
@@ -105,7 +115,7 @@ def center_head_loss_backward(ctx, out_base, gout_base, gscale=None):
     for ptr in a.ptrs + [a.hm_addr]:
         if not (lo <= ptr < hi):
             raise RuntimeError("center_head_loss_backward: head tensors must be views of the given output buffer")
-    d_gptr = torch.tensor([q + delta for q in a.ptrs], dtype=torch.int64, device=a.dev)
+    d_gptr = _table([q + delta for q in a.ptrs], torch.int64, a.dev, a.keep)
     rc = lib.fd_center_head_loss_backward(C.c_void_p(a.hm_addr), C.c_void_p(a.hm_addr + delta), a.hm_sb, a.hm.stride(1),
                                           a.hm_ssp, _ptr(a.hm_t), a.B, a.Cc, a.H, a.W, _ptr(a.ind), _ptr(a.mask),
                                           _ptr(a.cat), a.M, a.T, a.NC, _ptr(a.d_ptr), _ptr(d_gptr), _ptr(a.d_sb),

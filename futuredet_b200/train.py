@@ -407,6 +407,7 @@ class NativeTrainer:
             out._grad = g
         self.tape.backward()
         self.grads.flush()
+        self._last_loss_ctx = ctxs       # keeps the pinned argument tables alive (a captured graph re-reads them on replay)
         self.tape = self._loss_ctx = None
 
     def step(self, example=None, points=None, batch_offsets=None):
