@@ -22,15 +22,15 @@ namespace fd {
 
 namespace wg {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;                // 16 warps: the stage is latency bound (gather -> split -> store), not MMA bound
 constexpr int KP = 64;                     // pairs per stage
 constexpr int ROWB = 128;                  // bytes of one operand row (64 bf16 channels)
 constexpr int BLOCK_BYTES = KP * ROWB;     // one 64-channel column block of one plane: 8 KB
 constexpr int PLANE_BYTES = 2 * BLOCK_BYTES;   // up to 128 channels
 constexpr int OPER_BYTES = 2 * PLANE_BYTES;    // hi + lo
 constexpr int STAGE_BYTES = 2 * OPER_BYTES;    // A + B: 64 KB
-constexpr int QN = 512;
-constexpr size_t SMEM = 1024 + 2 * STAGE_BYTES + 2 * QN * 4 + 64 + 64;
+constexpr int QN = 1024;                   // pair ring: < KP leftovers + one batch of THREADS rows
+constexpr size_t SMEM = 1024 + 2 * STAGE_BYTES + 2 * QN * 4 + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -115,7 +115,7 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta,
   int* q_out = q_in + QN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(q_out + QN);           // [0], [1]: MMAs of stage s done
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2);
-  int* s_wcnt = reinterpret_cast<int*>(s_tmem + 1);                     // 8 ints
+  int* s_wcnt = reinterpret_cast<int*>(s_tmem + 1);                     // THREADS / 32 ints
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.d_n ? min(*a.d_n, a.n_cap) : a.n_cap;
