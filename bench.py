@@ -323,14 +323,13 @@ def train_bench(args, rank, world, dev):
 
 
 def run_gpu(args, rank, world, local):
-    from futuredet_b200 import lib, neck, shard, sparse
+    from futuredet_b200 import lib, shard
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib.load()
-    sparse.DEFAULT_PRECISION = neck.DEFAULT_PRECISION = args.precision
-    model = build_model()
+    model = build_model().set_precision(args.precision)
     sd_cpu = {k: v.clone() for k, v in model.state_dict().items()} if rank == 0 else None
     model.to(dev).configure_voxelizer(VOXEL_CFG)
     B = args.batch

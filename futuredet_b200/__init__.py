@@ -11,5 +11,6 @@ from .registry import (BACKBONES, DETECTORS, HEADS, NECKS, PIPELINES, READERS, R
 from . import sparse, reader, backbone, neck, head, detector, voxel_generator, pipelines  # noqa: F401,E402
 from .compat import install as install_det3d_aliases  # noqa: F401,E402
 from .detector import VoxelNet  # noqa: F401,E402
+from .precision import default_precision, set_default_precision, use_precision  # noqa: F401,E402
 
 __version__ = "0.1.0"

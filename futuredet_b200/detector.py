@@ -16,6 +16,7 @@ import torch
 from torch import nn
 
 from . import ops
+from . import precision as _precision
 from .registry import DETECTORS, build_backbone, build_head, build_neck, build_reader
 
 
@@ -69,6 +70,19 @@ class VoxelNet(SingleStageDetector):
     def __init__(self, reader, backbone, neck, bbox_head, train_cfg=None, test_cfg=None, pretrained=None):
         super().__init__(reader, backbone, neck, bbox_head, train_cfg, test_cfg, pretrained)
         self.voxel_cfg = None      # set by configure_voxelizer() for forward_points()
+        self.precision = None      # None -> precision.default_precision() ("bf16x3": the tcgen05 arm)
+        for cfg in (train_cfg, test_cfg):      # optional `precision` key in either config dict
+            p = cfg.get("precision") if hasattr(cfg, "get") else None
+            if p is not None:
+                self.set_precision(p)
+
+    def set_precision(self, p):
+        """Arithmetic arm of every convolution of this detector: "bf16x3" (tensor cores, fp32-class results; the
+        default), "fp32" (exact fp32 on CUDA cores) or "bf16" (single pass); None follows the process default."""
+        _precision.set_module_precision(self, p)
+        self.precision = p
+        self.__dict__.pop("_trainer", None)
+        return self
 
     def extract_feat(self, data):
         if "mean_features" in data:          # fused path: VFE already done by the voxelizer
@@ -79,8 +93,7 @@ class VoxelNet(SingleStageDetector):
         # (split bf16 hi/lo rows on the tensor-core arm); `fused=False` keeps every boundary a plain fp32 tensor
         fmt = "fp32"
         if data.get("fused", False):
-            from .neck import act_fmt
-            fmt = act_fmt()
+            fmt = _precision.act_fmt(self.precision)
         x, voxel_feature = self.backbone(feats, data["coors"], data["batch_size"], data["input_shape"],
                                          n_dev=data.get("n_dev"), n_cap=data.get("n_cap"), out_fmt=fmt)
         if self.with_neck:
@@ -90,14 +103,12 @@ class VoxelNet(SingleStageDetector):
     def native_trainer(self, precision=None, attach_grads=True):
         """The NativeTrainer of this model (train-mode forward + hand-written backward), created on first use."""
         from . import train
-        key = (precision or self.train_precision, attach_grads)
+        key = (_precision.resolve(precision or self.precision), attach_grads)
         tr = self.__dict__.get("_trainer")
         if tr is None or tr[0] != key:
             tr = (key, train.NativeTrainer(self, precision=key[0], attach_grads=attach_grads))
             self.__dict__["_trainer"] = tr
         return tr[1]
-
-    train_precision = "fp32"
 
     def forward(self, example, return_loss=True, **kwargs):
         if self.training and return_loss:
@@ -111,7 +122,10 @@ class VoxelNet(SingleStageDetector):
         data = dict(features=example["voxels"], num_voxels=example["num_points"], coors=example["coordinates"],
                     batch_size=len(num_voxels), input_shape=example["shape"][0])
         x, _ = self.extract_feat(data)
-        preds = self.bbox_head(x, None)
+        bev_map = None
+        if getattr(self.bbox_head, "bev_map", False):          # voxelnet.py:49
+            bev_map = torch.stack(list(example["bev_map"]), dim=1).float()
+        preds = self.bbox_head(x, bev_map)
         if return_loss:
             return self.bbox_head.loss(example, preds)
         return self.bbox_head.predict(example, preds, self.test_cfg)

@@ -43,16 +43,24 @@ class _TaskArgs:
         dev = hm.device
         self.dev = dev
         self.B, self.Cc, self.H, self.W = hm.shape
-        self.T = T = head.timesteps
-        if not all(k in p for k in ("reg", "height", "dim", "vel", "rot")):
-            raise NotImplementedError("CenterHead.loss: only the vel+rot box encoding of the n0/n3 configs is implemented")
+        if not all(k in p for k in ("reg", "height", "dim", "vel", "rot")) or "rvel" in p:
+            raise NotImplementedError("CenterHead.loss: only the vel+rot box encoding of the shipped configs is implemented")
         self.hm = hm
-        self.hm_t = example["hm"][0][task_id].to(dev, torch.float32).contiguous()
-        self.ind = example["ind"][0][task_id].to(dev, torch.int64).contiguous()
-        self.mask = example["mask"][0][task_id].to(dev, torch.uint8).contiguous()
-        self.cat = example["cat"][0][task_id].to(dev, torch.int64).contiguous()
-        self.masks_t = [example["mask"][i][task_id].to(dev, torch.uint8).contiguous() for i in range(T)]
-        self.tgts = [example["anno_box"][i][task_id].to(dev, torch.float32).contiguous() for i in range(T)]
+        if getattr(head, "dense", False):
+            # dense mode (center_head.py:413-415,441-443,485-487,506-507): task i is the single-timestep head of
+            # forecast timestep i, supervised by that timestep's targets of the one class group -> the same
+            # expression with T = 1 and example[...][task_id][0]
+            self.T = T = 1
+            ts, g = [task_id], 0
+        else:
+            self.T = T = head.timesteps
+            ts, g = list(range(T)), task_id
+        self.hm_t = example["hm"][ts[0]][g].to(dev, torch.float32).contiguous()
+        self.ind = example["ind"][ts[0]][g].to(dev, torch.int64).contiguous()
+        self.mask = example["mask"][ts[0]][g].to(dev, torch.uint8).contiguous()
+        self.cat = example["cat"][ts[0]][g].to(dev, torch.int64).contiguous()
+        self.masks_t = [example["mask"][i][g].to(dev, torch.uint8).contiguous() for i in ts]
+        self.tgts = [example["anno_box"][i][g].to(dev, torch.float32).contiguous() for i in ts]
         self.M = self.ind.shape[1]
         self.tgt_dim = self.tgts[0].shape[-1]
         self.keep = []
@@ -80,6 +88,10 @@ class _TaskArgs:
 
 def center_head_loss(head, example, preds_dicts, return_ctx=False):
     lib = L.load()
+    if not (getattr(head, "standard", True) or getattr(head, "dense", False)) or getattr(head, "two_stage", False):
+        raise NotImplementedError("CenterHead.loss: standard and dense modes are implemented (the modes of the shipped "
+                                  "configs); reverse / sparse / classify / wide_head / two_stage are not")
+    dense = getattr(head, "dense", False)
     rets, ctxs = [], []
     for task_id, p in enumerate(preds_dicts):
         a = _TaskArgs(head, example, p, task_id)
@@ -92,9 +104,10 @@ def center_head_loss(head, example, preds_dicts, return_ctx=False):
                                      _ptr(a.cw), _ptr(a.cwf), a.weight, _ptr(out), _ptr(ws), _stream())
         L.check(rc, "fd_center_head_loss")
         elem = out[3 + T:].view(T, NC)
+        le = [elem[t].detach().cpu() if not return_ctx else elem[t] for t in range(T)]
         rets.append({"loss": out[0], "hm_loss": out[1].detach().cpu() if not return_ctx else out[1],
                      "loc_loss": [out[3 + t] for t in range(T)],
-                     "loc_loss_elem": [elem[t].detach().cpu() if not return_ctx else elem[t] for t in range(T)],
+                     "loc_loss_elem": le[0] if dense else le,          # dense: one tensor, not a list (:530-532)
                      "num_positive": out[2]})
         ctxs.append(a)
     merged = defaultdict(list)

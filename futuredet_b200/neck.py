@@ -13,10 +13,9 @@ import torch
 from torch import nn
 
 from . import ops
+from . import precision as _precision
 from .registry import NECKS
 from .sparse import folded_epilogue
-
-DEFAULT_PRECISION = "fp32"
 
 
 def build_norm_2d(norm_cfg, planes):
@@ -47,13 +46,15 @@ def conv_weight_kio(conv):
 
 def act_fmt(precision=None):
     """Inter-layer activation format of a precision: fp32 rows, or split bf16 hi/lo rows on the tensor-core arm."""
-    return "fp32" if (precision or DEFAULT_PRECISION) == "fp32" else "split"
+    return _precision.act_fmt(precision)
 
 
 def conv_weight_kio_dmajor(conv, C, D):
     """Weight for an input whose channels arrive d-major (j = d*C + c) instead of the reference's c*D + d."""
     w = conv_weight_kio(conv)
-    key = (w.data_ptr(), C, D)
+    # keyed on the parameter itself: `w` is a derived temporary whose address the allocator recycles between
+    # optimizer steps (a stale hit would run the first neck conv with pre-update weights)
+    key = (conv.weight.data_ptr(), conv.weight._version, C, D)
     cache = conv.__dict__.setdefault("_kio_dmajor_cache", {})
     if cache.get("k") != key:
         j = torch.arange(C * D, device=w.device)
@@ -67,7 +68,7 @@ def run_conv(x, conv, bn, relu, out=None, pad=None, precision=None, out_fmt=None
     scale, shift = folded_epilogue(conv, bn)
     transposed = isinstance(conv, nn.ConvTranspose2d)
     padding = conv.padding if pad is None else pad
-    prec = precision or DEFAULT_PRECISION
+    prec = _precision.resolve(precision)
     if prec != "fp32" and conv.in_channels % 8 != 0:
         prec = "fp32"
     w = conv_weight_kio(conv) if dmajor is None else conv_weight_kio_dmajor(conv, *dmajor)
@@ -109,6 +110,7 @@ class RPN(nn.Module):
         assert len(ds_layer_strides) == len(layer_nums) == len(ds_num_filters)
         assert len(us_num_filters) == len(us_layer_strides)
         self._upsample_start_idx = len(layer_nums) - len(us_layer_strides)
+        self.precision = None     # None -> precision.default_precision()
         ratios = [us_layer_strides[i] / np.prod(ds_layer_strides[: i + self._upsample_start_idx + 1])
                   for i in range(len(us_layer_strides))]
         assert all(r == ratios[0] for r in ratios)
@@ -150,7 +152,8 @@ class RPN(nn.Module):
     def forward(self, x, out_fmt="fp32"):
         """x logical [B,C,H,W] (or a channels-last ops.Feat) -> logical [B, sum(us_num_filters), H', W']
         (channels-last memory); out_fmt="split" (fused pipeline) returns a split-row ops.Feat [B,H',W',C]."""
-        fmt = act_fmt()
+        prec = _precision.resolve(self.precision)
+        fmt = act_fmt(prec)
         dmajor = getattr(x, "bev_dmajor", None)          # set by the fused backbone (channel = d*C + c)
         x = as_nhwc_feat(x, fmt)
         B = x.t.shape[0]
@@ -160,9 +163,10 @@ class RPN(nn.Module):
         n_up = len(self.deblocks)
         for i, block in enumerate(self.blocks):
             mods = list(block)
-            x = ops.as_feat(run_conv(x, mods[1], mods[2], True, pad=(1, 1), dmajor=dmajor if i == 0 else None))   # ZeroPad2d(1) + conv(pad 0)
+            x = ops.as_feat(run_conv(x, mods[1], mods[2], True, pad=(1, 1), precision=prec,
+                                     dmajor=dmajor if i == 0 else None))   # ZeroPad2d(1) + conv(pad 0)
             for k in range(4, len(mods), 3):
-                x = ops.as_feat(run_conv(x, mods[k], mods[k + 1], True))
+                x = ops.as_feat(run_conv(x, mods[k], mods[k + 1], True, precision=prec))
             j = i - self._upsample_start_idx
             if j >= 0:
                 up, bn = self.deblocks[j][0], self.deblocks[j][1]
@@ -175,7 +179,7 @@ class RPN(nn.Module):
                     out = ops.Feat(torch.empty((B, Ho, Wo, sum(self._num_upsample_filters)), dtype=torch.float32,
                                                device=x.t.device), final_fmt)
                 c = self._num_upsample_filters[j]
-                run_conv(x, up, bn, True, out=out.slice(col, c))
+                run_conv(x, up, bn, True, out=out.slice(col, c), precision=prec)
                 col += c
         res = x if n_up == 0 else out
         if res.fmt == "split":

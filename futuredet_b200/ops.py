@@ -325,6 +325,18 @@ def to_split(x, n_dev=None):
     return Feat(out, "split")
 
 
+def copy_rows(src, dst, n_dev=None):
+    """dst[..., :] = src[..., :] between two Feat views (any format pair, channel slices allowed)."""
+    lib = L.load()
+    src, dst = as_feat(src), as_feat(dst)
+    if src.c != dst.c or src.rows != dst.rows:
+        raise RuntimeError("copy_rows: shape mismatch")
+    rc = lib.fd_convert_rows(C.c_void_p(src.ptr), FMT[src.fmt], src.row_stride, src.ctot, C.c_void_p(dst.ptr),
+                             FMT[dst.fmt], dst.row_stride, dst.ctot, src.c, _ptr(n_dev), src.rows, _stream())
+    L.check(rc, "fd_convert_rows")
+    return dst
+
+
 def _conv_desc(x, cin, w, scale, shift, residual, relu, out, precision, separate=False):
     d = L.ConvDesc()
     d.d_in = x.ptr; d.in_stride = x.row_stride; d.cin = cin

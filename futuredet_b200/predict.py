@@ -46,21 +46,41 @@ def _channels_last_layout(p, names):
 
 
 def center_head_predict(head, example, preds_dicts, test_cfg):
-    lib = L.load()
+    if getattr(head, "dense", False):
+        # dense mode (center_head.py:606-607,693-713): every task is an independent single-timestep head; each is
+        # decoded + NMS-ed on its own and the per-sample results are concatenated with label_preds offset by the
+        # number of classes of the preceding tasks
+        parts = [_predict_task(head, example, p, test_cfg, [0]) for p in preds_dicts]
+        out, flag = [], 0
+        flags = []
+        for nc in head.num_classes:
+            flags.append(flag)
+            flag += nc
+        for i in range(len(parts[0])):
+            out.append({"box3d_lidar": torch.cat([pt[i]["box3d_lidar"] for pt in parts]),
+                        "scores": torch.cat([pt[i]["scores"] for pt in parts]),
+                        "label_preds": torch.cat([pt[i]["label_preds"] + f for pt, f in zip(parts, flags)]),
+                        "metadata": parts[0][i]["metadata"], "cells": torch.cat([pt[i]["cells"] for pt in parts])})
+        return out
     if not getattr(head, "standard", True):
-        raise NotImplementedError("CenterHead.predict: only the standard mode is on the hot path")
+        raise NotImplementedError("CenterHead.predict: standard and dense modes are implemented")
+    T_head = head.timesteps
+    vel_i = list(range(T_head))
+    if len(vel_i) == 1:
+        vel_i = vel_i * head.target_timesteps                          # :566-567
+    return _predict_task(head, example, preds_dicts[0], test_cfg, vel_i)                  # center_head.py:560
+
+
+def _predict_task(head, example, p, test_cfg, vel_i):
+    lib = L.load()
     if _cfg(test_cfg, "circular_nms", False) or _cfg(test_cfg, "per_class_nms", False):
-        raise NotImplementedError("CenterHead.predict: circular / per-class NMS are not used by the n0 / n3 configs")
-    p = preds_dicts[0]                                                 # center_head.py:560
+        raise NotImplementedError("CenterHead.predict: circular / per-class NMS are not used by the shipped configs")
     names = ["reg", "height", "dim", "rot", "vel", "hm"]
     if not all(n in p for n in names):
-        raise NotImplementedError("CenterHead.predict: needs the reg/height/dim/rot/vel/hm heads of the n0 / n3 configs")
+        raise NotImplementedError("CenterHead.predict: needs the reg/height/dim/rot/vel/hm heads of the shipped configs")
     base, off = _channels_last_layout(p, names)
     B, H, W, S = base.shape
-    T_head = head.timesteps
-    vel_c = [off["vel"] + 2 * i for i in range(T_head)]
-    if len(vel_c) == 1:
-        vel_c = vel_c * head.target_timesteps                          # :566-567
+    vel_c = [off["vel"] + 2 * i for i in vel_i]
     T = len(vel_c)
     nms = _cfg(test_cfg, "nms")
     pre = int(_cfg(nms, "nms_pre_max_size"))

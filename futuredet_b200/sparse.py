@@ -17,8 +17,7 @@ import torch
 from torch import nn
 
 from . import ops
-
-DEFAULT_PRECISION = "fp32"
+from . import precision as _precision
 
 
 def _triple(v):
@@ -105,7 +104,7 @@ class _SparseConvBase(SparseModule):
         self.indice_key = indice_key
         self.weight = nn.Parameter(torch.empty(*self.kernel_size, in_channels, out_channels))
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
-        self.precision = None     # None -> sparse.DEFAULT_PRECISION
+        self.precision = None     # None -> precision.default_precision()
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -148,7 +147,7 @@ class _SparseConvBase(SparseModule):
         Tensor-core precisions keep activations in the split bf16 hi/lo row format between layers."""
         rb = self.rulebook(x)
         scale, shift = folded_epilogue(self, bn)
-        prec = self.precision or DEFAULT_PRECISION
+        prec = _precision.resolve(self.precision)
         xin = x._feat
         w = self.weight_kio()
         if prec != "fp32" and self.in_channels % 8 != 0:

@@ -256,9 +256,14 @@ def conv2d_train(tape, x, conv, grads, prec, pad=None, out=None):
 class NativeTrainer:
     """Train-mode forward + backward of a futuredet_b200 VoxelNet.  One instance per model / process."""
 
-    def __init__(self, model, precision="fp32", bucket_bytes=25 << 20, attach_grads=True):
+    def __init__(self, model, precision=None, bucket_bytes=25 << 20, attach_grads=True):
+        from . import precision as _precision
         self.model = model
-        self.precision = precision
+        self.precision = _precision.resolve(precision or getattr(model, "precision", None))
+        h = model.bbox_head
+        if h.forecast_feature or h.bev_map or h.two_stage or h.wide_head:
+            raise NotImplementedError("NativeTrainer: the forecast_feature / bev_map / two_stage / wide_head head variants "
+                                      "run forward (inference) only; training covers the standard and dense modes")
         self.grads = GradBuckets(list(model.parameters()), bucket_bytes, attach=attach_grads)
         self.tape = None
         self._loss_ctx = None

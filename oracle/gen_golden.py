@@ -19,6 +19,13 @@ that nothing on the GPU box needs the reference.  Usage:  python oracle/gen_gold
                      from det3d.models, and SpMiddleResNetFHD built by executing the reference's own
                      det3d/models/backbones/scn.py with `spconv` bound to the spconv-1.x-shaped classes of this repo
                      (checkpoint compatibility; `python oracle/gen_golden.py keys`)
+  backbone_scn.pt    the reference's OWN backbone source (det3d/models/backbones/scn.py:37-176, SparseBasicBlock +
+                     SpMiddleResNetFHD, executed unmodified) run on the CPU with `spconv` bound to oracle/spconv_shim.py:
+                     input voxels, state_dict, BEV output and per-stage features / indices on a reduced x/y grid
+                     (`python oracle/gen_golden.py backbone`)
+  head_variants.pt   reference CenterHead in the n3dtf (dense + forecast_feature) and n3dtfm (+ bev_map) modes
+                     (center_head.py:99-124,268-390): forward incl. `feats`, dense loss (:413-415,485-507)
+                     (`python oracle/gen_golden.py variants`)
   neck_head_train.pt the same reference classes in TRAINING mode: loss dict, every parameter gradient after
                      `sum(loss["loss"]).backward()` (trainer.py:85,317-344), the input gradient and the updated
                      BatchNorm running statistics  (`python oracle/gen_golden.py train` regenerates only this file)
@@ -277,6 +284,105 @@ def gen_assign():
     np.savez_compressed(os.path.join(OUT, "assign.npz"), **out)
 
 
+def load_ref_scn(spconv_module):
+    """Execute the reference's det3d/models/backbones/scn.py with `spconv` bound to `spconv_module`."""
+    import_ref_models()
+    sp = types.ModuleType("spconv")
+    for n in ("SparseConvTensor", "SubMConv3d", "SparseConv3d", "SparseSequential", "SparseModule"):
+        setattr(sp, n, getattr(spconv_module, n))
+    sys.modules["spconv"] = sp
+    spec = importlib.util.spec_from_file_location("det3d.models.backbones.scn_ref", REF + "/det3d/models/backbones/scn.py")
+    scn = importlib.util.module_from_spec(spec)
+    scn.__package__ = "det3d.models.backbones"
+    sys.modules[spec.name] = scn
+    spec.loader.exec_module(scn)
+    return scn
+
+
+BACKBONE_GRID = [96, 80, 40]       # (x, y, z): z as in the configs (41 -> 21 -> 11 -> 5 -> 2), x / y reduced
+
+
+def gen_backbone():
+    """Reference scn.py forward (eval mode) over the CPU spconv shim."""
+    from oracle import spconv_shim
+    scn = load_ref_scn(spconv_shim)
+    torch.manual_seed(3)
+    gen = torch.Generator().manual_seed(5)
+    from oracle.spconv_ref import seeded_state
+    bb = scn.SpMiddleResNetFHD(num_input_features=5, ds_factor=8)
+    bb.load_state_dict(seeded_state(bb, 33))        # the fixture stores the seed, not 11 MB of weights
+    bb.eval()
+    rng = np.random.default_rng(11)
+    gx, gy, gz = BACKBONE_GRID
+    B = 2
+    coors = []
+    for b in range(B):
+        n = 2600 - 700 * b
+        # clustered occupancy (objects + ground), unique cells, arbitrary (non-sorted) order as the voxelizer emits
+        cz = np.clip(rng.normal(12, 7, n), 0, gz - 1).astype(np.int64)
+        cy = np.clip(rng.normal(gy / 2, gy / 4, n), 0, gy - 1).astype(np.int64)
+        cx = np.clip(rng.normal(gx / 2, gx / 4, n), 0, gx - 1).astype(np.int64)
+        lin = np.unique((cz * gy + cy) * gx + cx)
+        rng.shuffle(lin)
+        c = np.stack([np.full(len(lin), b), lin // (gy * gx), (lin // gx) % gy, lin % gx], 1)
+        coors.append(c)
+    coors = np.concatenate(coors).astype(np.int32)
+    feats = torch.from_numpy(rng.normal(0, 1, (len(coors), 5)).astype(np.float32))
+    with torch.no_grad():
+        out, stages = bb(feats, torch.from_numpy(coors), B, BACKBONE_GRID)
+    torch.save(dict(grid=BACKBONE_GRID, batch_size=B, features=feats, coors=torch.from_numpy(coors), state_seed=33,
+                    state_shapes={k: tuple(v.shape) for k, v in bb.state_dict().items()}, out=out,
+                    stages={k: dict(features=v.features.clone() if k == "conv4" else None,
+                                    feature_sum=v.features.double().sum(0).float(),
+                                    indices=torch.as_tensor(np.asarray(v.indices)).clone(),
+                                    spatial_shape=list(v.spatial_shape)) for k, v in stages.items()}),
+               os.path.join(OUT, "backbone_scn.pt"))
+    print("backbone_scn: %d voxels -> out %s, stage rows %s" % (len(coors), tuple(out.shape),
+                                                              {k: len(v.features) for k, v in stages.items()}))
+
+
+def gen_head_variants(M):
+    """Reference CenterHead in the dense + forecast_feature (+ bev_map) modes of the n3dtf / n3dtfm configs."""
+    out = {}
+    for name, bev in (("n3dtf", False), ("n3dtfm", True)):
+        torch.manual_seed(21)
+        gen = torch.Generator().manual_seed(22)
+        cfg = dict(HEAD_CFG, dense=True, forecast_feature=True, bev_map=bev)
+        from oracle.spconv_ref import seeded_state
+        head = M.build_head(dict(cfg))
+        sd = seeded_state(head, 44)
+        for k in sd:
+            if k.endswith("hm.3.bias"):
+                sd[k] = sd[k] - 2.19
+        head.load_state_dict(sd)
+        head.eval()
+        x = torch.randn((2, 32, 12, 10), generator=gen)
+        bm = torch.rand((2, 6, 12, 10), generator=gen) if bev else None
+        with torch.no_grad():
+            preds = head(x, bm)
+            example = make_targets(2, 12, 10, 3, gen)
+            loss = head.loss(example, [{k: v.clone() for k, v in p.items()} for p in preds])
+        out[name] = dict(cfg=cfg, state_seed=44, state_shapes={k: tuple(v.shape) for k, v in head.state_dict().items()},
+                         x=x, bev_map=bm,
+                         preds=[{k: v.clone() for k, v in p.items()} for p in preds], example=example,
+                         loss={k: [t.detach() if torch.is_tensor(t) else t for t in v] if isinstance(v, list) else v
+                               for k, v in loss.items()})
+        print("head %s: %d tasks, keys %s, loss %s" % (name, len(preds), sorted(preds[0]), [float(l) for l in loss["loss"]]))
+    # dense-mode predict (center_head.py:606-607,693-713): every task decoded + NMS-ed on its own, labels offset per task
+    from det3d.core import box_torch_ops
+    from oracle import predict_ref as PR
+    box_torch_ops.rotate_nms_pcdet = lambda boxes, scores, thresh, pre_maxsize=None, post_max_size=None: \
+        PR.rotate_nms_ref(boxes, scores, thresh, pre_maxsize, post_max_size, PR.nms_np)
+    AttrDict = sys.modules["addict"].Dict
+    head = M.build_head(dict(HEAD_CFG, dense=True, forecast_feature=True))
+    tasks = [PR.synth_preds(2, 36, 44, 1, seed=50 + t, n_obj=10) for t in range(3)]
+    ret = head.predict({}, [{k: v.clone() for k, v in p.items()} for p in tasks], AttrDict(TEST_CFG))
+    out["dense_predict"] = dict(test_cfg=TEST_CFG, preds=tasks,
+                                ret=[{k: v for k, v in r.items() if k != "metadata"} for r in ret])
+    print("dense predict: %s boxes per sample" % [len(r["scores"]) for r in ret])
+    torch.save(out, os.path.join(OUT, "head_variants.pt"))
+
+
 def gen_state_keys():
     import json
     M = import_ref_models()
@@ -300,6 +406,12 @@ def gen_state_keys():
     for name, T in (("head_n0", 1), ("head_n3", 7)):
         head = M.build_head(dict(HEAD_CFG, in_channels=512, timesteps=T))
         out[name] = {k: list(v.shape) for k, v in head.state_dict().items()}
+    for name, flags in (("head_n3dtf", dict(dense=True, forecast_feature=True)),
+                        ("head_n3dtfm", dict(dense=True, forecast_feature=True, bev_map=True)),
+                        ("head_two_stage", dict(two_stage=True)), ("head_wide", dict(wide_head=True)),
+                        ("head_classify", dict(classify=True)), ("head_sparse", dict(sparse=True))):
+        head = M.build_head(dict(HEAD_CFG, in_channels=512, timesteps=7, **flags))
+        out[name] = {k: list(v.shape) for k, v in head.state_dict().items()}
     json.dump(out, open(os.path.join(OUT, "state_keys.json"), "w"), indent=0, sort_keys=True)
     print("state keys:", {k: len(v) for k, v in out.items()})
 
@@ -311,6 +423,12 @@ def main():
         return
     if "assign" in sys.argv[1:]:
         gen_assign()
+        return
+    if "backbone" in sys.argv[1:]:
+        gen_backbone()
+        return
+    if "variants" in sys.argv[1:]:
+        gen_head_variants(import_ref_models())
         return
     if "loader" in sys.argv[1:]:
         gen_loader()
@@ -360,6 +478,8 @@ def main():
     gen_predict(M)
     gen_loader()
     gen_assign()
+    gen_head_variants(M)
+    gen_backbone()
     gen_state_keys()
 
 

@@ -23,6 +23,34 @@ import torch
 import torch.nn.functional as F
 
 
+def seeded_state(module_or_shapes, seed):
+    """Deterministic state_dict for golden fixtures that store a seed instead of megabytes of weights: every tensor is
+    drawn from one seeded generator in sorted key order (weights ~ U(-b, b) with b = 1/sqrt(fan_in); BatchNorm
+    weight in [0.5, 1.5), bias / running_mean ~ 0.1 N(0,1), running_var in [0.5, 1.5))."""
+    shapes = module_or_shapes if isinstance(module_or_shapes, dict) else \
+        {k: tuple(v.shape) for k, v in module_or_shapes.state_dict().items()}
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        leaf = k.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            sd[k] = torch.zeros(shp, dtype=torch.int64)
+        elif leaf == "running_var" or (leaf == "weight" and len(shp) == 1):
+            sd[k] = torch.rand(shp, generator=g) + 0.5
+        elif leaf in ("running_mean", "bias"):
+            sd[k] = torch.randn(shp, generator=g) * 0.1
+        else:
+            n = 1
+            for d in shp:
+                n *= d
+            # conv weights: [kD,kH,kW,Cin,Cout] (spconv) or [Cout,Cin,kh,kw] (torch) -> fan_in = numel / Cout
+            cout = shp[-1] if len(shp) == 5 else shp[0]
+            b = 1.0 / max(n // max(cout, 1), 1) ** 0.5
+            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * b
+    return sd
+
+
 def _lin(coords, shape):
     c = coords.astype(np.int64)
     return ((c[:, 0] * shape[0] + c[:, 1]) * shape[1] + c[:, 2]) * shape[2] + c[:, 3]

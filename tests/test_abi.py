@@ -125,6 +125,52 @@ def test_state_dict_keys_match_reference_golden(golden_dir):
 
 def test_unsupported_variants_raise():
     import futuredet_b200 as fb
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):          # deformable convolution is outside the hot-path scope
         fb.build_head(dict(type="CenterHead", in_channels=32, tasks=[dict(num_class=1, class_names=["car"])],
-                           code_weights=[1.0] * 10, common_heads={"reg": (2, 2)}, dense=True, classify=False))
+                           code_weights=[1.0] * 10, common_heads={"reg": (2, 2)}, dcn_head=True, classify=False))
+
+
+REF_CFG_DIR = "/root/reference/configs/centerpoint"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG_DIR), reason="the reference tree exists only in the build container")
+def test_every_reference_voxelnet_config_loads_and_builds():
+    """The shipped configs load UNCHANGED through Config.fromfile and build through the registry: all 8 VoxelNet
+    configs (n0 / n3 / n3dtf / n3dtfm, car and pedestrian).  The 2 PointPillars configs are out of scope."""
+    import glob
+    import futuredet_b200 as fb
+    paths = sorted(glob.glob(os.path.join(REF_CFG_DIR, "*.py")))
+    vox = [p for p in paths if "_pp_" not in os.path.basename(p)]
+    assert len(vox) == 8
+    for p in vox:
+        cfg = fb.Config.fromfile(p)
+        assert cfg.model.type == "VoxelNet"
+        model = fb.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+        h = model.bbox_head
+        name = os.path.basename(p)
+        assert h.dense == ("n3dtf" in name) and h.forecast_feature == ("n3dtf" in name) and h.bev_map == ("n3dtfm" in name)
+        assert len(h.tasks) == (7 if "n3dtf" in name else 1)
+        assert model.precision is None and fb.default_precision() == "bf16x3"
+
+
+def test_precision_api():
+    import futuredet_b200 as fb
+    from futuredet_b200 import precision as P
+    assert fb.default_precision() == "bf16x3"                  # the tensor-core arm is the product default
+    with fb.use_precision("fp32"):
+        assert P.resolve(None) == "fp32" and P.act_fmt() == "fp32" and P.resolve("bf16x3") == "bf16x3"
+    assert P.resolve(None) == "bf16x3" and P.act_fmt() == "split"
+    with pytest.raises(ValueError):
+        P.check("fp16")
+    head = dict(type="CenterHead", in_channels=32, tasks=[dict(num_class=1, class_names=["car"])],
+                code_weights=[1.0] * 10, common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2),
+                                                       "vel": (2, 2)}, classify=False)
+    cfg = dict(type="VoxelNet", pretrained=None, reader=dict(type="VoxelFeatureExtractorV3", num_input_features=5),
+               backbone=dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8),
+               neck=dict(type="RPN", layer_nums=[1, 1], ds_layer_strides=[1, 2], ds_num_filters=[8, 16],
+                         us_layer_strides=[1, 2], us_num_filters=[16, 16], num_input_features=256), bbox_head=head)
+    m = fb.build_detector(cfg, test_cfg=dict(precision="fp32"))
+    assert m.precision == "fp32" and m.neck.precision == "fp32" and m.bbox_head.tasks[0].precision == "fp32"
+    assert all(c.precision == "fp32" for c in m.backbone.modules() if hasattr(c, "indice_key"))
+    m.set_precision(None)
+    assert m.neck.precision is None and m.backbone.conv_input[0].precision is None

@@ -26,6 +26,12 @@ def test_state_dict_layout_matches_reference_modules(golden_dir):
     assert shapes(neck) == want["neck"]
     assert shapes(fb.build_head(dict(HEAD, timesteps=1))) == want["head_n0"]
     assert shapes(fb.build_head(dict(HEAD, timesteps=7))) == want["head_n3"]
+    # head variants of the n3dtf / n3dtfm configs and the remaining flag combinations (center_head.py:99-126,320-372)
+    for name, flags in (("head_n3dtf", dict(dense=True, forecast_feature=True)),
+                        ("head_n3dtfm", dict(dense=True, forecast_feature=True, bev_map=True)),
+                        ("head_two_stage", dict(two_stage=True)), ("head_wide", dict(wide_head=True)),
+                        ("head_classify", dict(classify=True)), ("head_sparse", dict(sparse=True))):
+        assert shapes(fb.build_head(dict(HEAD, timesteps=7, **{**dict(classify=False), **flags}))) == want[name], name
     # spconv-1.x weight layout [kD, kH, kW, Cin, Cout] and the 2*timesteps velocity channels of the n3 head
     assert want["backbone"]["conv2.0.weight"] == [3, 3, 3, 16, 32]
     assert want["head_n3"]["tasks.0.vel.3.weight"] == [14, 64, 3, 3]

@@ -17,12 +17,9 @@ def scene_tensors(seed, n, dev):
 
 
 def test_graphed_forward_matches_eager(cuda):
-    from futuredet_b200 import neck, sparse
     from test_gpu_train import build_model
-    old = (sparse.DEFAULT_PRECISION, neck.DEFAULT_PRECISION)
-    sparse.DEFAULT_PRECISION = neck.DEFAULT_PRECISION = "bf16x3"
-    try:
-        model = build_model(1, cuda).to(cuda).eval()
+    if True:
+        model = build_model(1, cuda).to(cuda).eval().set_precision("bf16x3")
         model.configure_voxelizer(VOX)
         gf = graphs.GraphedForward(model, max_points=40000, batch_size=1)
         for seed, n in ((0, 30000), (1, 36000), (2, 20000)):          # one graph, three different clouds (growing and shrinking)
@@ -32,8 +29,6 @@ def test_graphed_forward_matches_eager(cuda):
             got = gf(pts, off)[0]
             for k in want:
                 assert torch.equal(got[k], want[k]), (seed, k)
-    finally:
-        sparse.DEFAULT_PRECISION, neck.DEFAULT_PRECISION = old
 
 
 def test_graphed_train_step_matches_eager(cuda):

@@ -28,11 +28,8 @@ def randomise_bn(module, seed):
 
 @pytest.fixture(params=["fp32", "bf16x3"])
 def precision(request):
-    from futuredet_b200 import neck, sparse
-    old = (sparse.DEFAULT_PRECISION, neck.DEFAULT_PRECISION)
-    sparse.DEFAULT_PRECISION = neck.DEFAULT_PRECISION = request.param
-    yield request.param
-    sparse.DEFAULT_PRECISION, neck.DEFAULT_PRECISION = old
+    with fb.use_precision(request.param):
+        yield request.param
 
 
 def test_rpn_and_center_head_match_reference_golden(cuda, golden_dir, precision):

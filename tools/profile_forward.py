@@ -7,13 +7,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from futuredet_b200 import neck, sparse  # noqa: E402
 from futuredet_b200.synth import synth_scene  # noqa: E402
 
 prec = os.environ.get("FD_PRECISION", "bf16x3")
-sparse.DEFAULT_PRECISION = neck.DEFAULT_PRECISION = prec
 dev = torch.device("cuda:0")
-model = bench.build_model().to(dev).configure_voxelizer(bench.VOXEL_CFG)
+model = bench.build_model().set_precision(prec).to(dev).configure_voxelizer(bench.VOXEL_CFG)
 nb = int(os.environ.get("FD_BATCH", "1"))
 scenes = [synth_scene(bench.N_TARGET, seed=i) for i in range(nb)]
 pts = torch.from_numpy(np.concatenate(scenes)).to(dev)
