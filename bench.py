@@ -9,7 +9,8 @@ batch of synthetic scenes (BASELINE.json configs[1]: forecast_n0 CenterPoint-Vox
 (the path shards by scene, no data-path collective) and rank 0 prints ONE JSON line.
 
 `--impl reference` times the reference's CPU path restated in oracle/ (the reference is Python: numba
-voxelizer, external spconv, torch neck/head -- nothing compiles into oracle/_ref) with all host threads.
+voxelizer, external spconv, torch neck/head -- nothing compiles into oracle/_ref) with all host threads, one FULL
+scene per step.
 """
 import argparse
 import json
@@ -164,43 +165,50 @@ def cpu_time_scene(sd, n_target, seed=0):
     return time.perf_counter() - t, len(scene)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms must use the box's cores regardless."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
 def run_reference(args, rank, world):
-    """--impl reference: rank 0 only; bounded sample per step so the run ends within a few minutes."""
+    """--impl reference: the reference's CPU path on the box's host cores, rank 0 only.  Every step is ONE FULL
+    305k-point scene (never sub-sampled or scaled); if the requested K steps would not fit the time budget, fewer
+    steps are timed and `steps` says how many.  The reference itself cannot travel to the GPU box (/root/reference
+    is absent there, its sources may not be copied) and it is Python over numba / external spconv / torch: the arm is
+    the oracle port (kind "port"): C restatement of the numba voxelizer, restated spconv-CPU indice_conv, and the same
+    torch.nn.functional conv2d / batch_norm calls the reference RPN / CenterHead modules make."""
     if rank != 0:
         return
+    cores = use_all_host_threads()
     model = build_model()
     sd = {k: v.clone() for k, v in model.state_dict().items()}
-    full_pts = len(synth_scene(N_TARGET, seed=0))
-    budget_s = 170.0
-    if os.environ.get("FD_REF_N_TARGET"):          # test hook: tiny scene
-        n_target = int(os.environ["FD_REF_N_TARGET"])
-        frac = max(N_TARGET // n_target, 1)
-    else:
-        # probe with a 1/8 scene to size the per-step sample
-        t_probe, n_probe = cpu_time_scene(sd, N_TARGET // 8, seed=99)
-        est_full = t_probe * 8
-        frac = 1
-        while frac < 8 and est_full / frac * (args.steps + args.warmup) > budget_s:
-            frac *= 2
-        n_target = N_TARGET // frac
-    for w in range(args.warmup):
-        cpu_time_scene(sd, n_target, seed=1000 + w)
-    t_total, pts_total = 0.0, 0
-    for s in range(args.steps):
-        t, n = cpu_time_scene(sd, n_target, seed=s)
+    n_target = int(os.environ.get("FD_REF_N_TARGET", N_TARGET))          # test hook: tiny scene
+    budget_s = float(os.environ.get("FD_REF_BUDGET_S", 200.0))
+    t_first, n_pts = cpu_time_scene(sd, n_target, seed=1000)             # warm-up step 0 doubles as the probe
+    warm = max(0, min(args.warmup - 1, int(budget_s * 0.25 / max(t_first, 1e-6))))
+    for w in range(warm):
+        cpu_time_scene(sd, n_target, seed=1001 + w)
+    steps = max(1, min(args.steps, int(budget_s * 0.75 / max(t_first, 1e-6))))
+    t_total = 0.0
+    for s_ in range(steps):
+        t, n_pts = cpu_time_scene(sd, n_target, seed=s_)
         t_total += t
-        pts_total += n
-    scenes_equiv = pts_total / full_pts
-    value = scenes_equiv / t_total
-    cores = torch.get_num_threads()
-    sample = ("%d step(s) of one synth_scene(%d) (%d pts; 1/%d of the 305,677-pt scene, scaled by points) through the "
-              "oracle port: C voxelizer (1 thread) + restated spconv-CPU + torch RPN/CenterHead"
-              % (args.steps, n_target, pts_total // max(args.steps, 1), frac))
-    line = dict(metric=METRIC, value=value, unit="scenes/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * t_total / max(args.steps, 1), higher_is_better=True, scaling="weak", vs_baseline=None,
+    value = steps / t_total
+    sample = ("%d timed step(s) (of %d requested; %d warm-up) of one FULL synth_scene(%d) (%d pts) each through the oracle "
+              "port: C voxelizer (1 thread) + restated spconv-CPU + torch RPN/CenterHead (%d threads)"
+              % (steps, args.steps, warm + 1, n_target, n_pts, cores))
+    line = dict(metric=METRIC, value=value, unit="scenes/s", n_gpus=args.gpus, steps=steps, warmup=warm + 1,
+                ms_per_step=1e3 * t_total / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="forecast_n0 CenterPoint-VoxelNet car, fwd-only, CPU reference path", batch=1,
-                            points_per_scene=full_pts, host_cpus=os.cpu_count()),
+                config=dict(workload="forecast_n0 CenterPoint-VoxelNet car, fwd-only (BASELINE configs[1])", batch_per_gpu=1,
+                            points_per_scene=n_pts, sweeps=10, max_voxels=160000, host_cpus=os.cpu_count(),
+                            note="CPU reference path; one full scene per step"),
                 cpu_baseline=dict(value=value, unit="scenes/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="scenes/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -256,34 +264,95 @@ def voxelize_roofline(model, dev, n_scenes=32):
                 algorithmic_bytes=nbytes, ms=ms, points=int(pts.shape[0]), voxels=m, peak_source=pk["src"] + " HBM copy")
 
 
+def cudnn_bar(model, dev, B):
+    """the bar for the dense neck + head is cuDNN-via-torch on the same box.  The model's own torch modules
+    (nn.Conv2d / BatchNorm2d / ReLU parameter containers of RPN and CenterHead, identical weights) are run through torch's
+    module forward (rpn.py:150-159, center_head.py:375-390) on a [B,256,180,180] BEV map, channels_last, TF32 off / on and
+    bf16 autocast, against the native dense kernels on the same input (CUDA events, 3 warm-up + 5 timed)."""
+    import torch.nn.functional as F  # noqa: F401
+    neck, head = model.neck, model.bbox_head
+    x = torch.randn((B, 256, 180, 180), device=dev).contiguous(memory_format=torch.channels_last)
+
+    def torch_fwd(inp):
+        ups, h = [], inp
+        for i, blk in enumerate(neck.blocks):
+            h = blk(h)
+            j = i - neck._upsample_start_idx
+            if j >= 0:
+                ups.append(neck.deblocks[j](h))
+        f = torch.cat(ups, dim=1) if ups else h
+        s_ = head.shared_conv(f)
+        return [{hn: getattr(t, hn)(s_) for hn in t.heads} for t in head.tasks]
+
+    def native_fwd(inp):
+        return head(neck(inp, out_fmt="split" if model.precision != "fp32" else "fp32"))
+
+    def time_it(fn, inp):
+        for _ in range(3):
+            fn(inp)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn(inp)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+
+    out = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for name, tf32 in (("cudnn_fp32_ms", False), ("cudnn_tf32_ms", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            out[name] = time_it(torch_fwd, x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out["cudnn_bf16_autocast_ms"] = time_it(torch_fwd, x)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    out["native_ms"] = time_it(native_fwd, x)
+    out["batch"] = B
+    out["what"] = ("RPN + CenterHead (n0) on a [B,256,180,180] map: torch module forward (cuDNN, channels_last, "
+                   "cudnn.benchmark) vs the native dense kernels (%s); fp32-class accuracy: native and cudnn_fp32; "
+                   "TF32 / bf16 autocast do not hold the 1e-3 contract over the whole network" % model.precision)
+    return out
+
+
 def train_bench(args, rank, world, dev):
-    """BASELINE configs[2]/[3]: forecast_n3 (7-timestep heads) forward + backward (+ AdamW step) per sample, one
-    305k-point scene per GPU per step; for world > 1 the parameter gradients are all-reduced over NCCL (bucketed,
-    overlapped with backward: shard.GradSync).  Auxiliary measurement, reported under "train" in the JSON line."""
+    """BASELINE configs[2]/[3]: forecast_n3 (7-timestep heads) forward + backward (+ AdamW step).  configs[2] (one GPU):
+    a single 305k-point sample per step; configs[3] (N GPUs): 4 samples per GPU per step (batch 32 at 8 GPUs,
+    det3d/torchie/apis/train.py:311-317, build_loader.py:35-36) with the parameter gradients all-reduced over NCCL.
+    The whole step (forward, backward and the bucket all-reduces) is captured into ONE CUDA graph per rank -- the NCCL
+    kernels are graph nodes, so a replayed step runs no Python (the eager multi-rank step was host-bound: 8 launch-heavy
+    ranks on 32 vCPUs took 70 ms at N=8 in round 1).  Auxiliary measurement, reported under "train" in the JSON line."""
     import futuredet_b200 as fb
     from futuredet_b200 import lib, shard, train
     from futuredet_b200.synth import synth_targets
     torch.manual_seed(0)
+    cores = shard.pin_rank_to_cores(dev.index, world) if world > 1 else None
     m = fb.build_detector(model_cfg(timesteps=7)).to(dev).train()
     m.configure_voxelizer(VOXEL_CFG, training=True)
     shard.broadcast_parameters(m)
     tr = train.NativeTrainer(m, precision=args.train_precision)
-    sync = shard.GradSync(tr.grads)
+    use_graph = not args.train_eager
+    sync = shard.GradSync(tr.grads, inline=use_graph)
     opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
-    B = 1
-    scene = synth_scene(N_TARGET, seed=shard.scene_seed(rank, 7, 0, B))
-    pts = torch.from_numpy(scene).to(dev)
-    off = torch.tensor([0, len(scene)], dtype=torch.int32, device=dev)
+    B = args.train_batch if args.train_batch > 0 else (4 if world > 1 else 1)
+    scenes = [synth_scene(N_TARGET, seed=shard.scene_seed(rank, 7, b, B)) for b in range(B)]
+    pts = torch.from_numpy(np.concatenate(scenes)).to(dev)
+    off = torch.tensor(np.r_[0, np.cumsum([len(sc) for sc in scenes])], dtype=torch.int32, device=dev)
     ex = synth_targets(B, 180, 180, 7, seed=rank)
     ex = {k: [[t.to(dev) for t in ts] for ts in v] for k, v in ex.items()}
     losses = None
-
-    # single rank: the sync-free step (764 launches) is replayed as ONE CUDA graph; several ranks keep the eager step so
-    # that the bucket all-reduces interleave with backward
-    graphed = None
-    if world == 1 and not args.train_eager:
+    graphed, graph_note = None, ""
+    if use_graph:
         from futuredet_b200 import graphs
-        graphed = graphs.GraphedTrainStep(tr, max_points=pts.shape[0], batch_size=B)
+        try:
+            graphed = graphs.GraphedTrainStep(tr, max_points=pts.shape[0], batch_size=B).capture(ex, pts, off)
+        except Exception as e:          # e.g. an NCCL build that refuses capture: keep measuring, say so
+            graphed, graph_note = None, "graph capture failed (%s: %s); eager step" % (type(e).__name__, str(e)[:120])
+            sync.inline = False
 
     def step():
         nonlocal losses
@@ -311,15 +380,18 @@ def train_bench(args, rank, world, dev):
     clocks = sampler.stop() if sampler else None
     ms = barrier_max(e0.elapsed_time(e1), world, dev) / args.train_steps
     loss = float(sum(losses["loss"]))
-    return dict(workload="forecast_n3 (7-timestep heads) car, fwd+bwd+AdamW, 1 x 305k-pt scene per GPU per step "
-                         "(BASELINE configs[2]; configs[3] for n_gpus > 1)", ms_per_step=ms,
-                samples_per_s=B * world / (ms / 1e3), precision=args.train_precision, steps=args.train_steps,
-                launch_mode="cuda graph replay" if graphed is not None else "eager",
+    grad_bytes = sum(b[0].numel() * 4 for b in tr.grads.buckets)
+    return dict(workload="forecast_n3 (7-timestep heads) car, fwd+bwd+AdamW, %d x 305k-pt scene(s) per GPU per step "
+                         "(BASELINE configs[%d]: global batch %d)" % (B, 2 if world == 1 else 3, B * world),
+                ms_per_step=ms, samples_per_s=B * world / (ms / 1e3), batch_per_gpu=B, global_batch=B * world,
+                precision=args.train_precision, steps=args.train_steps,
+                launch_mode=("cuda graph replay (NCCL all-reduce nodes inside the graph)" if world > 1 else
+                             "cuda graph replay") if graphed is not None else "eager", note=graph_note,
                 gpu_launches_per_step=(lib.launch_count() - n0) // args.train_steps, loss=loss,
-                params=sum(p.numel() for p in m.parameters()), clocks=clocks,
-                allreduce_bytes_per_step=sync.bytes_reduced // max(args.train_steps, 1),
-                exchange="bucketed all-reduce(sum)/world of the parameter gradients, %s" %
-                         ("NCCL over NVLink, overlapped with backward" if world > 1 else "single rank: none"))
+                params=sum(p.numel() for p in m.parameters()), clocks=clocks, cpu_affinity=cores,
+                allreduce_bytes_per_step=grad_bytes if world > 1 else 0,
+                exchange="bucketed all-reduce(avg) of the parameter gradients, %s" %
+                         ("NCCL over NVLink" if world > 1 else "single rank: none"))
 
 
 def run_gpu(args, rank, world, local):
@@ -399,6 +471,10 @@ def run_gpu(args, rank, world, local):
         ms_det, _ = timed(step_detect)
         prof = conv_profile(model, *pool_dev[0]) if rank == 0 else None
         vox_roof = voxelize_roofline(model, dev) if rank == 0 else None
+        # the reference's own samples_per_gpu = 1: latency-bound single-scene steps, same timing rules
+        one = [(p[:int(o[1])].contiguous(), o[:2].contiguous()) for p, o in pool_dev]
+        ms_b1, _ = timed(lambda i: (flush.zero_(), model.forward_points(*one[i % n_pool]))[1])
+        bar = cudnn_bar(model, dev, min(B, 4)) if rank == 0 and not args.no_cudnn_bar else None
     train_info = None
     if args.train_steps > 0:
         pool_dev.clear()
@@ -414,16 +490,21 @@ def run_gpu(args, rank, world, local):
     h2d = int(pool_host[0][0].numel() * 4 + pool_host[0][1].numel() * 4)
     d2h = int(sum(h.numel() for h in out_host) * 4)
     achieved = prof["flop"] / max(prof["ms"], 1e-9) / 1e9      # TFLOP/s
+    # dram bytes of the conv family from an ncu capture: only reported when a capture of THIS batch size is committed
     traffic = None
-    tpath = os.path.join(REPO, "profiles", "r1_traffic.json")      # dram bytes of the same kernels from one ncu capture
+    tpath = os.path.join(REPO, "profiles", "r2_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("conv_family_dram_bytes_per_step")
+        tj = json.load(open(tpath))
+        if tj.get("batch_per_gpu") == B and tj.get("precision") == args.precision:
+            traffic = tj.get("conv_family_dram_bytes_per_step")
     roofline = dict(bound="tensor", kernel="gather->implicit-GEMM conv family (%s), %d launches/step" %
                     (args.precision, prof["launches"]), achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s",
                     frac=achieved / pk["tf_sustained"], traffic=traffic, peak_source=pk["src"] + " bf16 dense, sustained",
                     algorithmic_gflop_per_step=prof["flop"] / 1e9, kernel_ms_per_step=prof["ms"], by_kind=prof["by_kind"])
+    cores = use_all_host_threads()
+    cpu_time_scene(sd_cpu, N_TARGET // 8, seed=1)                       # warm the thread pool / allocator
     cpu_t, cpu_n = cpu_time_scene(sd_cpu, N_TARGET, seed=0)
-    cpu_baseline = dict(value=1.0 / cpu_t, unit="scenes/s", cores=torch.get_num_threads(), kind="port",
+    cpu_baseline = dict(value=1.0 / cpu_t, unit="scenes/s", cores=cores, kind="port",
                         sample="1 synth_scene(%d) (%d pts) through the oracle port (C voxelizer + restated spconv-CPU + "
                                "torch RPN/CenterHead), %.1f s" % (N_TARGET, cpu_n, cpu_t), host_cpus=os.cpu_count())
     line = dict(metric=METRIC, value=value, unit="scenes/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -439,8 +520,12 @@ def run_gpu(args, rank, world, local):
                 detect=dict(value=scenes / (ms_det / 1e3), unit="scenes/s", ms_per_step=ms_det / args.steps,
                             what="host points -> H2D -> forward -> CenterHead.predict (decode + rotated NMS on device) -> "
                                  "detections D2H", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(det_bytes[0])),
+                batch1=dict(value=world * args.steps / (ms_b1 / 1e3), unit="scenes/s", ms_per_scene=ms_b1 / args.steps,
+                            what="one scene per step per GPU (the reference's samples_per_gpu), points resident"),
                 gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_voxelize=vox_roof,
                 cpu_baseline=cpu_baseline)
+    if bar is not None:
+        line["dense_bar"] = bar
     if train_info is not None:
         line["train"] = train_info
     print(json.dumps(line))
@@ -459,14 +544,15 @@ def main():
                     help="bf16x3 (default): tcgen05 tensor cores with a 3-term bf16 split, holds the 1e-3 parity contract; "
                          "fp32: CUDA-core exact arm; bf16: single pass, outside the parity contract")
     ap.add_argument("--train-steps", type=int, default=8, help="timed forecast_n3 fwd+bwd steps reported under 'train' (0: skip)")
+    ap.add_argument("--no-cudnn-bar", action="store_true", help="skip the cuDNN-via-torch neck+head comparison")
     ap.add_argument("--train-eager", action="store_true", help="do not replay the training step as a CUDA graph")
+    ap.add_argument("--train-batch", type=int, default=0,
+                    help="samples per GPU per training step (0: 1 on one GPU = configs[2], 4 on several = configs[3])")
     ap.add_argument("--train-precision", default="bf16x3", choices=["fp32", "bf16x3"],
                     help="forward / data-gradient convolutions of the training step (weight gradients are always fp32)")
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus, init=args.impl != "reference")
     if args.impl == "reference":
-        if args.steps > 3 and "--steps" not in sys.argv:
-            args.steps, args.warmup = 3, 1
         run_reference(args, rank, world)        # rank 0 alone; no process group needed
         return
     args.warmup = max(args.warmup, 3)

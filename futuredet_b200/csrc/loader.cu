@@ -81,12 +81,17 @@ sweep_emit_kernel(const SweepArgs a) {
     const float* p = a.raw + (size_t)i * a.raw_stride;
     float* o = a.out + (size_t)row * ostride;
     float x = p[0], y = p[1], z = p[2];
-    if (a.flags[s] & 1) {                              // float64 like numpy's matrix.dot(float32 points), stored as float32
+    if (a.flags[s] & 1) {
+      // float64 like numpy's `transform_matrix.dot(vstack(xyz, ones))` (loading.py:55-57), stored back as float32.
+      // numpy hands the [4,4]x[4,n] product to BLAS dgemm, whose micro-kernel accumulates over k = 0..3 with one FMA per
+      // term starting from zero: rn(T0*x), fma(T1,y,.), fma(T2,z,.), fma(T3,1,.) = rn(. + T3).  The explicit intrinsics
+      // pin exactly that order (a bare expression lets nvcc pick which product feeds the FMA, which flips the last
+      // float64 bit -- and now and then the float32 rounding -- of some coordinates).
       const double* T = a.xform + (size_t)s * 16;
       const double dx = x, dy = y, dz = z;
-      x = (float)(T[0] * dx + T[1] * dy + T[2] * dz + T[3]);
-      y = (float)(T[4] * dx + T[5] * dy + T[6] * dz + T[7]);
-      z = (float)(T[8] * dx + T[9] * dy + T[10] * dz + T[11]);
+      x = (float)__dadd_rn(__fma_rn(T[2], dz, __fma_rn(T[1], dy, __dmul_rn(T[0], dx))), T[3]);
+      y = (float)__dadd_rn(__fma_rn(T[6], dz, __fma_rn(T[5], dy, __dmul_rn(T[4], dx))), T[7]);
+      z = (float)__dadd_rn(__fma_rn(T[10], dz, __fma_rn(T[9], dy, __dmul_rn(T[8], dx))), T[11]);
     }
     o[0] = x; o[1] = y; o[2] = z;
     for (int c = 3; c < nf; ++c) o[c] = p[c];

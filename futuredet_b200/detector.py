@@ -76,6 +76,14 @@ class VoxelNet(SingleStageDetector):
             if p is not None:
                 self.set_precision(p)
 
+    def train(self, mode=True):
+        # derived-weight caches (folded BatchNorm, layout copies, tensor-core packs) are keyed on tensor versions, which
+        # a replayed CUDA-graph training step does not advance: drop them whenever the mode flips
+        if mode != self.training:
+            from .graphs import clear_weight_caches
+            clear_weight_caches(self)
+        return super().train(mode)
+
     def set_precision(self, p):
         """Arithmetic arm of every convolution of this detector: "bf16x3" (tensor cores, fp32-class results; the
         default), "fp32" (exact fp32 on CUDA cores) or "bf16" (single pass); None follows the process default."""

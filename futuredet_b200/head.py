@@ -93,7 +93,8 @@ class SepHead(nn.Module):
         firsts = [groups[h][0] for h in self.heads]
         key = tuple((c.weight.data_ptr(), c.weight._version, c.bias._version,
                      None if b is None else (b.weight._version, b.bias._version, b.running_mean._version,
-                                             b.running_var._version, b.training)) for c, b, _ in firsts)
+                                             b.running_var._version, b.training, getattr(b, "_fd_stats_version", 0)))
+                    for c, b, _ in firsts)
         cache = self.__dict__.setdefault("_fused_cache", {})
         if cache.get("k") != key:
             ws, scs, shs = [], [], []

@@ -236,7 +236,10 @@ def _prof_end(e0, kind, flops, launches=1):
     PROFILE.append(dict(kind=kind, start=e0, end=e1, flops=flops, launches=launches))
 
 
-_PACK_CACHE = {}
+import collections
+
+_PACK_CACHE = collections.OrderedDict()      # LRU: live layers are touched every pass, per-step temporaries age out
+_PACK_CACHE_MAX = 192
 
 
 def packed_weights(w, separate_offsets=False):
@@ -246,6 +249,7 @@ def packed_weights(w, separate_offsets=False):
     key = (w.data_ptr(), w._version, tuple(w.shape), bool(separate_offsets))
     hit = _PACK_CACHE.get(key)
     if hit is not None:
+        _PACK_CACHE.move_to_end(key)
         return hit[1]
     K, cin, cout = w.shape
     if separate_offsets:
@@ -257,8 +261,8 @@ def packed_weights(w, separate_offsets=False):
     else:
         buf = torch.empty((lib.fd_conv_packed_bytes(K, cin, cout),), dtype=torch.uint8, device=w.device)
         L.check(lib.fd_conv_pack_weights(_ptr(w), K, cin, cout, _ptr(buf), _stream()), "fd_conv_pack_weights")
-    if len(_PACK_CACHE) > 512:
-        _PACK_CACHE.clear()
+    while len(_PACK_CACHE) >= _PACK_CACHE_MAX:
+        _PACK_CACHE.popitem(last=False)          # evict the least recently used pack (and the weight it pins)
     _PACK_CACHE[key] = (w, buf)      # keep w alive so the data_ptr key cannot be recycled
     return buf
 

@@ -40,12 +40,18 @@ class GradSync:
     Gradients already live in flat buckets (train.GradBuckets), in the order backward finalises them, so there is no
     pack/unpack copy: as soon as the last gradient of a bucket is written its all-reduce is launched asynchronously
     (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests) and overlaps the rest of backward;
-    `finish()` waits for the outstanding reductions and applies the 1/world averaging in place.
+    `finish()` waits for the outstanding reductions.  On NCCL the averaging is part of the collective
+    (ReduceOp.AVG: no extra elementwise launch per bucket); gloo has no AVG, so the CPU tests scale after the wait.
+
+    `inline=True` (CUDA-graph capture of a multi-rank step): every bucket's all-reduce is enqueued synchronously on
+    the current stream the moment the bucket is final, so the NCCL kernels become nodes of the captured graph and a
+    replayed step involves no Python at all; nothing is left for finish() to wait for.
     """
 
-    def __init__(self, buckets, group=None):
-        self.buckets, self.group = buckets, group
+    def __init__(self, buckets, group=None, inline=False):
+        self.buckets, self.group, self.inline = buckets, group, inline
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.avg = self.world > 1 and dist.get_backend(group) == "nccl"
         self.handles = []
         self.bytes_reduced = 0
         buckets.on_bucket_ready = self._launch
@@ -53,14 +59,37 @@ class GradSync:
     def _launch(self, index, flat):
         if self.world == 1:
             return
-        self.handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
+        op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
+        if self.inline:
+            dist.all_reduce(flat, op=op, group=self.group)
+            if not self.avg:
+                flat.mul_(1.0 / self.world)
+        else:
+            self.handles.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
         self.bytes_reduced += flat.numel() * 4
 
     def finish(self):
         for h, flat in self.handles:
             h.wait()
-            flat.mul_(1.0 / self.world)
+            if not self.avg:
+                flat.mul_(1.0 / self.world)
         self.handles = []
+
+
+def pin_rank_to_cores(local_rank, local_world):
+    """Give every rank of a node its own slice of the host cores (8 launch-heavy Python processes plus NCCL proxy
+    threads sharing all cores migrate and contend; measured on the 8-GPU box).  Returns the cores or None."""
+    import os
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(local_world, 1)
+        if per < 1:
+            return None
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return None
 
 
 def broadcast_parameters(module, src=0, group=None):

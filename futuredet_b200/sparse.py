@@ -189,7 +189,9 @@ def folded_epilogue(conv, bn):
     if bn is None and bias is None:
         return None, None
     key = _versions(bias, *( (bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else ()))
-    key = (id(bn), bn.training if bn is not None else False) + key
+    # `_fd_stats_version`: bumped by the native train-mode BatchNorm, which updates the running statistics through raw
+    # pointers (tensor version counters do not see it)
+    key = (id(bn), bn.training if bn is not None else False, getattr(bn, "_fd_stats_version", 0)) + key
     cache = conv.__dict__.setdefault("_fold_cache", {})
     hit = cache.get("k")
     if hit == key:

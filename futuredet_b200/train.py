@@ -118,11 +118,21 @@ class GradBuckets:
                 if self.attach and (p.grad is None or p.grad.data_ptr() != view.data_ptr()):
                     p.grad = view
 
+    def has(self, p):
+        """False for frozen parameters (requires_grad=False): their gradient kernels are skipped."""
+        return id(p) in self.where
+
     def grad(self, p):
         return self.where[id(p)][1]
 
+    def scratch(self, p):
+        """Gradient destination of `p`: its bucket view, or a throw-away buffer when `p` is frozen."""
+        return self.where[id(p)][1] if id(p) in self.where else torch.empty_like(p, dtype=torch.float32)
+
     def done(self, p):
         """The gradient of `p` is final for this step."""
+        if id(p) not in self.where:
+            return
         b = self.where[id(p)][0]
         self.pending[b] -= 1
         if self.pending[b] == 0 and self.on_bucket_ready is not None:
@@ -168,9 +178,10 @@ def sparse_conv_train(tape, x, conv, xt, grads, prec):
         gy = y.grad
         if gy is None:
             return
-        T.sparse_conv_wgrad(xin, gy, rb, grads.grad(conv.weight).view(K, cin, cout), precision=prec)
-        grads.done(conv.weight)
-        if conv.bias is not None:
+        if grads.has(conv.weight):
+            T.sparse_conv_wgrad(xin, gy, rb, grads.grad(conv.weight).view(K, cin, cout), precision=prec)
+            grads.done(conv.weight)
+        if conv.bias is not None and grads.has(conv.bias):
             T.col_sum(gy, grads.grad(conv.bias), rb.n_out_dev, rb.n_out_cap)
             grads.done(conv.bias)
         if x.needs_grad:
@@ -199,8 +210,8 @@ def bn_train(tape, x, bn, grads, residual=None, relu=True, out=None):
         if gy is None:
             return
         want_res = residual is not None and residual.needs_grad
-        dx, dres = T.bn_backward(gy, y.t, relu, x.t, saved, bn.weight.detach(), grads.grad(bn.weight),
-                                 grads.grad(bn.bias), want_res, x.n_dev, x.n_cap)
+        dx, dres = T.bn_backward(gy, y.t, relu, x.t, saved, bn.weight.detach(), grads.scratch(bn.weight),
+                                 grads.scratch(bn.bias), want_res, x.n_dev, x.n_cap)
         grads.done(bn.weight)
         grads.done(bn.bias)
         x.accumulate(dx)
@@ -229,13 +240,14 @@ def conv2d_train(tape, x, conv, grads, prec, pad=None, out=None):
         gy = y.grad
         if gy is None:
             return
-        gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=w.device)
-        T.conv2d_wgrad(x.t, gy, gw, ksize, stride, padding, transposed, precision=prec)
-        g4 = gw.view(ksize[0], ksize[1], cin, cout)
-        # back to the parameter layout: Conv2d [Cout,Cin,kh,kw], ConvTranspose2d [Cin,Cout,kh,kw]
-        grads.grad(conv.weight).copy_(g4.permute(2, 3, 0, 1) if transposed else g4.permute(3, 2, 0, 1))
-        grads.done(conv.weight)
-        if conv.bias is not None:
+        if grads.has(conv.weight):
+            gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=w.device)
+            T.conv2d_wgrad(x.t, gy, gw, ksize, stride, padding, transposed, precision=prec)
+            g4 = gw.view(ksize[0], ksize[1], cin, cout)
+            # back to the parameter layout: Conv2d [Cout,Cin,kh,kw], ConvTranspose2d [Cin,Cout,kh,kw]
+            grads.grad(conv.weight).copy_(g4.permute(2, 3, 0, 1) if transposed else g4.permute(3, 2, 0, 1))
+            grads.done(conv.weight)
+        if conv.bias is not None and grads.has(conv.bias):
             T.col_sum(gy, grads.grad(conv.bias))
             grads.done(conv.bias)
         if x.needs_grad:

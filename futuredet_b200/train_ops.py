@@ -170,6 +170,8 @@ def bn_train_stats(x, bn, n_dev=None, n_cap=None):
                                _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
                                _ptr(s.mean), _ptr(s.invstd), _ptr(s.scale), _ptr(s.shift), _ptr(ws), _stream())
     L.check(rc, "fd_bn_train_stats")
+    # the running statistics were updated through raw pointers: invalidate eval-mode folded-BN caches keyed on them
+    bn.__dict__["_fd_stats_version"] = bn.__dict__.get("_fd_stats_version", 0) + 1
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return s
