@@ -252,6 +252,11 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, 
 __device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void* src, uint32_t sz) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+// same through L1 (.ca): gathered rows stay in the SM's L1 (the part of the 228 KB the CTA does not claim as shared
+// memory), where the neighbouring kernel offsets of the same tile find them again
+__device__ __forceinline__ void cp_async16_sz_ca(uint32_t dst, const void* src, uint32_t sz) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -376,6 +381,8 @@ struct TcArgs {
   int T;                     // M tiles per super-tile (weight reuse factor)
   int split;                 // 1: bf16x3, 0: single-pass bf16
   int dbg;                   // FD_TC_DEBUG ablation bits (perf triage only): 1 no A gather, 2 no MMA, 4 no B copy, 8 no stores
+  int sa;                    // A ring slots in use (<= TcCfg::SA); fewer slots leave more of the SM's 228 KB to L1
+  int l1;                    // 1: gather through L1 (cp.async.ca)
 };
 
 template <int NT> struct TcCfg {
@@ -420,7 +427,8 @@ template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const TcArgs t) {
   using Cfg = TcCfg<NT>;
-  constexpr int SA = Cfg::SA, SB = Cfg::SB;
+  constexpr int SB = Cfg::SB;
+  const int SA = t.sa;
   constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, NT);
   constexpr uint32_t IDESC2 = umma_idesc_bf16(TC_BM, Cfg::FUSE_N ? 2 * NT : NT);
   constexpr int ACC = Cfg::ACC_COLS;
@@ -588,11 +596,22 @@ conv_tc_kernel(const TcArgs t) {
           const char* gh = in_b + ch * 2;
           const char* gl = in_lo + ch * 2;
 #pragma unroll
-          for (int q = 0; q < PASSES; ++q) {
-            const uint32_t sz = cur[q] >= 0 ? 16u : 0u;
-            const size_t goff = (size_t)(uint32_t)max(cur[q], 0) * row_bytes;
-            cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB, gh + goff, sz);
-            cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB + TC_A_PLANE, gl + goff, sz);
+          if (t.l1) {
+#pragma unroll
+            for (int q = 0; q < PASSES; ++q) {
+              const uint32_t sz = cur[q] >= 0 ? 16u : 0u;
+              const size_t goff = (size_t)(uint32_t)max(cur[q], 0) * row_bytes;
+              cp_async16_sz_ca(dst0 + q * ROWS_PER_PASS * TC_ROWB, gh + goff, sz);
+              cp_async16_sz_ca(dst0 + q * ROWS_PER_PASS * TC_ROWB + TC_A_PLANE, gl + goff, sz);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < PASSES; ++q) {
+              const uint32_t sz = cur[q] >= 0 ? 16u : 0u;
+              const size_t goff = (size_t)(uint32_t)max(cur[q], 0) * row_bytes;
+              cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB, gh + goff, sz);
+              cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB + TC_A_PLANE, gl + goff, sz);
+            }
           }
           cp_async_mbar_arrive_noinc(fbar);
         } else {
@@ -841,13 +860,28 @@ conv_tc_kernel(const TcArgs t) {
 static int pick_nt(int cout) { return cout >= 128 ? 128 : cout >= 64 ? 64 : cout >= 32 ? 32 : 16; }
 static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 
+// perf-triage knobs, settable at run time through fd_debug_set_tc (not part of the documented ABI)
+static int g_dbg = -1;          // FD_TC_DEBUG bits
+static int g_sa_cap[2] = {0, 0};   // A-ring slot cap [sparse, dense] (0: all that fit)
+static int g_l1[2] = {0, 0};       // gather through L1 [sparse, dense]
+
 template <int NT>
 static int launch_tc(TcArgs& t, cudaStream_t stream) {
   using Cfg = TcCfg<NT>;
-  static bool configured = false;
-  if (!configured) {
+  static int configured_sa = 0;
+  const int cls = t.c.mode == FD_GATHER_TABLE ? 0 : 1;
+  int sa = Cfg::SA;
+  if (g_sa_cap[cls] > 0 && g_sa_cap[cls] < sa) sa = g_sa_cap[cls] < TC_GROUPS ? TC_GROUPS : g_sa_cap[cls];
+  t.sa = sa;
+  t.l1 = g_l1[cls];
+  const size_t smem = Cfg::SMEM - (size_t)(Cfg::SA - sa) * Cfg::A_BYTES;
+  if (configured_sa != sa) {
     FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    configured = true;
+    // shared-memory carve-out just large enough for this launch: the rest of the 228 KB is L1
+    int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;
+    if (pct > 100) pct = 100;
+    FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    configured_sa = sa;
   }
   // weight reuse factor: as many M tiles per weight fetch as TMEM allows while keeping >= one unit per SM
   const int tiles_m = ceil_div(t.c.n_cap, TC_BM);
@@ -856,7 +890,7 @@ static int launch_tc(TcArgs& t, cudaStream_t stream) {
   t.T = T;
   const int64_t units = (int64_t)ceil_div(tiles_m, T) * t.n_tiles_n;
   const int grid = units < kNumSMs ? (int)units : kNumSMs;   // persistent: one CTA per SM
-  conv_tc_kernel<NT><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(t);
+  conv_tc_kernel<NT><<<grid, TC_THREADS, smem, stream>>>(t);
   FD_LAUNCHED();
   return 0;
 }
@@ -881,7 +915,8 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
   t.ktot_pad = pad_to(a.K * a.cin, TC_BK);
   t.n_tiles_n = t.cout_pad / NT;
   t.split = precision == FD_PREC_BF16X3;
-  { static const int dbg = getenv("FD_TC_DEBUG") ? atoi(getenv("FD_TC_DEBUG")) : 0; t.dbg = dbg; }
+  if (g_dbg < 0) g_dbg = getenv("FD_TC_DEBUG") ? atoi(getenv("FD_TC_DEBUG")) : 0;
+  t.dbg = g_dbg;
   switch (NT) {
     case 128: return launch_tc<128>(t, stream);
     case 64: return launch_tc<64>(t, stream);
@@ -899,6 +934,19 @@ int fd_debug_read_tc_trace(long long* out, int role) {
   if (role < 0 || role >= 4) return -1;
   return (int)cudaMemcpyFromSymbol(out, fd::g_tc_trace, sizeof(long long) * fd::TC_TRACE_N,
                                    sizeof(long long) * fd::TC_TRACE_N * role, cudaMemcpyDeviceToHost);
+}
+
+/* perf-triage helper (not part of the documented ABI): key 0 = FD_TC_DEBUG bits, 1 / 2 = A-ring slot cap of the
+ * sparse / dense launches, 3 / 4 = gather through L1 for sparse / dense launches */
+int fd_debug_set_tc(int key, int value) {
+  switch (key) {
+    case 0: fd::g_dbg = value; return 0;
+    case 1: fd::g_sa_cap[0] = value; return 0;
+    case 2: fd::g_sa_cap[1] = value; return 0;
+    case 3: fd::g_l1[0] = value; return 0;
+    case 4: fd::g_l1[1] = value; return 0;
+  }
+  return -1;
 }
 
 size_t fd_conv_packed_bytes(int K, int cin, int cout) {

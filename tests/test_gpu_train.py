@@ -497,7 +497,7 @@ def test_reference_trainer_idiom_loss_backward(cuda):
     native backward through the autograd bridge and fills param.grad with the same gradients as NativeTrainer.step."""
     from oracle.gen_golden import make_targets
     rng = np.random.default_rng(4)
-    model = build_model(3, cuda).to(cuda).train()
+    model = build_model(3, cuda).to(cuda).train().set_precision("fp32")      # compared with the exact-fp32 trainer below
     B, grid = 1, [64, 64, 40]
     c = random_sites(rng, B, [40, 64, 64], 3000)
     n = len(c)
