@@ -21,6 +21,7 @@
 //               D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (3-term split, ~2^-16 relative error: fp32-class results
 //               on the bf16 tensor pipe); tcgen05.commit releases A / B slots and publishes the accumulators;
 //   warps 9-12  epilogue: tcgen05.ld, fused BN(eval)/bias, residual, ReLU, split once into bf16 hi/lo, store.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -262,6 +263,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// TMA gather: rows r0..r3 of the 2-D tensor (64 bf16 = 128 bytes each, starting at column `col`) -> 4 consecutive
+// 128-byte shared-memory rows at `dst`, swizzled by the hardware (SWIZZLE_128B); a row index outside the tensor
+// (the rulebook's -1) is filled with zeros and reads nothing; completion is counted in bytes on `bar`
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+// TMA tile load of a 4-D box {64 channels, bw, bh, 1} at (c, x, y, b); coordinates may lie outside the tensor
+// (negative / >= extent): those elements are zero-filled, which is exactly the convolution's zero padding
+__device__ __forceinline__ void tma_tile4d(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int b, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c), "r"(x), "r"(y), "r"(b), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -373,6 +390,9 @@ pack_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, int N
 }
 
 struct TcArgs {
+  // TMA descriptor of the input activation matrix viewed as a 2-D bf16 tensor [rows, hi plane | lo plane] with a
+  // {64 channels, 1 row} box and SWIZZLE_128B: the operand of cp.async.bulk.tensor...tile::gather4 (valid when tma)
+  alignas(64) CUtensorMap tmap;
   ConvArgs c;
   const __nv_bfloat16* wp;   // packed weights
   const uint32_t* tile_mask; // per 128-row tile: active kernel offsets (NULL: all)
@@ -383,6 +403,12 @@ struct TcArgs {
   int dbg;                   // FD_TC_DEBUG ablation bits (perf triage only): 1 no A gather, 2 no MMA, 4 no B copy, 8 no stores
   int sa;                    // A ring slots in use (<= TcCfg::SA); fewer slots leave more of the SM's 228 KB to L1
   int l1;                    // 1: gather through L1 (cp.async.ca)
+  int tma;                   // 0: per-thread cp.async gather; 1: TMA gather4 (wide split-bf16 inputs);
+                             // 2: dense 2-D stride-1 convs, TMA TILE loads: an M tile is a bw x bh pixel patch and
+                             //    every (tap, 64-channel chunk) stage is ONE 4-D box per plane, shifted by the tap,
+                             //    out-of-image pixels zero-filled by the copy engine (tmap is 4-D [B,H,W,C] then)
+  int bw, bh, tiles_x, tiles_y;   // tma == 2: patch shape and patches per image
+  int nbr_vec;               // rulebook rows may be read as int4 (16-byte aligned table)
 };
 
 template <int NT> struct TcCfg {
@@ -425,7 +451,7 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* v) {
 
 template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const TcArgs t) {
+conv_tc_kernel(const __grid_constant__ TcArgs t) {
   using Cfg = TcCfg<NT>;
   constexpr int SB = Cfg::SB;
   const int SA = t.sa;
@@ -453,7 +479,18 @@ conv_tc_kernel(const TcArgs t) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.d_n ? min(*a.d_n, a.n_cap) : a.n_cap;
   const int T = t.T;
-  const int n_tiles_m = (n + TC_BM - 1) / TC_BM;
+  const bool tiled = t.tma == 2;
+  const int tiles_img = t.tiles_x * t.tiles_y;
+  const int n_tiles_m = tiled ? (n / (a.Hout * a.Wout)) * tiles_img : (n + TC_BM - 1) / TC_BM;
+  // tiled mode: output pixel of accumulator row r of M tile tm (or -1: outside the patch / the image)
+  auto tile_row_to_o = [&](int tm, int r) -> int {
+    const int b = tm / tiles_img, rem = tm - b * tiles_img;
+    const int ty = rem / t.tiles_x, tx = rem - ty * t.tiles_x;
+    const int h = r / t.bw, w = r - h * t.bw;
+    const int oy = ty * t.bh + h, ox = tx * t.bw + w;
+    if (h >= t.bh || oy >= a.Hout || ox >= a.Wout) return -1;
+    return (b * a.Hout + oy) * a.Wout + ox;
+  };
   const int n_super = (n_tiles_m + T - 1) / T;
   const int n_units = n_super * t.n_tiles_n;
   const int ktot = a.K * a.cin;
@@ -468,7 +505,9 @@ conv_tc_kernel(const TcArgs t) {
   const bool ss_smem = t.cout_pad <= TC_SS_MAX;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), GT); mbar_init(smem_u32(&a_empty[s]), 1); }
+    // A stage complete: every thread of the filling group arrives (cp.async path) / one expect_tx arrival + the
+    // stage's bytes (TMA path)
+    for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), t.tma ? 1 : GT); mbar_init(smem_u32(&a_empty[s]), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 128); }
     fence_barrier_init();
@@ -508,7 +547,120 @@ conv_tc_kernel(const TcArgs t) {
     return gm ? gm : 1u;
   };
 
-  if (warp < TC_PRODUCER_WARPS) {
+  if (warp < TC_PRODUCER_WARPS && tiled) {
+    // ===================================== PRODUCER (dense 2-D, TMA tile loads) =====================================
+    // one elected thread: per A stage (M tile x tap x 64-channel chunk) two box loads (hi plane, lo plane)
+    if (warp == 0 && lane == 0) {
+      const uint32_t a_ring_u32 = smem_u32(a_ring);
+      const CUtensorMap* tmap = &t.tmap;
+      const uint32_t stage_bytes = (uint32_t)(2 * t.bw * t.bh * TC_ROWB);
+      uint32_t slot = 0, phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int st = unit / t.n_tiles_n;
+        const int live = min(T, n_tiles_m - st * T);
+        for (int k = 0; k < a.K; ++k) {
+          const int ky = k / a.kw, kx = k - ky * a.kw;
+          for (int sub = 0; sub < spo; ++sub) {
+            for (int ti = 0; ti < live; ++ti) {
+              const int tm = st * T + ti;
+              const int b = tm / tiles_img, rem = tm - b * tiles_img;
+              const int ty = rem / t.tiles_x, tx = rem - ty * t.tiles_x;
+              mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1, 2);
+              const uint32_t fbar = smem_u32(&a_full[slot]);
+              const uint32_t dst = a_ring_u32 + slot * Cfg::A_BYTES;
+              if (t.dbg & 1) {
+                mbar_arrive(fbar);
+              } else {
+                mbar_arrive_expect_tx(fbar, stage_bytes);
+                const int x0 = tx * t.bw - a.pw + kx, y0 = ty * t.bh - a.ph + ky;
+                tma_tile4d(dst, tmap, sub * TC_BK, x0, y0, b, fbar);
+                tma_tile4d(dst + TC_A_PLANE, tmap, a.in_ctot + sub * TC_BK, x0, y0, b, fbar);
+              }
+              if (++slot == (uint32_t)SA) { slot = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < TC_PRODUCER_WARPS && t.tma) {
+    // ===================================== PRODUCERS (A gather by TMA) =====================================
+    // One warp per group (warps 0..G-1); group g fills emitted A stages g, g+G, ... : lane l owns rows 4l..4l+3 of the
+    // 128-row tile, reads their four rulebook entries as one int4 (prefetched one owned stage ahead) and issues two
+    // gather4 copies (hi plane, lo plane).  The copy engine does the address generation, the swizzled shared-memory
+    // writes and the byte-counted arrival on the stage's mbarrier; the SM spends 2 instructions per stage and lane.
+    if (warp < G) {
+      const int grp = warp;
+      const uint32_t a_ring_u32 = smem_u32(a_ring), idx_u32 = smem_u32(s_idx);
+      const bool table = a.mode == FD_GATHER_TABLE;
+      const CUtensorMap* tmap = &t.tmap;
+      uint32_t c_base = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int st = unit / t.n_tiles_n;
+        const int live = min(T, n_tiles_m - st * T);
+        if (!table) {
+          named_bar_sync(1, G * 32);                       // every group is done reading the previous unit's indices
+          for (int e = threadIdx.x; e < live * a.K * TC_BM; e += G * 32) {
+            const int ti = e / (a.K * TC_BM), rem = e - ti * a.K * TC_BM;
+            const int k = rem >> 7, r = rem & (TC_BM - 1);
+            const int o = (st * T + ti) * TC_BM + r;
+            sts_u32(idx_u32 + (uint32_t)((ti * TC_DENSE_MAXK + k) * TC_BM + r) * 4, (uint32_t)(o < n ? gather_row(a, o, k) : -1));
+          }
+          named_bar_sync(1, G * 32);
+        }
+        const uint32_t gmask = unit_gmask(st);
+        const int n_emit = __popc(gmask) * spg * live;
+        int p = (int)((grp + G - (c_base % G)) % G);
+        uint32_t slot = (c_base + p) % SA, phase = ((c_base + p) / SA) & 1;
+        uint32_t rem = gmask;
+        int act_idx = 0;
+        int4 nxt = make_int4(-1, -1, -1, -1);
+        int col_n = 0;
+        auto fetch = [&](int pos) {
+          const int want = pos / live;
+          const int ti = pos - want * live;
+          const int gi = want / spg, sub = want - gi * spg;
+          while (act_idx < gi) { rem &= rem - 1; ++act_idx; }
+          const int kk = __ffs((int)rem) - 1;              // wide layers: one kernel offset per group of stages
+          col_n = sub * TC_BK;
+          const int row0 = (st * T + ti) * TC_BM + 4 * lane;
+          if (table) {
+            const int32_t* nrow = a.nbr + (size_t)kk * a.nbr_stride + row0;
+            if (row0 + 3 < n && t.nbr_vec) {
+              nxt = __ldg(reinterpret_cast<const int4*>(nrow));
+            } else {
+              nxt.x = row0 < n ? __ldg(nrow) : -1;
+              nxt.y = row0 + 1 < n ? __ldg(nrow + 1) : -1;
+              nxt.z = row0 + 2 < n ? __ldg(nrow + 2) : -1;
+              nxt.w = row0 + 3 < n ? __ldg(nrow + 3) : -1;
+            }
+          } else {
+            const uint32_t ib = idx_u32 + (uint32_t)((ti * TC_DENSE_MAXK + kk) * TC_BM + 4 * lane) * 4;
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(nxt.x), "=r"(nxt.y), "=r"(nxt.z), "=r"(nxt.w) : "r"(ib) : "memory");
+          }
+        };
+        if (p < n_emit) fetch(p);
+        for (; p < n_emit; p += G) {
+          const int4 cur = nxt;
+          const int col = col_n;
+          if (p + G < n_emit) fetch(p + G);
+          mbar_wait_warp(smem_u32(&a_empty[slot]), phase ^ 1, 2);
+          const uint32_t fbar = smem_u32(&a_full[slot]);
+          const uint32_t dst = a_ring_u32 + slot * Cfg::A_BYTES + lane * (4 * TC_ROWB);
+          slot += G;
+          while (slot >= (uint32_t)SA) { slot -= SA; phase ^= 1; }
+          if (t.dbg & 1) {                                   // triage: no data movement
+            if (lane == 0) mbar_arrive(fbar);
+            continue;
+          }
+          if (lane == 0) mbar_arrive_expect_tx(fbar, Cfg::A_BYTES);
+          __syncwarp();
+          tma_gather4(dst, tmap, col, cur.x, cur.y, cur.z, cur.w, fbar);
+          tma_gather4(dst + TC_A_PLANE, tmap, a.in_ctot + col, cur.x, cur.y, cur.z, cur.w, fbar);
+        }
+        c_base += (uint32_t)n_emit;
+      }
+    }
+  } else if (warp < TC_PRODUCER_WARPS) {
     // ===================================== PRODUCERS (A gather) =====================================
     // 4 groups of 64 threads; group g fills emitted A stages g, g+4, ... on its own, so several stages are being
     // issued concurrently, and the rulebook indices of a group's next stage are prefetched while it waits for a slot.
@@ -752,9 +904,9 @@ conv_tc_kernel(const TcArgs t) {
       if (threadIdx.x == (TC_MMA_WARP + 1) * 32) TC_TRACE(2, 2 * it, clock64());
       tc_fence_after();
       for (int ti = 0; ti < live; ++ti) {
-        const int o = (st * T + ti) * TC_BM + q * 32 + lane;
+        const int o = tiled ? tile_row_to_o(st * T + ti, q * 32 + lane) : (st * T + ti) * TC_BM + q * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + ti) * ACC);
-        const bool live_row = o < n;
+        const bool live_row = o >= 0 && o < n;
         OutRow orow{nullptr, 0, 1};
         if (live_row) orow = map_out_row(a, o);
         const float* res = (a.residual && live_row) ? a.residual + (size_t)o * a.res_stride : nullptr;
@@ -864,6 +1016,9 @@ static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 static int g_dbg = -1;          // FD_TC_DEBUG bits
 static int g_sa_cap[2] = {0, 0};   // A-ring slot cap [sparse, dense] (0: all that fit)
 static int g_l1[2] = {0, 0};       // gather through L1 [sparse, dense]
+static int g_tma = 0;              // TMA gather4 producer where the layer allows it (measured slower than the cp.async
+                                   // gather: ~6 cycles per 128-byte row in the copy engine vs ~4 through the LSU)
+static int g_tma_dense = 1;        // TMA tile loads for dense stride-1 2-D convolutions
 
 template <int NT>
 static int launch_tc(TcArgs& t, cudaStream_t stream) {
@@ -883,8 +1038,9 @@ static int launch_tc(TcArgs& t, cudaStream_t stream) {
     FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     configured_sa = sa;
   }
-  // weight reuse factor: as many M tiles per weight fetch as TMEM allows while keeping >= one unit per SM
-  const int tiles_m = ceil_div(t.c.n_cap, TC_BM);
+  // weight reuse factor: as many M tiles per weight fetch as TMEM allows while keeping >= one unit per SM (a cost model
+  // that also counted the wave tail picked smaller T and measured slower: the extra weight traffic outweighs the tail)
+  const int tiles_m = t.tma == 2 ? (t.c.n_cap / (t.c.Hout * t.c.Wout)) * t.tiles_x * t.tiles_y : ceil_div(t.c.n_cap, TC_BM);
   int T = Cfg::TMAX;
   while (T > 1 && (int64_t)ceil_div(tiles_m, T) * t.n_tiles_n < kNumSMs) T >>= 1;
   t.T = T;
@@ -917,6 +1073,53 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
   t.split = precision == FD_PREC_BF16X3;
   if (g_dbg < 0) g_dbg = getenv("FD_TC_DEBUG") ? atoi(getenv("FD_TC_DEBUG")) : 0;
   t.dbg = g_dbg;
+  // TMA gather for the A operand: wide layers (Cin a multiple of the 64-channel stage) reading split-bf16 rows
+  t.tma = 0;
+  t.nbr_vec = a.mode == FD_GATHER_TABLE && a.nbr_stride % 4 == 0 && (((uintptr_t)a.nbr) & 15) == 0;
+  if (g_tma && a.in_fmt == FD_FMT_SPLIT_BF16 && a.cin % TC_BK == 0 && TC_BK == 64 &&
+      (a.mode == FD_GATHER_TABLE || a.mode == FD_GATHER_CONV2D || a.mode == FD_GATHER_CONV2D_DGRAD) &&
+      ((size_t)a.in_stride * 4) % 16 == 0) {
+    // 2-D view: dim0 = bf16 columns of one row (hi plane, then the lo plane in_ctot further), dim1 = rows.  The row
+    // count only bounds the zero-filled "no neighbour" index -1: valid indices always point at real rows.
+    const cuuint64_t dims[2] = {(cuuint64_t)a.in_ctot + (cuuint64_t)a.cin, (cuuint64_t)1 << 30};
+    const cuuint64_t strides[1] = {(cuuint64_t)a.in_stride * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = cuTensorMapEncodeTiled(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.in, dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS)
+      return set_error((int)cr, "fd_conv_forward: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    t.tma = 1;
+  }
+  // dense stride-1 convolutions: TMA tile loads over the [B,H,W,C] activation tensor
+  if (g_tma_dense && a.in_fmt == FD_FMT_SPLIT_BF16 && a.cin % TC_BK == 0 && TC_BK == 64 && a.mode == FD_GATHER_CONV2D &&
+      a.sh == 1 && a.sw == 1 && ((size_t)a.in_stride * 4) % 16 == 0 && a.n_cap % (a.Hout * a.Wout) == 0) {
+    // patch shape bw x bh <= 128 rows with the fewest wasted accumulator rows
+    int bw = 1, bh = 1;
+    double best_util = -1.0;
+    for (int w = 1; w <= TC_BM && w <= a.Wout; ++w) {
+      int h = TC_BM / w;
+      if (h > a.Hout) h = a.Hout;
+      if (h < 1 || h > 256) continue;
+      const double util = (double)a.Hout * a.Wout / ((double)ceil_div(a.Wout, w) * ceil_div(a.Hout, h) * TC_BM);
+      if (util > best_util + 1e-9) { best_util = util; bw = w; bh = h; }
+    }
+    const int nb = a.n_cap / (a.Hout * a.Wout);
+    const cuuint64_t dims[4] = {(cuuint64_t)a.in_ctot + (cuuint64_t)a.cin, (cuuint64_t)a.Win, (cuuint64_t)a.Hin, (cuuint64_t)nb};
+    const cuuint64_t strides[3] = {(cuuint64_t)a.in_stride * 4, (cuuint64_t)a.in_stride * 4 * a.Win,
+                                   (cuuint64_t)a.in_stride * 4 * a.Win * a.Hin};
+    const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = cuTensorMapEncodeTiled(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.in, dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS)
+      return set_error((int)cr, "fd_conv_forward: cuTensorMapEncodeTiled (4-D) failed (%d)", (int)cr);
+    t.tma = 2;
+    t.bw = bw; t.bh = bh;
+    t.tiles_x = ceil_div(a.Wout, bw); t.tiles_y = ceil_div(a.Hout, bh);
+  }
   switch (NT) {
     case 128: return launch_tc<128>(t, stream);
     case 64: return launch_tc<64>(t, stream);
@@ -937,7 +1140,7 @@ int fd_debug_read_tc_trace(long long* out, int role) {
 }
 
 /* perf-triage helper (not part of the documented ABI): key 0 = FD_TC_DEBUG bits, 1 / 2 = A-ring slot cap of the
- * sparse / dense launches, 3 / 4 = gather through L1 for sparse / dense launches */
+ * sparse / dense launches, 3 / 4 = gather through L1 for sparse / dense launches, 5 = TMA gather4 producer on/off */
 int fd_debug_set_tc(int key, int value) {
   switch (key) {
     case 0: fd::g_dbg = value; return 0;
@@ -945,6 +1148,8 @@ int fd_debug_set_tc(int key, int value) {
     case 2: fd::g_sa_cap[1] = value; return 0;
     case 3: fd::g_l1[0] = value; return 0;
     case 4: fd::g_l1[1] = value; return 0;
+    case 5: fd::g_tma = value; return 0;
+    case 6: fd::g_tma_dense = value; return 0;
   }
   return -1;
 }

@@ -20,14 +20,15 @@ pts = torch.from_numpy(np.concatenate(scenes)).to(dev)
 off = torch.tensor(np.r_[0, np.cumsum([len(s) for s in scenes])], dtype=torch.int32, device=dev)
 L = lib.load()
 L.fd_debug_set_tc.argtypes = [C.c_int, C.c_int]
-CONFIGS = [("base", {}), ("sparse L1", {3: 1}), ("sparse L1 sa4", {3: 1, 1: 4}), ("sparse sa4", {1: 4}),
-           ("sparse L1 + dense L1", {3: 1, 4: 1}), ("sparse L1 sa4 + dense L1 sa4", {3: 1, 1: 4, 4: 1, 2: 4})]
+CONFIGS = [("cp.async gather everywhere", {6: 0}), ("dense: TMA tile loads", {6: 1})]
 if len(sys.argv) > 2:
     CONFIGS = [(a, eval(a)) for a in sys.argv[2:]]
 with torch.no_grad():
     for name, knobs in CONFIGS:
         for k in range(5):
             L.fd_debug_set_tc(k, 0)
+        L.fd_debug_set_tc(5, 0)
+        L.fd_debug_set_tc(6, 1)
         for k, v in knobs.items():
             L.fd_debug_set_tc(k, v)
         for _ in range(2):
