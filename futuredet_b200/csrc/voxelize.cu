@@ -1,18 +1,25 @@
 // Fused, deterministic voxelize + mean-VFE for sm_100a.
 //
 // Reproduces the *sequential* semantics of the reference loop
-// (det3d/ops/point_cloud/point_cloud_ops.py:7-55) with data-parallel passes:
-//   P1  every point -> float32 voxel coordinate (true IEEE sub/div/floor, :36),
-//       claim a hash slot for its voxel and atomicMin the voxel's first point index;
-//   P2  rank voxels by first point index = exclusive scan over "is first point"
-//       flags (voxel id == order of first appearance, :44-50);
-//   P3  voxels whose per-scene rank >= max_voxels are dropped (:46-47); every
-//       surviving point bubbles its index into the voxel's sorted list of the
-//       max_points smallest indices (first max_points points in input order, :51-54);
-//   P4  one thread per voxel sums those points in input order and divides by the
-//       count (det3d/models/readers/voxel_encoder.py:20-22), writes features,
-//       (b,z,y,x) coordinates (collate.py:199-206) and num_points.
-// All indices are bit-exact with the reference; no atomics on floats anywhere.
+// (det3d/ops/point_cloud/point_cloud_ops.py:7-55) with data-parallel passes over scene-contiguous points:
+//   K1  every point -> float32 voxel coordinate (true IEEE sub/div/floor, :36) -> ONE 64-bit hash word per voxel,
+//       (cell << 32) | first point index: an empty slot is claimed with a CAS, a slot that already holds the cell is
+//       lowered with a 64-bit atomicMin -- key match and "first point of the voxel" (:44-50) in the same word.  Every
+//       scene hashes into its own region of the table, sized 1.5x its point count (device-side, from the batch
+//       offsets), so the live region (3.7 MB for a 305 k-point scene) stays L2 resident while its points stream by;
+//   K2  bit i of a bitmap = "point i is the first point of its voxel"; an exclusive popcount scan over the bitmap words
+//       (1/32 of the points) turns it into the voxel rank = order of first appearance, without a per-point rank array;
+//   K3  voxels whose per-scene rank >= max_voxels are dropped (:46-47); every surviving point pushes itself onto its
+//       voxel's linked list (one atomicExch on head[voxel]; next[] lives beside the points);
+//   K4  one thread per voxel walks the list, keeps the max_points smallest indices (= the first max_points points in
+//       input order, :51-54) in registers, sums them in that order and divides by the count
+//       (det3d/models/readers/voxel_encoder.py:20-22), writes features, (b,z,y,x) coordinates (collate.py:199-206)
+//       and num_points.
+// All indices are bit-exact with the reference; no atomics on floats anywhere; the result does not depend on thread
+// scheduling (atomicMin / the set of list members are order independent, the sum order is fixed by sorting).
+// HBM traffic per scene: points read once in K1 (20 N) and, L2 permitting, not again; table memset 12 N; pslot / next
+// 8 N written + read; outputs 52 M.  Round 1 moved 25 N of memsets for a 4x table plus 40 M of 10-slot lists per voxel
+// and missed L2 on every atomic once the batch grew (805 MB of tables at 32 scenes).
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -24,7 +31,7 @@ struct VoxGeom {
   int grid[3];  // gx, gy, gz
 };
 
-constexpr int kSlotEmpty = 0x7f7f7f7f;  // memset(0x7f) pattern; > any point index we accept
+constexpr unsigned long long kEmptyWord = ~0ull;   // memset(0xff)
 
 __device__ __forceinline__ int find_scene(const int32_t* s_off, int B, int i) {
   int lo = 0, hi = B;  // offsets[lo] <= i < offsets[hi]
@@ -35,157 +42,198 @@ __device__ __forceinline__ int find_scene(const int32_t* s_off, int B, int i) {
   return lo;
 }
 
-// ---- P1 -----------------------------------------------------------------------
+// table region of a scene: [3*off[b]/2, 3*off[b+1]/2) + b  (the "+ b" keeps one spare slot per scene so that an
+// empty slot always terminates a probe sequence)
+__device__ __forceinline__ uint32_t region_start(int off_b, int b) { return (uint32_t)(((long long)off_b * 3) >> 1) + (uint32_t)b; }
+
+// ---- K1 -----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 vox_hash_points(const float* __restrict__ pts, int n, int pstride, const int32_t* __restrict__ boff,
-                int B, VoxGeom g, long long* __restrict__ keys, int* __restrict__ first,
-                uint32_t mask, uint32_t scene_cap, int* __restrict__ pslot) {
+                int B, VoxGeom g, unsigned long long* __restrict__ table, int* __restrict__ pslot) {
   extern __shared__ int32_t s_off[];
   for (int j = threadIdx.x; j <= B; j += blockDim.x) s_off[j] = boff[j];
   __syncthreads();
-  const long long cells = (long long)g.grid[0] * g.grid[1] * g.grid[2];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int n32 = (n + 31) & ~31;                    // whole warps walk the loop together (warp-wide match / shuffle)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) {
     const float* p = pts + (size_t)i * pstride;
-    int c[3];
-    bool ok = true;
+    int c[3] = {0, 0, 0};
+    bool ok = i < n;
+    if (ok) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float f = floorf(__fdiv_rn(__fsub_rn(p[j], g.lo[j]), g.vs[j]));
-      ok = ok && (f >= 0.0f) && (f < (float)g.grid[j]);
-      c[j] = (int)f;
+      for (int j = 0; j < 3; ++j) {
+        float f = floorf(__fdiv_rn(__fsub_rn(p[j], g.lo[j]), g.vs[j]));
+        ok = ok && (f >= 0.0f) && (f < (float)g.grid[j]);
+        c[j] = (int)f;
+      }
     }
     int slot = -1;
+    // (electing one lane per distinct cell of a warp with __match_any_sync was measured: no gain -- the match costs as
+    // much as the atomics it saves)
     if (ok) {
-      int b = find_scene(s_off, B, i);
-      long long key = (long long)b * cells + ((long long)c[2] * g.grid[1] + c[1]) * g.grid[0] + c[0];
-      // every scene hashes into its own region of the table (probing may spill into the next one): blocks run in
-      // launch order over scene-contiguous points, so the live part of the table stays L2 resident in a big batch
-      uint32_t h = ((uint32_t)b * scene_cap + (hash64((uint64_t)key) & (scene_cap - 1))) & mask;
+      const int b = find_scene(s_off, B, i);
+      const uint32_t cell = ((uint32_t)c[2] * g.grid[1] + c[1]) * g.grid[0] + c[0];
+      const uint32_t r0 = region_start(s_off[b], b), size = region_start(s_off[b + 1], b + 1) - r0;
+      const unsigned long long word = ((unsigned long long)cell << 32) | (uint32_t)i;
+      uint32_t h = __umulhi(hash64(cell), size);
       while (true) {
-        long long prev = atomicCAS((unsigned long long*)&keys[h], (unsigned long long)kEmptyKey,
-                                   (unsigned long long)key);
-        if (prev == kEmptyKey || prev == key) break;
-        h = (h + 1) & mask;
+        unsigned long long cur = __ldcg(&table[r0 + h]);      // L2 (coherent with the atomics), not a stale L1 line
+        if (cur == kEmptyWord) {
+          cur = atomicCAS(&table[r0 + h], kEmptyWord, word);
+          if (cur == kEmptyWord) break;
+        }
+        if ((uint32_t)(cur >> 32) == cell) {           // same voxel: keep the smallest point index
+          if (cur > word) atomicMin(&table[r0 + h], word);
+          break;
+        }
+        if (++h == size) h = 0;
       }
-      atomicMin(&first[h], i);
-      slot = (int)h;
+      slot = (int)(r0 + h);
     }
-    pslot[i] = slot;
+    if (i < n) pslot[i] = slot;
   }
 }
 
-// ---- P2: flag functor for the scan --------------------------------------------
-struct LoadIsFirst {
-  const int* pslot;
-  const int* first;
-  __device__ __forceinline__ int operator()(int64_t i) const {
-    int s = pslot[i];
-    return (s >= 0 && first[s] == (int)i) ? 1 : 0;
-  }
-};
-
-// ---- per-scene bookkeeping (tiny) ----------------------------------------------
-__global__ void vox_scene_counts(const int32_t* __restrict__ rank, const int32_t* __restrict__ total_first,
-                                 const int32_t* __restrict__ boff, int B, int n, int max_voxels,
-                                 int32_t* __restrict__ scene_rank0, int32_t* __restrict__ out_base,
-                                 int32_t* __restrict__ nvox, int32_t* __restrict__ total) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int run = 0;
-  for (int b = 0; b < B; ++b) {
-    int o0 = boff[b], o1 = boff[b + 1];
-    int r0 = o0 < n ? rank[o0] : *total_first;
-    int r1 = o1 < n ? rank[o1] : *total_first;
-    int cnt = r1 - r0;
-    if (cnt > max_voxels) cnt = max_voxels;
-    scene_rank0[b] = r0;
-    out_base[b] = run;
-    nvox[b] = cnt;
-    run += cnt;
-  }
-  out_base[B] = run;
-  *total = run;
-}
-
-// ---- P3 -----------------------------------------------------------------------
+// ---- K2: "first point of its voxel" bitmap ----------------------------------------
 __global__ void __launch_bounds__(256)
-vox_assign_points(int n, const int32_t* __restrict__ boff, int B, VoxGeom g,
-                  const long long* __restrict__ keys, const int* __restrict__ first,
-                  const int* __restrict__ pslot, const int32_t* __restrict__ rank,
-                  const int32_t* __restrict__ scene_rank0, const int32_t* __restrict__ out_base,
-                  int max_voxels, int max_points, int* __restrict__ slots, int32_t* __restrict__ coords) {
+vox_first_bits(int n, const unsigned long long* __restrict__ table, const int* __restrict__ pslot,
+               uint32_t* __restrict__ bits) {
+  const int n32 = (n + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) {
+    bool first = false;
+    if (i < n) {
+      const int s = pslot[i];
+      first = s >= 0 && (uint32_t)table[s] == (uint32_t)i;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if ((threadIdx.x & 31) == 0) bits[i >> 5] = m;
+  }
+}
+
+// voxel rank of first point f = number of first points before it
+__device__ __forceinline__ int first_rank(const uint32_t* bits, const int32_t* wordprefix, int f) {
+  return wordprefix[f >> 5] + __popc(bits[f >> 5] & ((1u << (f & 31)) - 1u));
+}
+
+// ---- per-scene bookkeeping (tiny): one block, a thread per scene + a block-wide exclusive scan -----------------
+__global__ void __launch_bounds__(256)
+vox_scene_counts(const uint32_t* __restrict__ bits, const int32_t* __restrict__ wordprefix,
+                 const int32_t* __restrict__ total_first, const int32_t* __restrict__ boff, int B, int n,
+                 int max_voxels, int32_t* __restrict__ scene_rank0, int32_t* __restrict__ out_base,
+                 int32_t* __restrict__ nvox, int32_t* __restrict__ total) {
+  int carry = 0;
+  for (int base = 0; base < B; base += 256) {
+    const int b = base + threadIdx.x;
+    int cnt = 0;
+    if (b < B) {
+      const int o0 = boff[b], o1 = boff[b + 1];
+      const int r0 = o0 < n ? first_rank(bits, wordprefix, o0) : *total_first;
+      const int r1 = o1 < n ? first_rank(bits, wordprefix, o1) : *total_first;
+      cnt = min(r1 - r0, max_voxels);
+      scene_rank0[b] = r0;
+      nvox[b] = cnt;
+    }
+    int t;
+    const int e = block_excl_scan<256>(cnt, &t);
+    if (b < B) out_base[b] = carry + e;
+    carry += t;
+  }
+  if (threadIdx.x == 0) { out_base[B] = carry; *total = carry; }
+}
+
+// ---- K3 -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vox_link_points(int n, const int32_t* __restrict__ boff, int B, VoxGeom g,
+                const unsigned long long* __restrict__ table, const int* __restrict__ pslot,
+                const uint32_t* __restrict__ bits, const int32_t* __restrict__ wordprefix,
+                const int32_t* __restrict__ scene_rank0, const int32_t* __restrict__ out_base,
+                int max_voxels, int* __restrict__ head, int* __restrict__ next, int32_t* __restrict__ coords) {
   extern __shared__ int32_t s_off[];
   int32_t* s_r0 = s_off + (B + 1);
   int32_t* s_base = s_r0 + B;
   for (int j = threadIdx.x; j <= B; j += blockDim.x) s_off[j] = boff[j];
   for (int j = threadIdx.x; j < B; j += blockDim.x) { s_r0[j] = scene_rank0[j]; s_base[j] = out_base[j]; }
   __syncthreads();
-  const long long cells = (long long)g.grid[0] * g.grid[1] * g.grid[2];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int ps = pslot[i];
+    const int ps = pslot[i];
     if (ps < 0) continue;
-    int f = first[ps];
-    int b = find_scene(s_off, B, i);
-    int local = rank[f] - s_r0[b];
+    const unsigned long long w = table[ps];
+    const int f = (int)(uint32_t)w;
+    const int b = find_scene(s_off, B, i);
+    const int local = first_rank(bits, wordprefix, f) - s_r0[b];
     if (local >= max_voxels) continue;
-    int vid = s_base[b] + local;
+    const int vid = s_base[b] + local;
     if (f == i) {
-      long long lin = keys[ps] - (long long)b * cells;
-      int x = (int)(lin % g.grid[0]);
-      long long t = lin / g.grid[0];
-      int y = (int)(t % g.grid[1]);
-      int z = (int)(t / g.grid[1]);
+      uint32_t cell = (uint32_t)(w >> 32);
+      const int x = (int)(cell % (uint32_t)g.grid[0]);
+      cell /= (uint32_t)g.grid[0];
+      const int y = (int)(cell % (uint32_t)g.grid[1]);
+      const int z = (int)(cell / (uint32_t)g.grid[1]);
       reinterpret_cast<int4*>(coords)[vid] = make_int4(b, z, y, x);
     }
-    // bubble i into the ascending list of the max_points smallest indices of this voxel
-    int* sl = slots + (size_t)vid * max_points;
-    int cur = i;
-    for (int s = 0; s < max_points; ++s) {
-      int old = atomicMin(&sl[s], cur);
-      if (old == kSlotEmpty) break;
-      cur = old > cur ? old : cur;
-    }
+    next[i] = atomicExch(&head[vid], i);          // push onto the voxel's list (order irrelevant: K4 sorts)
   }
 }
 
-// ---- P4 -----------------------------------------------------------------------
+// ---- K4 -----------------------------------------------------------------------
+template <int MAXP>
 __global__ void __launch_bounds__(256)
-vox_reduce_mean(const float* __restrict__ pts, int pstride, int num_feat, const int* __restrict__ slots,
-                int max_points, const int32_t* __restrict__ total, float* __restrict__ feat,
-                int feat_stride, int32_t* __restrict__ npts, float* __restrict__ voxels) {
+vox_reduce_mean(const float* __restrict__ pts, int pstride, int num_feat, const int* __restrict__ head,
+                const int* __restrict__ next, int max_points, const int32_t* __restrict__ total,
+                float* __restrict__ feat, int feat_stride, int32_t* __restrict__ npts, float* __restrict__ voxels) {
   const int nv = *total;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
-    const int* sl = slots + (size_t)v * max_points;
+    // the max_points smallest point indices of the list, ascending (insertion into a sorted register array)
+    int best[MAXP];
+    int cnt = 0;
+    for (int idx = head[v]; idx >= 0; idx = next[idx]) {
+      if (cnt == max_points && idx > best[cnt - 1]) continue;
+      int j = cnt < max_points ? cnt : max_points - 1;
+#pragma unroll
+      for (int q = MAXP - 1; q > 0; --q)
+        if (q <= j && best[q - 1] > idx) { best[q] = best[q - 1]; j = q - 1; }
+#pragma unroll
+      for (int q = 0; q < MAXP; ++q)
+        if (q == j) best[q] = idx;
+      if (cnt < max_points) ++cnt;
+    }
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    int cnt = 0;
-    for (int s = 0; s < max_points; ++s) {
-      int idx = sl[s];
-      if (idx == kSlotEmpty) break;
-      const float* p = pts + (size_t)idx * pstride;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c < num_feat) {
-          float q = p[c];
-          acc[c] = __fadd_rn(acc[c], q);
-          if (voxels) voxels[((size_t)v * max_points + s) * num_feat + c] = q;
-        }
-      ++cnt;
+    for (int s = 0; s < MAXP; ++s) {
+      if (s < cnt) {
+        const float* p = pts + (size_t)best[s] * pstride;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < num_feat) {
+            float q = p[c];
+            acc[c] = __fadd_rn(acc[c], q);
+            if (voxels) voxels[((size_t)v * max_points + s) * num_feat + c] = q;
+          }
+      }
     }
     if (voxels)
       for (int e = cnt * num_feat; e < max_points * num_feat; ++e) voxels[(size_t)v * max_points * num_feat + e] = 0.f;
     const float fc = (float)cnt;
     float* o = feat + (size_t)v * feat_stride;
+    if (feat_stride == 8 && (((uintptr_t)o) & 15) == 0) {          // the fused pipeline's padded rows: two 128-bit stores
+      float r[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c < feat_stride) o[c] = c < num_feat ? __fdiv_rn(acc[c], fc) : 0.f;
-    for (int c = 8; c < feat_stride; ++c) o[c] = 0.f;
+      for (int c = 0; c < 8; ++c) r[c] = c < num_feat ? __fdiv_rn(acc[c], fc) : 0.f;
+      reinterpret_cast<float4*>(o)[0] = make_float4(r[0], r[1], r[2], r[3]);
+      reinterpret_cast<float4*>(o)[1] = make_float4(r[4], r[5], r[6], r[7]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < feat_stride) o[c] = c < num_feat ? __fdiv_rn(acc[c], fc) : 0.f;
+      for (int c = 8; c < feat_stride; ++c) o[c] = 0.f;
+    }
     npts[v] = cnt;
   }
 }
 
 struct VoxWorkspace {
-  long long* keys; int* first; int* pslot; int32_t* rank; int* slots;
+  unsigned long long* table; int* head; int* pslot; int* next; uint32_t* bits; int32_t* wordprefix;
   int32_t* scene_rank0; int32_t* out_base; int32_t* total_first; void* scan_tmp;
   int64_t cap; size_t bytes;
 };
@@ -194,22 +242,24 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static VoxWorkspace carve(void* base, int64_t n, int B, int max_voxels, int max_points) {
   VoxWorkspace w{};
-  int64_t cap = 1024;
-  while (cap < 4 * n) cap <<= 1;      // load factor <= 0.25 overall, <= 0.5 inside a scene region for any B
+  (void)max_points;
+  const int64_t cap = (n * 3) / 2 + B + 1;       // every scene region holds 1.5x its points (+ its spare slot)
   w.cap = cap;
+  const int64_t words = (n + 31) / 32 + 1;
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes); return (void*)r; };
-  // [keys] is memset to 0xff; [first | slots] are contiguous and memset to 0x7f
-  w.keys = (long long*)take(sizeof(long long) * cap);
-  w.first = (int*)take(sizeof(int) * cap);
-  w.slots = (int*)take(sizeof(int) * (size_t)B * max_voxels * max_points);
+  // [table | head] are contiguous and memset to 0xff with one call (empty word / empty list)
+  w.table = (unsigned long long*)take(sizeof(unsigned long long) * cap);
+  w.head = (int*)take(sizeof(int) * (size_t)B * max_voxels);
   w.pslot = (int*)take(sizeof(int) * (n > 0 ? n : 1));
-  w.rank = (int32_t*)take(sizeof(int32_t) * (n > 0 ? n : 1));
+  w.next = (int*)take(sizeof(int) * (n > 0 ? n : 1));
+  w.bits = (uint32_t*)take(sizeof(uint32_t) * words);
+  w.wordprefix = (int32_t*)take(sizeof(int32_t) * words);
   w.scene_rank0 = (int32_t*)take(sizeof(int32_t) * (B + 1));
   w.out_base = (int32_t*)take(sizeof(int32_t) * (B + 1));
   w.total_first = (int32_t*)take(sizeof(int32_t));
-  w.scan_tmp = take(fd_scan_tmp_bytes(n));
+  w.scan_tmp = take(fd_scan_tmp_bytes(words));
   w.bytes = off;
   return w;
 }
@@ -281,35 +331,41 @@ int fd_voxelize_vfe(const float* d_points, int64_t total_points, int point_strid
     FD_REQUIRE(grid3[j] > 0 && voxel_size3[j] > 0.f, "fd_voxelize_vfe: bad grid/voxel size");
   }
   const int n = (int)total_points;
-  FD_CUDA(cudaMemsetAsync(w.keys, 0xff, sizeof(long long) * w.cap, stream));
-  // first[] and slots[] are adjacent in the workspace: one memset covers both
-  FD_CUDA(cudaMemsetAsync(w.first, 0x7f, (char*)w.pslot - (char*)w.first, stream));
+  FD_REQUIRE((long long)grid3[0] * grid3[1] * grid3[2] < 0x7fffffffLL, "fd_voxelize_vfe: grid of %lld cells does not fit the 32-bit cell key",
+             (long long)grid3[0] * grid3[1] * grid3[2]);
+  // table and list heads are adjacent in the workspace: one memset covers both
+  FD_CUDA(cudaMemsetAsync(w.table, 0xff, (char*)w.pslot - (char*)w.table, stream));
   const int threads = 256;
   const int grid_pts = ceil_div(n, threads) > 0 ? ceil_div(n, threads) : 1;   // one block per 256 consecutive points
-  uint32_t scene_cap = 1024;                                                   // per-scene region: pow2 >= 2 * mean scene size
-  while ((int64_t)scene_cap * B < w.cap) scene_cap <<= 1;
-  if ((int64_t)scene_cap * B > w.cap) scene_cap >>= 1;
+  const int64_t words = ((int64_t)n + 31) / 32;
   if (n > 0) {
     vox_hash_points<<<grid_pts, threads, (B + 1) * sizeof(int32_t), stream>>>(
-        d_points, n, point_stride, d_batch_offsets, B, g, w.keys, w.first, (uint32_t)(w.cap - 1), scene_cap, w.pslot);
+        d_points, n, point_stride, d_batch_offsets, B, g, w.table, w.pslot);
+    FD_LAUNCHED();
+    vox_first_bits<<<grid_pts, threads, 0, stream>>>(n, w.table, w.pslot, w.bits);
     FD_LAUNCHED();
   }
-  // rank[i] = number of voxel-first points before i
+  // wordprefix[j] = number of voxel-first points before point 32 j
   {
-    int rc = scan_impl(LoadIsFirst{w.pslot, w.first}, w.rank, n, w.total_first, w.scan_tmp, stream);
+    int rc = exclusive_scan_popc(w.bits, w.wordprefix, words, w.total_first, w.scan_tmp, stream);
     if (rc) return rc;
   }
-  vox_scene_counts<<<1, 32, 0, stream>>>(w.rank, w.total_first, d_batch_offsets, B, n, max_voxels,
+  vox_scene_counts<<<1, 256, 0, stream>>>(w.bits, w.wordprefix, w.total_first, d_batch_offsets, B, n, max_voxels,
                                          w.scene_rank0, w.out_base, d_nvox, d_total);
   FD_LAUNCHED();
   if (n > 0) {
-    vox_assign_points<<<grid_pts, threads, (3 * B + 1) * sizeof(int32_t), stream>>>(
-        n, d_batch_offsets, B, g, w.keys, w.first, w.pslot, w.rank, w.scene_rank0, w.out_base,
-        max_voxels, max_points, w.slots, d_coords);
+    vox_link_points<<<grid_pts, threads, (3 * B + 1) * sizeof(int32_t), stream>>>(
+        n, d_batch_offsets, B, g, w.table, w.pslot, w.bits, w.wordprefix, w.scene_rank0, w.out_base,
+        max_voxels, w.head, w.next, d_coords);
     FD_LAUNCHED();
     const int64_t vcap = (int64_t)B * max_voxels;
-    vox_reduce_mean<<<persistent_grid(ceil_div(vcap < n ? vcap : n, threads), 8), threads, 0, stream>>>(
-        d_points, point_stride, num_feat, w.slots, max_points, d_total, d_feat, feat_stride, d_npts, d_voxels);
+    const int grid_vox = ceil_div(vcap < n ? vcap : n, threads);
+    if (max_points <= 16)
+      vox_reduce_mean<16><<<grid_vox, threads, 0, stream>>>(d_points, point_stride, num_feat, w.head, w.next, max_points,
+                                                           d_total, d_feat, feat_stride, d_npts, d_voxels);
+    else
+      vox_reduce_mean<64><<<grid_vox, threads, 0, stream>>>(d_points, point_stride, num_feat, w.head, w.next, max_points,
+                                                           d_total, d_feat, feat_stride, d_npts, d_voxels);
     FD_LAUNCHED();
   }
   return 0;
