@@ -101,7 +101,8 @@ __device__ __forceinline__ float load_residual(const ConvArgs& a, int o, int c) 
 
 int conv_forward_simt(const ConvArgs& a, cudaStream_t stream);
 bool wgrad_tc_supported(const ConvArgs& a);                              // wgrad_tc.cu
-int conv_wgrad_tc(const ConvArgs& a, float* dw, cudaStream_t stream);   // wgrad_tc.cu
+int conv_wgrad_tc_chunks(const ConvArgs& a);                                              // wgrad_tc.cu
+int conv_wgrad_tc(const ConvArgs& a, float* dw, float* partial, cudaStream_t stream);    // wgrad_tc.cu
 int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream);
 
 }  // namespace fd

@@ -50,7 +50,8 @@ __device__ __forceinline__ int wg_col(int tx, int j) {
 
 template <int TI, int TO>
 __global__ void __launch_bounds__(WG_THREADS)
-conv_wgrad_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta, int tiles_ci, int tiles_co) {
+conv_wgrad_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict__ partial, int rows_per_cta, int tiles_ci,
+                  int tiles_co) {
   constexpr int RI = TI >= 64 ? 8 : 4, RO = TO >= 64 ? 8 : 4;
   constexpr int TXN = TO / RO, TYN = TI / RI, GS = TXN * TYN, G = WG_THREADS / GS;
   // rows per shared-memory batch: 32 KB of operands in flight per CTA whatever the tile width
@@ -71,10 +72,13 @@ conv_wgrad_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta, in
   // of active sites, and chunks cut from the capacity would leave most CTAs without rows
   rows_per_cta = ((n + (int)gridDim.x - 1) / (int)gridDim.x + 63) & ~63;
   const long long rb = (long long)blockIdx.x * rows_per_cta;
-  if (rb >= n) return;
-  const int row_begin = (int)rb;
-  const int row_end = (int)min((long long)n, rb + rows_per_cta);
   const int grp = tid / GS, tx = (tid % GS) % TXN, ty = (tid % GS) / TXN;   // tx -> RO output, ty -> RI input channels
+  // deterministic mode: every (row chunk, thread group) owns a slot of the partial buffer laid out like dW; the slots
+  // are added in ascending order by wgrad_reduce_kernel (no float atomics -> bit-reproducible gradients)
+  float* pslot = partial ? partial + ((size_t)blockIdx.x * G + grp) * a.K * a.cin * a.cout : nullptr;
+  if (rb >= n && !pslot) return;
+  const int row_begin = (int)min((long long)n, rb);
+  const int row_end = (int)min((long long)n, rb + rows_per_cta);
   const bool vec_a = (a.cin % 4 == 0) && (a.in_stride % 4 == 0) && ((((uintptr_t)a.in) & 15) == 0);
   const bool vec_b = a.out_map == FD_OUTMAP_IDENTITY && (a.cout % 4 == 0) && (a.out_stride % 4 == 0) &&
                      ((((uintptr_t)a.out) & 15) == 0);
@@ -167,7 +171,7 @@ conv_wgrad_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta, in
       q_cnt -= take;
     }
   }
-  float* dwk = dw + (size_t)k * a.cin * a.cout;
+  float* dwk = (pslot ? pslot : dw) + (size_t)k * a.cin * a.cout;
 #pragma unroll
   for (int i = 0; i < RI; ++i) {
     const int ci = ci0 + ty * RI + i;
@@ -175,49 +179,105 @@ conv_wgrad_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta, in
 #pragma unroll
     for (int j = 0; j < RO; ++j) {
       const int co = co0 + wg_col<RO, TXN>(tx, j);
-      if (co < a.cout && acc[i][j] != 0.f) atomicAdd(dwk + (size_t)ci * a.cout + co, acc[i][j]);
+      if (co < a.cout) {
+        if (pslot) dwk[(size_t)ci * a.cout + co] = acc[i][j];
+        else if (acc[i][j] != 0.f) atomicAdd(dwk + (size_t)ci * a.cout + co, acc[i][j]);
+      }
     }
+  }
+}
+
+// dW[e] += sum over slots (ascending) of partial[slot][e]: the ordered reduce of the deterministic weight gradient
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int slots, long long elems, float* __restrict__ dw) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < slots; ++c) s = __fadd_rn(s, partial[(size_t)c * elems + e]);
+    dw[e] = __fadd_rn(dw[e], s);
   }
 }
 
 static int wg_tile(int c) { return c >= 96 ? 128 : c >= 48 ? 64 : c >= 24 ? 32 : 16; }
 
-template <int TI, int TO>
-static int launch_wgrad_t(const ConvArgs& a, float* dw, cudaStream_t stream) {
-  const int tiles_ci = ceil_div(a.cin, TI), tiles_co = ceil_div(a.cout, TO);
-  const int tiles = a.K * tiles_ci * tiles_co;
-  FD_REQUIRE(tiles <= 65535, "fd_conv_wgrad: K*tiles = %d exceeds the grid limit", tiles);
+constexpr int wg_groups(int TI, int TO) {
+  return WG_THREADS / ((TO / (TO >= 64 ? 8 : 4)) * (TI / (TI >= 64 ? 8 : 4)));
+}
+static int wg_simt_chunks(const ConvArgs& a, int TI, int TO) {
+  const int tiles = a.K * ceil_div(a.cin, TI) * ceil_div(a.cout, TO);
   int chunks = ceil_div((int64_t)kNumSMs * 8, tiles);
   const int max_chunks = ceil_div(a.n_cap, 8 * WG_R);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   int rows_per_cta = ceil_div(a.n_cap, chunks);
   rows_per_cta = ceil_div(rows_per_cta, WG_R) * WG_R;
-  chunks = ceil_div(a.n_cap, rows_per_cta);
-  conv_wgrad_kernel<TI, TO><<<dim3(chunks, tiles), WG_THREADS, 0, stream>>>(a, dw, rows_per_cta, tiles_ci, tiles_co);
+  return ceil_div(a.n_cap, rows_per_cta);
+}
+
+// partial == nullptr: accumulate with atomics; otherwise *slots receives the number of partial slots written
+template <int TI, int TO>
+static int launch_wgrad_t(const ConvArgs& a, float* dw, float* partial, int* slots, cudaStream_t stream) {
+  const int tiles_ci = ceil_div(a.cin, TI), tiles_co = ceil_div(a.cout, TO);
+  const int tiles = a.K * tiles_ci * tiles_co;
+  FD_REQUIRE(tiles <= 65535, "fd_conv_wgrad: K*tiles = %d exceeds the grid limit", tiles);
+  const int chunks = wg_simt_chunks(a, TI, TO);
+  const int rows_per_cta = ceil_div(ceil_div(a.n_cap, chunks), WG_R) * WG_R;
+  if (slots) *slots = chunks * wg_groups(TI, TO);
+  if (!stream && !dw) return 0;                                   // planning call
+  conv_wgrad_kernel<TI, TO><<<dim3(chunks, tiles), WG_THREADS, 0, stream>>>(a, dw, partial, rows_per_cta, tiles_ci, tiles_co);
   FD_LAUNCHED();
   return 0;
 }
 
 template <int TI>
-static int launch_wgrad_i(const ConvArgs& a, float* dw, cudaStream_t stream) {
+static int launch_wgrad_i(const ConvArgs& a, float* dw, float* partial, int* slots, cudaStream_t stream) {
   switch (wg_tile(a.cout)) {
-    case 128: return launch_wgrad_t<TI, 128>(a, dw, stream);
-    case 64: return launch_wgrad_t<TI, 64>(a, dw, stream);
-    case 32: return launch_wgrad_t<TI, 32>(a, dw, stream);
-    default: return launch_wgrad_t<TI, 16>(a, dw, stream);
+    case 128: return launch_wgrad_t<TI, 128>(a, dw, partial, slots, stream);
+    case 64: return launch_wgrad_t<TI, 64>(a, dw, partial, slots, stream);
+    case 32: return launch_wgrad_t<TI, 32>(a, dw, partial, slots, stream);
+    default: return launch_wgrad_t<TI, 16>(a, dw, partial, slots, stream);
   }
 }
 
-static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream, int precision = FD_PREC_FP32) {
+// Number of partial slots the deterministic path of this launch writes (planning only, nothing is launched).
+static int wgrad_slots(const ConvArgs& a, int precision) {
   if (a.n_cap <= 0) return 0;
-  if (precision == FD_PREC_BF16X3 && wgrad_tc_supported(a)) return conv_wgrad_tc(a, dw, stream);
+  if (precision == FD_PREC_BF16X3 && wgrad_tc_supported(a)) return conv_wgrad_tc_chunks(a);
+  int slots = 0;
   switch (wg_tile(a.cin)) {
-    case 128: return launch_wgrad_i<128>(a, dw, stream);
-    case 64: return launch_wgrad_i<64>(a, dw, stream);
-    case 32: return launch_wgrad_i<32>(a, dw, stream);
-    default: return launch_wgrad_i<16>(a, dw, stream);
+    case 128: launch_wgrad_i<128>(a, nullptr, nullptr, &slots, nullptr); break;
+    case 64: launch_wgrad_i<64>(a, nullptr, nullptr, &slots, nullptr); break;
+    case 32: launch_wgrad_i<32>(a, nullptr, nullptr, &slots, nullptr); break;
+    default: launch_wgrad_i<16>(a, nullptr, nullptr, &slots, nullptr); break;
   }
+  return slots;
+}
+
+// ws == nullptr: fp32 atomics into dw; otherwise per-chunk partial tiles in ws + an ordered reduce into dw
+static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream, int precision = FD_PREC_FP32, float* ws = nullptr,
+                        size_t ws_bytes = 0) {
+  if (a.n_cap <= 0) return 0;
+  const long long elems = (long long)a.K * a.cin * a.cout;
+  int slots = 0;
+  if (ws) {
+    slots = wgrad_slots(a, precision);
+    FD_REQUIRE((size_t)slots * elems * sizeof(float) <= ws_bytes, "fd_conv_wgrad_det: workspace %zu < required %zu", ws_bytes,
+               (size_t)slots * elems * sizeof(float));
+  }
+  int rc;
+  if (precision == FD_PREC_BF16X3 && wgrad_tc_supported(a)) {
+    rc = conv_wgrad_tc(a, dw, ws, stream);
+  } else {
+    switch (wg_tile(a.cin)) {
+      case 128: rc = launch_wgrad_i<128>(a, dw, ws, nullptr, stream); break;
+      case 64: rc = launch_wgrad_i<64>(a, dw, ws, nullptr, stream); break;
+      case 32: rc = launch_wgrad_i<32>(a, dw, ws, nullptr, stream); break;
+      default: rc = launch_wgrad_i<16>(a, dw, ws, nullptr, stream); break;
+    }
+  }
+  if (rc || !ws) return rc;
+  wgrad_reduce_kernel<<<persistent_grid(ceil_div(elems, 256), 8), 256, 0, stream>>>(ws, slots, elems, dw);
+  FD_LAUNCHED();
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- reductions
@@ -523,10 +583,28 @@ int fd_rulebook_transpose(const int32_t* d_nbr, int nbr_stride, const int32_t* d
   return 0;
 }
 
+static int wgrad_entry(const fd_conv_desc* d, float* d_dw, float* ws, size_t ws_bytes, size_t* need, void* stream_);
+
 int fd_conv_wgrad(const fd_conv_desc* d, float* d_dw, void* stream_) {
+  return wgrad_entry(d, d_dw, nullptr, 0, nullptr, stream_);
+}
+
+size_t fd_conv_wgrad_workspace_bytes(const fd_conv_desc* d) {
+  size_t need = 0;
+  if (wgrad_entry(d, nullptr, nullptr, 0, &need, nullptr) != 0) return 0;
+  return need;
+}
+
+int fd_conv_wgrad_det(const fd_conv_desc* d, float* d_dw, void* d_workspace, size_t workspace_bytes, void* stream_) {
+  FD_REQUIRE(d_workspace != nullptr, "fd_conv_wgrad_det: null workspace");
+  return wgrad_entry(d, d_dw, (float*)d_workspace, workspace_bytes, nullptr, stream_);
+}
+
+// need != nullptr: planning call, *need = workspace bytes of the deterministic path, nothing is launched
+static int wgrad_entry(const fd_conv_desc* d, float* d_dw, float* ws, size_t ws_bytes, size_t* need, void* stream_) {
   using namespace fd;
   cudaStream_t stream = (cudaStream_t)stream_;
-  FD_REQUIRE(d != nullptr && d_dw != nullptr, "fd_conv_wgrad: null argument");
+  FD_REQUIRE(d != nullptr && (d_dw != nullptr || need), "fd_conv_wgrad: null argument");
   FD_REQUIRE(d->d_in && d->d_out, "fd_conv_wgrad: null in / dy pointer");
   FD_REQUIRE(d->cin >= 1 && d->cout >= 1 && d->K >= 1, "fd_conv_wgrad: bad cin/cout/K");
   FD_REQUIRE(d->in_format == FD_FMT_FP32 && d->out_format == FD_FMT_FP32, "fd_conv_wgrad: fp32 rows only");
@@ -546,12 +624,14 @@ int fd_conv_wgrad(const fd_conv_desc* d, float* d_dw, void* stream_) {
     case FD_GATHER_TABLE:
       FD_REQUIRE(d->d_nbr && d->nbr_stride >= d->n_out_cap, "fd_conv_wgrad: bad neighbour table");
       FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY && d->out_stride >= d->cout, "fd_conv_wgrad: identity out rows only");
-      return launch_wgrad(a, d_dw, stream, d->precision);
+      if (need) { *need = (size_t)wgrad_slots(a, d->precision) * a.K * a.cin * a.cout * sizeof(float); return 0; }
+      return launch_wgrad(a, d_dw, stream, d->precision, ws, ws_bytes);
     case FD_GATHER_CONV2D:
       FD_REQUIRE(d->K == d->kh * d->kw && d->sh >= 1 && d->sw >= 1, "fd_conv_wgrad: bad conv2d geometry");
       FD_REQUIRE(d->n_out_cap == d->B * d->Hout * d->Wout && !d->d_n_out, "fd_conv_wgrad: conv2d rows must be B*Hout*Wout");
       FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY && d->out_stride >= d->cout, "fd_conv_wgrad: identity out rows only");
-      return launch_wgrad(a, d_dw, stream, d->precision);
+      if (need) { *need = (size_t)wgrad_slots(a, d->precision) * a.K * a.cin * a.cout * sizeof(float); return 0; }
+      return launch_wgrad(a, d_dw, stream, d->precision, ws, ws_bytes);
     case FD_GATHER_CONVT2D: {
       FD_REQUIRE(d->kh == d->sh && d->kw == d->sw && d->kh == d->kw && d->ph == 0 && d->pw == 0 && d->K == d->kh * d->kw,
                  "fd_conv_wgrad: convT2d supports kernel == stride, pad 0 only");
@@ -564,7 +644,8 @@ int fd_conv_wgrad(const fd_conv_desc* d, float* d_dw, void* stream_) {
         p.Hout = d->Hin; p.Wout = d->Win;
         p.out_map = OUTMAP_UPSAMPLE;
         p.up_s = d->sh; p.up_dy = k / d->kw; p.up_dx = k % d->kw;
-        int rc = launch_wgrad(p, d_dw + (size_t)k * d->cin * d->cout, stream);
+        if (need) { *need = (size_t)wgrad_slots(p, FD_PREC_FP32) * p.cin * p.cout * sizeof(float); return 0; }
+        int rc = launch_wgrad(p, d_dw + (size_t)k * d->cin * d->cout, stream, FD_PREC_FP32, ws, ws_bytes);
         if (rc) return rc;
       }
       return 0;

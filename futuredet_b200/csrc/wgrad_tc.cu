@@ -13,7 +13,9 @@
 // them into bf16 hi/lo planes in registers and stores them swizzled; one thread issues 12 tcgen05.mma per stage
 // (K = 16 pairs each; A_hi*B_hi + A_hi*B_lo + A_lo*B_hi: ~2^-16 relative, fp32-class) into a 128-lane x NT-column fp32
 // accumulator in TMEM; two stages alternate so the gather of one overlaps the MMAs of the other.  The epilogue reads
-// TMEM (lane = ci, column = co) and adds into dW with fp32 atomics (several row chunks share a tile).
+// TMEM (lane = ci, column = co).  Several row chunks share a tile: with a `partial` buffer every chunk stores its tile
+// into its own slot and wgrad_reduce_kernel adds the slots in ascending order (bit-reproducible gradients); without
+// one the chunks add into dW with fp32 atomics (order varies run to run).
 #include <cuda_bf16.h>
 
 #include "conv_common.cuh"
@@ -106,7 +108,8 @@ __device__ __forceinline__ void store_split8(uint32_t plane_hi, int r, int c16, 
 __device__ int g_wg_abort = 0;
 
 __global__ void __launch_bounds__(wg::THREADS, 1)
-conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta, int tiles_ci, int tiles_co) {
+conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict__ partial, int rows_per_cta, int tiles_ci,
+                     int tiles_co) {
   using namespace wg;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -130,7 +133,14 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta,
   // of active sites, and chunks cut from the capacity would leave most CTAs without rows
   rows_per_cta = ((n + (int)gridDim.x - 1) / (int)gridDim.x + 63) & ~63;
   const long long rb = (long long)blockIdx.x * rows_per_cta;
-  if (rb >= n) return;
+  // deterministic mode: this chunk's slot of the partial buffer, laid out like dW
+  float* pslot = partial ? partial + (size_t)blockIdx.x * a.K * a.cin * a.cout : nullptr;
+  if (rb >= n) {
+    if (pslot)                                        // a chunk without rows still owns (and zeroes) its tile
+      for (int e = tid; e < cin_t * cout_t; e += THREADS)
+        pslot[((size_t)k * a.cin + ci0 + e / cout_t) * a.cout + co0 + e % cout_t] = 0.f;
+    return;
+  }
   const int row_begin = (int)rb, row_end = (int)min((long long)n, rb + rows_per_cta);
 
   if (tid == 0) {
@@ -247,9 +257,13 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!ok && tid == 0) atomicAdd(&g_wg_abort, 1);
   // ---- epilogue: TMEM lane = ci, column = co; warps 0-3 own the four lane quarters
+  if (pslot && it == 0) {                              // no pair in this chunk: the slot still has to be defined
+    for (int e = tid; e < cin_t * cout_t; e += THREADS)
+      pslot[((size_t)k * a.cin + ci0 + e / cout_t) * a.cout + co0 + e % cout_t] = 0.f;
+  }
   if (it > 0 && ok && warp < 4) {
     const int ci = warp * 32 + lane;
-    float* dwk = dw + ((size_t)k * a.cin + ci0 + ci) * a.cout + co0;
+    float* dwk = (pslot ? pslot : dw) + ((size_t)k * a.cin + ci0 + ci) * a.cout + co0;
     for (int c0 = 0; c0 < NT; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
@@ -258,7 +272,10 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, int rows_per_cta,
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float x = __uint_as_float(v[j]);
-          if (c0 + j < cout_t && x != 0.f) atomicAdd(dwk + c0 + j, x);
+          if (c0 + j < cout_t) {
+            if (pslot) dwk[c0 + j] = x;
+            else if (x != 0.f) atomicAdd(dwk + c0 + j, x);
+          }
         }
       }
     }
@@ -274,7 +291,19 @@ bool wgrad_tc_supported(const ConvArgs& a) {
          a.out_stride % 4 == 0 && ((((uintptr_t)a.in) | ((uintptr_t)a.out)) & 15) == 0;
 }
 
-int conv_wgrad_tc(const ConvArgs& a, float* dw, cudaStream_t stream) {
+// row chunks (= partial slots) of a launch
+int conv_wgrad_tc_chunks(const ConvArgs& a) {
+  const int tiles = a.K * ceil_div(a.cin, 128) * ceil_div(a.cout, 128);
+  int chunks = ceil_div((int64_t)kNumSMs * 4, tiles);
+  const int max_chunks = ceil_div(a.n_cap, 1024);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int rows_per_cta = ceil_div(a.n_cap, chunks);
+  rows_per_cta = ceil_div(rows_per_cta, 64) * 64;
+  return ceil_div(a.n_cap, rows_per_cta);
+}
+
+int conv_wgrad_tc(const ConvArgs& a, float* dw, float* partial, cudaStream_t stream) {
   if (a.n_cap <= 0) return 0;
   static bool configured = false;
   if (!configured) {
@@ -291,7 +320,7 @@ int conv_wgrad_tc(const ConvArgs& a, float* dw, cudaStream_t stream) {
   int rows_per_cta = ceil_div(a.n_cap, chunks);
   rows_per_cta = ceil_div(rows_per_cta, 64) * 64;
   chunks = ceil_div(a.n_cap, rows_per_cta);
-  conv_wgrad_tc_kernel<<<dim3(chunks, tiles), wg::THREADS, wg::SMEM, stream>>>(a, dw, rows_per_cta, tiles_ci, tiles_co);
+  conv_wgrad_tc_kernel<<<dim3(chunks, tiles), wg::THREADS, wg::SMEM, stream>>>(a, dw, partial, rows_per_cta, tiles_ci, tiles_co);
   FD_LAUNCHED();
   return 0;
 }

@@ -104,6 +104,8 @@ SIGNATURES = {
     "fd_rulebook_transpose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p]),
     "fd_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]),
+    "fd_conv_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
+    "fd_conv_wgrad_det": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "fd_bn_workspace_bytes": (C.c_size_t, [C.c_int]),
     "fd_bn_train_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

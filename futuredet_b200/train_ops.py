@@ -75,6 +75,18 @@ def Rulebook_pair_num(rb):
 
 
 # ------------------------------------------------------------------------------------------ weight gradients
+DETERMINISTIC_WGRAD = True      # per-chunk partial tiles + ordered reduce (bit-reproducible); False: fp32 atomics
+
+
+def _run_wgrad(lib, d, dw, what):
+    if DETERMINISTIC_WGRAD:
+        need = lib.fd_conv_wgrad_workspace_bytes(C.byref(d))
+        ws = _workspace(dw.device, max(int(need), 256))
+        L.check(lib.fd_conv_wgrad_det(C.byref(d), _ptr(dw), _ptr(ws), ws.numel(), _stream()), what)
+    else:
+        L.check(lib.fd_conv_wgrad(C.byref(d), _ptr(dw), _stream()), what)
+
+
 def sparse_conv_wgrad(x, dy, rb, dw, precision="fp32"):
     """dw [K,Cin,Cout] += sum over rulebook pairs of x[i]^T dy[o] (dw must be zeroed by the caller)."""
     lib = L.load()
@@ -92,7 +104,7 @@ def sparse_conv_wgrad(x, dy, rb, dw, precision="fp32"):
     d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
     d.out_map = L.OUTMAP_IDENTITY
     d.precision = L.PRECISIONS[precision]
-    L.check(lib.fd_conv_wgrad(C.byref(d), _ptr(dw), _stream()), "fd_conv_wgrad(sparse)")
+    _run_wgrad(lib, d, dw, "fd_conv_wgrad(sparse)")
     return dw
 
 
@@ -115,7 +127,7 @@ def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False, precision=
     d.out_map = L.OUTMAP_IDENTITY
     d.n_out_cap = B * H * W if transposed else B * Ho * Wo
     d.precision = L.PRECISIONS[precision]
-    L.check(lib.fd_conv_wgrad(C.byref(d), _ptr(dw), _stream()), "fd_conv_wgrad(conv2d)")
+    _run_wgrad(lib, d, dw, "fd_conv_wgrad(conv2d)")
     return dw
 
 

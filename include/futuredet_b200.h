@@ -248,6 +248,11 @@ int fd_rulebook_transpose(const int32_t* d_nbr, int nbr_stride, const int32_t* d
  * (both operands MN-major, 3-term bf16 split, fp32 accumulation in TMEM) where the rows allow it (Cin, Cout multiples
  * of 8, 16-byte aligned rows, identity output map), the CUDA-core kernel otherwise.                            */
 int fd_conv_wgrad(const fd_conv_desc* desc, float* d_dw, void* stream);
+/* Same gradient, bit-reproducible: every row chunk of a (kernel offset, Cin x Cout) tile stores its partial tile into
+ * its own slot of d_workspace and an ordered reduce adds the slots into d_dw (no floating-point atomics anywhere;
+ * torch autograd over cuDNN / spconv makes no such promise).  fd_conv_wgrad_workspace_bytes(desc) sizes the buffer. */
+size_t fd_conv_wgrad_workspace_bytes(const fd_conv_desc* desc);
+int fd_conv_wgrad_det(const fd_conv_desc* desc, float* d_dw, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* BatchNorm1d/2d in training mode over the first n rows of x [n, C] (det3d/models/utils/norm.py:59-64 ->
  * torch.nn.BatchNorm*: biased batch variance for normalisation, unbiased for the running estimate).

@@ -128,6 +128,20 @@ def test_sparse_conv_backward(cuda, cin, cout, strided):
     dw3 = torch.zeros((27, cin, cout), device=cuda)            # tcgen05 arm (CUDA-core kernel when Cin % 8 != 0)
     T.sparse_conv_wgrad(xg, gg, rb, dw3, precision="bf16x3")
     close(dw3, wr.grad, 3e-4, "wgrad bf16x3")
+    # deterministic accumulation (per-chunk partial tiles + ordered reduce): bit-identical run to run, on both arms,
+    # and equal (to rounding) to the atomics path
+    for prec, first in (("fp32", dw), ("bf16x3", dw3)):
+        again = torch.zeros((27, cin, cout), device=cuda)
+        T.sparse_conv_wgrad(xg, gg, rb, again, precision=prec)
+        assert torch.equal(again, first), "weight gradient not bit-reproducible (%s)" % prec
+    assert T.DETERMINISTIC_WGRAD
+    T.DETERMINISTIC_WGRAD = False
+    try:
+        dwa = torch.zeros((27, cin, cout), device=cuda)
+        T.sparse_conv_wgrad(xg, gg, rb, dwa, precision="bf16x3")
+    finally:
+        T.DETERMINISTIC_WGRAD = True
+    close(dwa, dw3, 1e-5, "atomics vs ordered reduce")
     wg = w.to(cuda)
     if strided:
         nbr_t = T.rulebook_transpose(rb, cap)
