@@ -61,7 +61,7 @@ def build_library(force=False, verbose=False):
             if log:
                 sys.stderr.write(log)
     if force or _stale(LIB_PATH, objs):
-        cmd = [NVCC, "-shared", "-o", LIB_PATH] + objs + ARCH_FLAGS + ["-Xcompiler", "-fPIC", "-lcuda"]
+        cmd = [NVCC, "-shared", "-o", LIB_PATH] + objs + ARCH_FLAGS + ["-Xcompiler", "-fPIC"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -1009,6 +1009,23 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: the library must load (and export its symbols)
+// on a machine without libcuda.so.1 -- the CPU-only build / ABI checks
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
 static int pick_nt(int cout) { return cout >= 128 ? 128 : cout >= 64 ? 64 : cout >= 32 ? 32 : 16; }
 static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -1085,7 +1102,9 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
     const cuuint64_t strides[1] = {(cuuint64_t)a.in_stride * 4};
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, 1};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = cuTensorMapEncodeTiled(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.in, dims, strides, box, estr,
+    EncodeTiledFn enc = encode_tiled_fn();
+    FD_REQUIRE(enc != nullptr, "fd_conv_forward: the CUDA driver does not export cuTensorMapEncodeTiled");
+    CUresult cr = enc(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.in, dims, strides, box, estr,
                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS)
@@ -1111,7 +1130,9 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
                                    (cuuint64_t)a.in_stride * 4 * a.Win * a.Hin};
     const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = cuTensorMapEncodeTiled(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.in, dims, strides, box, estr,
+    EncodeTiledFn enc = encode_tiled_fn();
+    FD_REQUIRE(enc != nullptr, "fd_conv_forward: the CUDA driver does not export cuTensorMapEncodeTiled");
+    CUresult cr = enc(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.in, dims, strides, box, estr,
                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS)
