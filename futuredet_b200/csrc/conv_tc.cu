@@ -63,6 +63,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // waiter reports which barrier starved, raises g_tc_abort and gives up; every other waiter then falls through
 // too, the kernel drains (its output is garbage) and conv_forward_tc() turns the flag into an error.
 __device__ int g_tc_abort = 0;
+__device__ long long g_tc_timeout = 2000000000LL;      // clock cycles; raised for runs under compute-sanitizer (10-100x slower)
 // FD_TC_DEBUG & 32: block 0 records clock64() timestamps of its pipeline events (perf triage only)
 constexpr int TC_TRACE_N = 8192;
 __device__ long long g_tc_trace[4][TC_TRACE_N];
@@ -88,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
         if (*(volatile int*)&g_tc_abort) return;
         const long long now = clock64();
         if (t0 == 0) t0 = now;
-        else if (now - t0 > 2000000000LL) {
+        else if (now - t0 > g_tc_timeout) {
           if (atomicAdd(&g_tc_abort, 1) < 8)
             printf("futuredet_b200: mbarrier wait timed out (tag %d, block %d, thread %d, bar 0x%x, parity %u)\n", tag,
                    (int)blockIdx.x, (int)threadIdx.x, bar, parity);
@@ -220,7 +221,7 @@ __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity, int tag
       if (*(volatile int*)&g_tc_abort) return;
       const long long now = clock64();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000LL) {
+      else if (now - t0 > g_tc_timeout) {
         if (atomicAdd(&g_tc_abort, 1) < 8)
           printf("futuredet_b200: mbarrier spin timed out (tag %d, block %d, thread %d, bar 0x%x, parity %u)\n", tag,
                  (int)blockIdx.x, (int)threadIdx.x, bar, parity);
@@ -1171,6 +1172,10 @@ int fd_debug_set_tc(int key, int value) {
     case 4: fd::g_l1[1] = value; return 0;
     case 5: fd::g_tma = value; return 0;
     case 6: fd::g_tma_dense = value; return 0;
+    case 7: {                                     // watchdog of the mbarrier waits, in units of 2^30 cycles (0: ~never)
+      const long long v = value > 0 ? (long long)value << 30 : (1LL << 62);
+      return (int)cudaMemcpyToSymbol(fd::g_tc_timeout, &v, sizeof(v));
+    }
   }
   return -1;
 }
