@@ -319,6 +319,35 @@ def cudnn_bar(model, dev, B):
     return out
 
 
+def stress_bench(args, dev):
+    """BASELINE configs[4]: mixed car + pedestrian heads (two SepHeads, center_head.py:351-372), 7-timestep forecast_n3
+    heads, 500k-point dense scenes, forward only; 2 scenes per step per GPU, same timing rules as the main metric."""
+    import futuredet_b200 as fb
+    torch.manual_seed(3)
+    cfg = model_cfg(timesteps=7)
+    cfg["bbox_head"]["tasks"] = [dict(num_class=1, class_names=["car"]), dict(num_class=1, class_names=["pedestrian"])]
+    m = fb.build_detector(cfg).eval().set_precision(args.precision).to(dev).configure_voxelizer(VOXEL_CFG)
+    scenes = [synth_scene(590000, seed=70 + i) for i in range(2)]
+    pts = torch.from_numpy(np.concatenate(scenes)).to(dev)
+    off = torch.tensor(np.r_[0, np.cumsum([len(sc) for sc in scenes])], dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            m.forward_points(pts, off)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 6
+        e0.record()
+        for _ in range(reps):
+            flush.zero_()
+            m.forward_points(pts, off)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return dict(workload="pedestrian_forecast_n3-style mixed car+ped heads, 2 x %d-pt scenes per step, fwd-only "
+                         "(BASELINE configs[4])" % (pts.shape[0] // 2), ms_per_step=ms, scenes_per_s_per_gpu=2 / (ms / 1e3))
+
+
 def train_bench(args, rank, world, dev):
     """BASELINE configs[2]/[3]: forecast_n3 (7-timestep heads) forward + backward (+ AdamW step).  configs[2] (one GPU):
     a single 305k-point sample per step; configs[3] (N GPUs): 4 samples per GPU per step (batch 32 at 8 GPUs,
@@ -475,6 +504,7 @@ def run_gpu(args, rank, world, local):
         one = [(p[:int(o[1])].contiguous(), o[:2].contiguous()) for p, o in pool_dev]
         ms_b1, _ = timed(lambda i: (flush.zero_(), model.forward_points(*one[i % n_pool]))[1])
         bar = cudnn_bar(model, dev, min(B, 4)) if rank == 0 and not args.no_cudnn_bar else None
+        stress = stress_bench(args, dev) if rank == 0 else None
     train_info = None
     if args.train_steps > 0:
         pool_dev.clear()
@@ -526,6 +556,8 @@ def run_gpu(args, rank, world, local):
                 cpu_baseline=cpu_baseline)
     if bar is not None:
         line["dense_bar"] = bar
+    if stress is not None:
+        line["stress_500k_two_task"] = stress
     if train_info is not None:
         line["train"] = train_info
     print(json.dumps(line))

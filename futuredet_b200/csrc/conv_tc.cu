@@ -34,6 +34,9 @@ constexpr int TC_BM = 128;
 // stages in flight in the same shared memory).  Both are parity-green; measured on the 4-scene forward, 64 is faster
 // (14.6 ms vs 18.5 ms): the per-stage hand-shake cost outweighs the deeper ring.
 #define FD_TC_BK 64
+#ifndef FD_TC_SB2_MIN_NT
+#define FD_TC_SB2_MIN_NT 128     // N tiles at least this wide use a 2-slot weight ring (the rest of shared memory is A ring)
+#endif
 constexpr int TC_BK = FD_TC_BK;
 constexpr int TC_ROWB = TC_BK * 2;        // bytes of one stage row (one swizzle atom row)
 constexpr int TC_CHUNKS = TC_ROWB / 16;   // 16-byte chunks per row
@@ -402,7 +405,8 @@ struct TcArgs {
   int T;                     // M tiles per super-tile (weight reuse factor)
   int split;                 // 1: bf16x3, 0: single-pass bf16
   int dbg;                   // FD_TC_DEBUG ablation bits (perf triage only): 1 no A gather, 2 no MMA, 4 no B copy, 8 no stores
-  int sa;                    // A ring slots in use (<= TcCfg::SA); fewer slots leave more of the SM's 228 KB to L1
+  int sa;                    // A ring slots in use; fewer slots leave more of the SM's 228 KB to L1
+  int sb;                    // B (weight) ring slots in use
   int l1;                    // 1: gather through L1 (cp.async.ca)
   int tma;                   // 0: per-thread cp.async gather; 1: TMA gather4 (wide split-bf16 inputs);
                              // 2: dense 2-D stride-1 convs, TMA TILE loads: an M tile is a bw x bh pixel patch and
@@ -415,7 +419,7 @@ struct TcArgs {
 template <int NT> struct TcCfg {
   static constexpr int A_BYTES = 2 * TC_A_PLANE;
   static constexpr int B_BYTES = 2 * NT * TC_ROWB;
-  static constexpr int SB = (TC_BK == 64 && NT >= 128) ? 2 : 4;   // B ring slots (weights are requested SB-1 K stages ahead)
+  static constexpr int SB = (TC_BK == 64 && NT >= FD_TC_SB2_MIN_NT) ? 2 : 4;   // B ring slots (weights are requested SB-1 K stages ahead)
   // NT <= 64: the split products A_hi*B_hi and A_hi*B_lo are issued as ONE MMA of width 2*NT against the adjacent
   // [B_hi | B_lo] planes (each MMA re-reads its whole A tile from shared memory, which is what bounds narrow tiles),
   // so a tile owns two accumulator column blocks that the epilogue adds.
@@ -454,7 +458,7 @@ template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs t) {
   using Cfg = TcCfg<NT>;
-  constexpr int SB = Cfg::SB;
+  const int SB = t.sb;
   const int SA = t.sa;
   constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, NT);
   constexpr uint32_t IDESC2 = umma_idesc_bf16(TC_BM, Cfg::FUSE_N ? 2 * NT : NT);
@@ -1037,24 +1041,37 @@ static int g_l1[2] = {0, 0};       // gather through L1 [sparse, dense]
 static int g_tma = 0;              // TMA gather4 producer where the layer allows it (measured slower than the cp.async
                                    // gather: ~6 cycles per 128-byte row in the copy engine vs ~4 through the LSU)
 static int g_tma_dense = 1;        // TMA tile loads for dense stride-1 2-D convolutions
+static int g_dense_ring[2] = {0, 0};   // A / B ring slots of the TMA tile path (0: the per-NT defaults)
 
 template <int NT>
 static int launch_tc(TcArgs& t, cudaStream_t stream) {
   using Cfg = TcCfg<NT>;
   static int configured_sa = 0;
   const int cls = t.c.mode == FD_GATHER_TABLE ? 0 : 1;
-  int sa = Cfg::SA;
+  int sa = Cfg::SA, sb = Cfg::SB;
   if (g_sa_cap[cls] > 0 && g_sa_cap[cls] < sa) sa = g_sa_cap[cls] < TC_GROUPS ? TC_GROUPS : g_sa_cap[cls];
+  if (t.tma == 2 && g_dense_ring[0] > 0 && g_dense_ring[1] > 0) {
+    // TMA tile producer (one thread, no per-group slots): the ring split between A and B stages is free
+    sa = g_dense_ring[0]; sb = g_dense_ring[1];
+    const size_t budget = (size_t)Cfg::SA * Cfg::A_BYTES + (size_t)Cfg::SB * Cfg::B_BYTES;
+    auto need = [&](int a_, int b_) { return (size_t)a_ * Cfg::A_BYTES + (size_t)b_ * Cfg::B_BYTES + (size_t)(a_ + b_) * 16; };
+    while (sb > 1 && need(sa, sb) > budget) --sb;
+    while (sa > 1 && need(sa, sb) > budget) --sa;
+  }
   t.sa = sa;
+  t.sb = sb;
   t.l1 = g_l1[cls];
-  const size_t smem = Cfg::SMEM - (size_t)(Cfg::SA - sa) * Cfg::A_BYTES;
-  if (configured_sa != sa) {
+  size_t smem = Cfg::SMEM - (size_t)(Cfg::SA - sa) * Cfg::A_BYTES;
+  if (sb != Cfg::SB)
+    smem = Cfg::SMEM - ((size_t)Cfg::SA * Cfg::A_BYTES + (size_t)Cfg::SB * Cfg::B_BYTES) +
+           ((size_t)sa * Cfg::A_BYTES + (size_t)sb * Cfg::B_BYTES + (size_t)(sa + sb) * 16);
+  if (configured_sa != sa * 100 + sb) {
     FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     // shared-memory carve-out just large enough for this launch: the rest of the 228 KB is L1
     int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;
     if (pct > 100) pct = 100;
     FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    configured_sa = sa;
+    configured_sa = sa * 100 + sb;
   }
   // weight reuse factor: as many M tiles per weight fetch as TMEM allows while keeping >= one unit per SM (a cost model
   // that also counted the wave tail picked smaller T and measured slower: the extra weight traffic outweighs the tail)
@@ -1172,6 +1189,8 @@ int fd_debug_set_tc(int key, int value) {
     case 4: fd::g_l1[1] = value; return 0;
     case 5: fd::g_tma = value; return 0;
     case 6: fd::g_tma_dense = value; return 0;
+    case 8: fd::g_dense_ring[0] = value; return 0;
+    case 9: fd::g_dense_ring[1] = value; return 0;
     case 7: {                                     // watchdog of the mbarrier waits, in units of 2^30 cycles (0: ~never)
       const long long v = value > 0 ? (long long)value << 30 : (1LL << 62);
       return (int)cudaMemcpyToSymbol(fd::g_tc_timeout, &v, sizeof(v));
