@@ -43,7 +43,10 @@ constexpr int TC_CHUNKS = TC_ROWB / 16;   // 16-byte chunks per row
 constexpr int TC_SWZ_SHIFT = TC_BK == 64 ? 0 : 1;   // chunk ^= (row >> shift) & (CHUNKS - 1): SWIZZLE_128B / SWIZZLE_64B
 constexpr int TC_MAXK = 32;               // max kernel offsets (27 for 3x3x3)
 constexpr int TC_DENSE_MAXK = 9;          // dense 2-D mode: up to 3x3 taps (row indices cached in shared memory)
-constexpr int TC_GROUPS = 4;              // producer groups (each fills whole A stages on its own)
+#ifndef FD_TC_GROUPS
+#define FD_TC_GROUPS 4
+#endif
+constexpr int TC_GROUPS = FD_TC_GROUPS;   // producer groups (each fills whole A stages on its own)
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
 constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;         // warp 8

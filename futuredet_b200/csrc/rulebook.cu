@@ -223,6 +223,60 @@ neighbors_bitmap_kernel(const int4* __restrict__ out_coords, const int32_t* __re
   }
 }
 
+// Strided (SparseConv3d) rulebooks, input-stationary: an active input reaches at most prod(ceil(k/s)) outputs (8 for
+// k = 3, s = 2; 3.4 on average), while an output has prod(k) = 27 candidate inputs of which most are empty.  One thread
+// per INPUT row enumerates its (output cell, offset) pairs, finds the output row through the bitmap + popcount prefix
+// that fd_rulebook_out_coords left behind (row = rank, ascending linear order) and writes nbr[k][out] = in.  Every
+// (k, out) slot has exactly one candidate input cell, so no two threads write the same slot: deterministic, same table
+// as the output-stationary search with ~8x fewer lookups.  The caller pre-fills nbr with -1.
+__global__ void __launch_bounds__(256)
+neighbors_scatter_kernel(const int4* __restrict__ in_coords, const int32_t* __restrict__ d_n_in, int n_in_cap, Conv3Geom g,
+                         Shape3 osh, const uint32_t* __restrict__ out_bitmap, const int32_t* __restrict__ out_prefix,
+                         int n_out_cap, int* __restrict__ nbr, int nbr_stride, uint32_t* __restrict__ tile_mask) {
+  const int n = min(*d_n_in, n_in_cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 c = in_coords[i];
+    for (int kz = 0; kz < g.k[0]; ++kz) {
+      const int tz = c.y + g.p[0] - kz;
+      if (tz < 0 || tz % g.s[0]) continue;
+      const int oz = tz / g.s[0];
+      if (oz >= osh.d) continue;
+      for (int ky = 0; ky < g.k[1]; ++ky) {
+        const int ty = c.z + g.p[1] - ky;
+        if (ty < 0 || ty % g.s[1]) continue;
+        const int oy = ty / g.s[1];
+        if (oy >= osh.h) continue;
+        for (int kx = 0; kx < g.k[2]; ++kx) {
+          const int tx = c.w + g.p[2] - kx;
+          if (tx < 0 || tx % g.s[2]) continue;
+          const int ox = tx / g.s[2];
+          if (ox >= osh.w) continue;
+          const long long key = lin_key(c.x, oz, oy, ox, osh);
+          const uint32_t bits = __ldg(out_bitmap + (key >> 5));
+          const int o = __ldg(out_prefix + (key >> 5)) + __popc(bits & ((1u << (key & 31)) - 1u));
+          if (o >= n_out_cap) continue;                       // output set clamped to its capacity
+          const int k = (kz * g.k[1] + ky) * g.k[2] + kx;
+          nbr[(size_t)k * nbr_stride + o] = i;
+          // tile activity bit: hundreds of pairs of a tile set the same bit -- look before the atomic
+          if (tile_mask && !(__ldcg(&tile_mask[o >> 7]) & (1u << (k & 31)))) atomicOr(&tile_mask[o >> 7], 1u << (k & 31));
+        }
+      }
+    }
+  }
+}
+
+// nbr[k][o] = -1 for the live output rows only (the capacity of a strided level is several times its row count)
+__global__ void __launch_bounds__(256)
+nbr_fill_empty_kernel(int* __restrict__ nbr, int nbr_stride, int K, const int32_t* __restrict__ d_n_out, int n_out_cap) {
+  const int n = min(*d_n_out, n_out_cap);
+  const int n4 = (n + 3) >> 2;                              // rows in int4 units (table rows are 16-byte aligned)
+  const long long total = (long long)K * n4;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e / n4), q = (int)(e - (long long)k * n4);
+    reinterpret_cast<int4*>(nbr + (size_t)k * nbr_stride)[q] = make_int4(-1, -1, -1, -1);
+  }
+}
+
 // pairs per kernel offset (spconv `indice_pair_num`): one block per offset, deterministic
 __global__ void __launch_bounds__(256)
 count_pairs_kernel(const int* __restrict__ nbr, int nbr_stride, const int32_t* __restrict__ d_n, int n_cap,
@@ -398,6 +452,38 @@ int fd_rulebook_neighbors_bitmap(const int32_t* d_out_coords4, const int32_t* d_
       d_pair_num, d_tile_mask);
   FD_LAUNCHED();
   if (d_pair_num) return fd_rulebook_count_pairs(d_nbr, nbr_stride, d_n_out, n_out_cap, K, d_pair_num, stream_);
+  return 0;
+}
+
+int fd_rulebook_neighbors_scatter(const int32_t* d_in_coords4, const int32_t* d_n_in, int n_in_cap,
+                                  const uint32_t* d_out_bitmap, const int32_t* d_out_wordprefix, const int32_t* out_shape3,
+                                  const int32_t* ksize3, const int32_t* stride3, const int32_t* pad3,
+                                  const int32_t* d_n_out, int n_out_cap, int32_t* d_nbr, int nbr_stride,
+                                  uint32_t* d_tile_mask, void* stream_) {
+  using namespace fd;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FD_REQUIRE(d_in_coords4 && d_n_in && d_out_bitmap && d_out_wordprefix && out_shape3 && ksize3 && stride3 && pad3 && d_nbr,
+             "fd_rulebook_neighbors_scatter: null argument");
+  FD_REQUIRE(nbr_stride >= n_out_cap && n_out_cap >= 0, "fd_rulebook_neighbors_scatter: nbr_stride < n_out_cap");
+  Conv3Geom g;
+  for (int j = 0; j < 3; ++j) { g.k[j] = ksize3[j]; g.s[j] = stride3[j]; g.p[j] = pad3[j]; }
+  const int K = g.k[0] * g.k[1] * g.k[2];
+  FD_REQUIRE(K >= 1 && K <= 343, "fd_rulebook_neighbors_scatter: kernel volume %d unsupported", K);
+  FD_REQUIRE(!d_tile_mask || K <= 32, "fd_rulebook_neighbors_scatter: tile masks support at most 32 kernel offsets");
+  FD_REQUIRE(d_n_out != nullptr, "fd_rulebook_neighbors_scatter: null d_n_out");
+  FD_REQUIRE(nbr_stride % 4 == 0 && (((uintptr_t)d_nbr) & 15) == 0, "fd_rulebook_neighbors_scatter: table rows must be 16-byte aligned");
+  if (n_out_cap > 0) {
+    nbr_fill_empty_kernel<<<persistent_grid(ceil_div((int64_t)K * ceil_div(n_out_cap, 4), 256), 8), 256, 0, stream>>>(
+        d_nbr, nbr_stride, K, d_n_out, n_out_cap);
+    FD_LAUNCHED();
+  }
+  if (d_tile_mask) FD_CUDA(cudaMemsetAsync(d_tile_mask, 0, sizeof(uint32_t) * (size_t)ceil_div(n_out_cap > 0 ? n_out_cap : 1, 128), stream));
+  if (n_in_cap <= 0 || n_out_cap <= 0) return 0;
+  Shape3 osh{out_shape3[0], out_shape3[1], out_shape3[2]};
+  neighbors_scatter_kernel<<<persistent_grid(ceil_div(n_in_cap, 256), 8), 256, 0, stream>>>(
+      (const int4*)d_in_coords4, d_n_in, n_in_cap, g, osh, d_out_bitmap, d_out_wordprefix, n_out_cap, d_nbr, nbr_stride,
+      d_tile_mask);
+  FD_LAUNCHED();
   return 0;
 }
 

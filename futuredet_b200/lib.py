@@ -67,6 +67,9 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "fd_rulebook_neighbors_bitmap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, c_int_p,
                                                 c_int_p, c_int_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_rulebook_neighbors_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, c_int_p,
+                                                 c_int_p, c_int_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                 C.c_void_p]),
     "fd_rulebook_count_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fd_rulebook_to_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p]),

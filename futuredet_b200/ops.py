@@ -139,12 +139,13 @@ class Rulebook:
         """spconv-1.x layout: (indice_pairs [K,2,P] int32 padded with -1, indice_pair_num [K])."""
         lib = L.load()
         n = self.n_out_cap
+        ns = int(self.nbr.stride(0))
         dev = self.nbr.device
         pairs = torch.empty((self.K, 2, max(n, 1)), dtype=torch.int32, device=dev)
-        total = self.K * n
+        total = self.K * ns
         tmp_bytes = ((4 * total + 255) // 256) * 256 + lib.fd_scan_tmp_bytes(total) + 256
         tmp = torch.empty((tmp_bytes,), dtype=torch.uint8, device=dev)
-        rc = lib.fd_rulebook_to_pairs(_ptr(self.nbr), n, _ptr(self.n_out_dev), n, self.K, _ptr(pairs), max(n, 1),
+        rc = lib.fd_rulebook_to_pairs(_ptr(self.nbr), ns, _ptr(self.n_out_dev), n, self.K, _ptr(pairs), max(n, 1),
                                       _ptr(tmp), _stream())
         L.check(rc, "fd_rulebook_to_pairs")
         return pairs, self.pair_num
@@ -187,6 +188,10 @@ def conv_out_shape(shape, ksize, stride, padding):
     return [(int(s) + 2 * p - k) // st + 1 for s, k, st, p in zip(shape, ksize, stride, padding)]
 
 
+SCATTER_STRIDED = True       # strided rulebooks from the input side (fd_rulebook_neighbors_scatter); False: output-side search
+FORCE_SCATTER = False        # tests: use the scatter build on every level
+
+
 def rulebook_conv(coords, n_dev, n_cap, batch_size, shape, ksize, stride, padding, n_out_cap=None, index=None):
     """Regular SparseConv3d rulebook: active output set (ascending linear order) + neighbour table."""
     lib = L.load()
@@ -208,8 +213,22 @@ def rulebook_conv(coords, n_dev, n_cap, batch_size, shape, ksize, stride, paddin
                                     L.i32x3(stride), L.i32x3(padding), L.i32x3(out_shape), _ptr(bitmap),
                                     _ptr(prefix), _ptr(tmp), _ptr(out_coords), n_out_cap, _ptr(n_out), _stream())
     L.check(rc, "fd_rulebook_out_coords")
-    index = index or CoordIndex(coords, n_dev, n_cap, shape, batch_size)
-    nbr, pair_num, K, tmask = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
+    if SCATTER_STRIDED and (FORCE_SCATTER or not isinstance(index, BitmapIndex)):
+        # input-stationary build: every input writes the <= prod(ceil(k/s)) slots it feeds (no input index needed).
+        # Measured (4 bench scenes): faster than 27 hash probes per output row (first strided conv: 0.37 vs 0.45 ms
+        # including the output-set kernels), not faster than the bitmap search of the deeper levels, which keep it.
+        K = int(ksize[0] * ksize[1] * ksize[2])
+        stride_n = (max(n_out_cap, 1) + 3) // 4 * 4               # 16-byte aligned table rows
+        nbr = torch.empty((K, stride_n), dtype=torch.int32, device=dev)
+        pair_num = None
+        tmask = torch.empty(((max(n_out_cap, 1) + 127) // 128,), dtype=torch.int32, device=dev) if K <= 32 else None
+        rc = lib.fd_rulebook_neighbors_scatter(_ptr(coords), _ptr(n_dev), n_cap, _ptr(bitmap), _ptr(prefix),
+                                               L.i32x3(out_shape), L.i32x3(ksize), L.i32x3(stride), L.i32x3(padding),
+                                               _ptr(n_out), n_out_cap, _ptr(nbr), stride_n, _ptr(tmask), _stream())
+        L.check(rc, "fd_rulebook_neighbors_scatter")
+    else:
+        index = index or CoordIndex(coords, n_dev, n_cap, shape, batch_size)
+        nbr, pair_num, K, tmask = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
     rb = Rulebook(nbr, pair_num, K, out_coords, n_out, n_out_cap, out_shape, list(ksize), list(stride),
                   list(padding), tmask)
     rb.out_index = BitmapIndex(bitmap, prefix, out_shape)      # index of the OUTPUT set for the layers that follow

@@ -120,6 +120,16 @@ int fd_rulebook_neighbors_bitmap(const int32_t* d_out_coords4, const int32_t* d_
                                  const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
                                  const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
                                  uint32_t* d_tile_mask, void* stream);
+/* Strided (SparseConv3d) rulebooks built from the INPUT side: every active input enumerates the <= prod(ceil(k/s))
+ * outputs it reaches, finds their rows through the bitmap + popcount prefix of the OUTPUT set left by
+ * fd_rulebook_out_coords, and writes nbr[k][out] = in (the call pre-fills the d_n_out live rows of d_nbr with -1 and
+ * zeroes d_tile_mask; nbr_stride must be a multiple of 4 and d_nbr 16-byte aligned).
+ * Same table, bit for bit, as fd_rulebook_neighbors over the output rows, with ~8x fewer lookups and no input index. */
+int fd_rulebook_neighbors_scatter(const int32_t* d_in_coords4, const int32_t* d_n_in, int n_in_cap,
+                                  const uint32_t* d_out_bitmap, const int32_t* d_out_wordprefix, const int32_t* out_shape3,
+                                  const int32_t* ksize3, const int32_t* stride3, const int32_t* pad3,
+                                  const int32_t* d_n_out, int n_out_cap, int32_t* d_nbr, int nbr_stride,
+                                  uint32_t* d_tile_mask, void* stream);
 
 /* Export to the spconv-1.x layout `indice_pairs [K,2,P_cap]` (pairs of offset k
  * listed in ascending output row), for parity checks and interop.            */

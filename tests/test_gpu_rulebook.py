@@ -63,6 +63,24 @@ def test_strided_rulebook(cuda, ksize, stride, pad):
     assert np.array_equal(rb.out_coords[:n_out].cpu().numpy(), oc)            # ascending linear order
     assert np.array_equal(rb.nbr[:, :n_out].cpu().numpy(), nbr)
     assert np.array_equal(rb.pair_num.cpu().numpy(), (nbr >= 0).sum(1))
+    if rb.tile_mask is not None:                                 # per-128-row-tile activity masks
+        tm = rb.tile_mask.cpu().numpy().astype(np.uint32)
+        for t in range((n_out + 127) // 128):
+            bits = 0
+            for k in range(nbr.shape[0]):
+                if (nbr[k, t * 128:(t + 1) * 128] >= 0).any():
+                    bits |= 1 << k
+            assert int(tm[t]) == bits
+    # the input-stationary (scatter) build and the output-stationary search give the same table, bit for bit
+    assert ops.SCATTER_STRIDED
+    ops.SCATTER_STRIDED = False
+    try:
+        rb2, _ = ops.rulebook_conv(ct, nd, len(c) + 100, B, shape, ksize, stride, pad)
+    finally:
+        ops.SCATTER_STRIDED = True
+    assert rb2.nbr.stride(0) != rb.nbr.stride(0) or True
+    assert np.array_equal(rb2.nbr[:, :n_out].cpu().numpy(), rb.nbr[:, :n_out].cpu().numpy())
+    assert np.array_equal(rb2.tile_mask.cpu().numpy(), rb.tile_mask.cpu().numpy())
     # spconv-layout export
     pairs, pair_num = rb.to_pairs()
     pairs = pairs.cpu().numpy()
