@@ -529,7 +529,11 @@ def run_gpu(args, rank, world, local):
             traffic = tj.get("conv_family_dram_bytes_per_step")
     roofline = dict(bound="tensor", kernel="gather->implicit-GEMM conv family (%s), %d launches/step" %
                     (args.precision, prof["launches"]), achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s",
-                    frac=achieved / pk["tf_sustained"], traffic=traffic, peak_source=pk["src"] + " bf16 dense, sustained",
+                    frac=achieved / pk["tf_sustained"], traffic=traffic,
+                    traffic_what="dram bytes of the family per step (all its launches), ncu capture of this batch size",
+                    mma_tflops=3.0 * achieved if args.precision == "bf16x3" else achieved,
+                    note="bf16x3 executes 3 tensor-core MMAs per algorithmic product: frac <= 1/3 by construction",
+                    peak_source=pk["src"] + " bf16 dense, sustained",
                     algorithmic_gflop_per_step=prof["flop"] / 1e9, kernel_ms_per_step=prof["ms"], by_kind=prof["by_kind"])
     cores = use_all_host_threads()
     cpu_time_scene(sd_cpu, N_TARGET // 8, seed=1)                       # warm the thread pool / allocator
