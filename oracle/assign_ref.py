@@ -74,6 +74,34 @@ def assign_ref(boxes, classes, num_cls, fm_size, pc_range, voxel_size, osf, over
     return hm, anno, ind, mask, cat
 
 
+TRAJECTORY_CLASS = {"static": 1, "linear": 2, "nonlinear": 3}        # preprocess.py:372-376 (per class name)
+
+
+def synth_trajectories(seed, n):
+    rng = np.random.default_rng(1000 + seed)
+    return np.array(["static", "linear", "nonlinear"])[rng.integers(0, 3, n)]
+
+
+def regroup(boxes, classes, num_cls):
+    """Class-by-class grouping of one task (preprocess.py:417-441 and its trajectory / forecast copies)."""
+    idx = np.concatenate([np.where(np.asarray(classes) == j + 1)[0] for j in range(num_cls)])
+    return np.asarray(boxes, np.float32)[idx], np.asarray(classes)[idx]
+
+
+def trajectory_task(boxes_t, trajectories):
+    """`*_trajectory` targets of timestep t (:573-760): one task, classes static / linear / nonlinear."""
+    cls = np.array([TRAJECTORY_CLASS[t] for t in trajectories], np.int32)
+    return regroup(boxes_t, cls, 3)
+
+
+def forecast_task(boxes_all):
+    """`*_forecast` targets (:762-895): the boxes of ALL timesteps in one 7-class task, class = timestep + 1; the same
+    list is used for every timestep (only radius_mult's (1 + i) factor differs)."""
+    boxes = np.concatenate([np.asarray(b, np.float32) for b in boxes_all])
+    cls = np.concatenate([np.full(len(b), i + 1, np.int32) for i, b in enumerate(boxes_all)])
+    return regroup(boxes, cls, 7)
+
+
 def synth_annotations(seed, n_obj=40, timesteps=3):
     """Car-like boxes on the nuScenes range, some outside it, some degenerate; later timesteps move along the velocity."""
     rng = np.random.default_rng(seed)

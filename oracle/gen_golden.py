@@ -280,6 +280,32 @@ def gen_assign():
             for key in ("hm", "anno_box", "ind", "mask", "cat"):
                 out[key + "_" + tag] = np.stack([tg[key][t][0] for t in range(3)])
             print("assign rm=%d sample %d: %d objects placed at t0" % (radius_mult, sample, int(tg["mask"][0][0].sum())))
+    # sampler_type = "trajectory" (the n3dtf / n3dtfm configs, preprocess.py:573-897): the standard targets plus
+    # `*_trajectory` (one 3-class task: static / linear / nonlinear) and `*_forecast` (one 7-class task: the boxes of all
+    # timesteps, class = timestep) -- same per-task routine on regrouped classes
+    for radius_mult in (False, True):
+        cfg = AttrDict(dict(ASSIGN_CFG, radius_mult=radius_mult, sampler_type="trajectory"))
+        cfg.target_assigner = AttrDict(tasks=None)
+        cfg.target_assigner.tasks = [AttrDict(num_class=1, class_names=["car"])]
+        al = PP.AssignLabel(cfg=cfg)
+        boxes = AR.synth_annotations(2)
+        n = len(boxes[0])
+        traj = AR.synth_trajectories(2, n)
+        res = dict(mode="train", type="NuScenesDataset", lidar=dict(
+            voxels=dict(shape=np.array([1440, 1440, 40]), range=np.array(NUSC_RANGE, np.float32),
+                        size=np.array(NUSC_VOXEL, np.float32)),
+            annotations=dict(gt_boxes=[b.copy() for b in boxes], gt_names=[np.array(["car"] * n)] * 3,
+                             gt_classes=[np.ones(n, np.int32) for _ in range(3)],
+                             gt_trajectory=[traj.copy() for _ in range(3)])))
+        res, _ = al(res, {})
+        tg = res["lidar"]["targets"]
+        tag = "traj%d" % int(radius_mult)
+        for suffix in ("", "_trajectory", "_forecast"):
+            for key in ("hm", "anno_box", "ind", "mask", "cat"):
+                out[key + suffix + "_" + tag] = np.stack([tg[key + suffix][t][0] for t in range(3)])
+        print("assign trajectory rm=%d: %d / %d / %d objects placed at t0 (standard / trajectory / forecast)" %
+              (radius_mult, int(tg["mask"][0][0].sum()), int(tg["mask_trajectory"][0][0].sum()),
+               int(tg["mask_forecast"][0][0].sum())))
     # heat maps are sparse: store them compressed
     np.savez_compressed(os.path.join(OUT, "assign.npz"), **out)
 

@@ -35,6 +35,28 @@ def test_assign_matches_reference_golden(cuda, golden_dir, radius_mult):
         assert np.array_equal(got[..., [0, 1, 2, 6, 7, 8, 9]], want[..., [0, 1, 2, 6, 7, 8, 9]])   # no transcendental: exact
 
 
+@pytest.mark.parametrize("radius_mult", [False, True])
+def test_trajectory_sampler_matches_reference_golden(cuda, golden_dir, radius_mult):
+    """sampler_type "trajectory" (n3dtf / n3dtfm configs): standard + 3-class trajectory + 7-class forecast targets."""
+    g = np.load(os.path.join(golden_dir, "assign.npz"))
+    boxes = AR.synth_annotations(2)
+    traj = AR.synth_trajectories(2, len(boxes[0]))
+    anno = dict(gt_boxes=boxes, gt_classes=[np.ones(len(b), np.int32) for b in boxes], gt_trajectory=[traj] * 3)
+    ex = assign.assign_targets([anno], [dict(num_class=1, class_names=["car"])],
+                               dict(CFG, radius_mult=radius_mult, sampler_type="trajectory"), [1440, 1440, 40], NUSC_RANGE,
+                               NUSC_VOXEL, cuda)
+    tag = "traj%d" % int(radius_mult)
+    for suffix in ("", "_trajectory", "_forecast"):
+        for t in range(3):
+            for key in ("hm", "ind", "mask", "cat"):
+                got = ex[key + suffix][t][0][0].cpu().numpy()
+                want = g[key + suffix + "_" + tag][t]
+                assert got.dtype == want.dtype and np.array_equal(got, want), (key + suffix, t)
+            np.testing.assert_allclose(ex["anno_box" + suffix][t][0][0].cpu().numpy(), g["anno_box" + suffix + "_" + tag][t],
+                                       rtol=2e-6, atol=2e-7)
+    assert ex["hm_forecast"][0][0].shape[1] == 7 and ex["hm_trajectory"][0][0].shape[1] == 3
+
+
 def test_assign_two_tasks_many_objects(cuda):
     """car + pedestrian tasks (BASELINE configs[4] shape): class grouping and per-task local class ids, max_objs cap."""
     rng = np.random.default_rng(3)
