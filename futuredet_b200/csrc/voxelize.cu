@@ -9,10 +9,13 @@
 //       offsets), so the live region (3.7 MB for a 305 k-point scene) stays L2 resident while its points stream by;
 //   K2  bit i of a bitmap = "point i is the first point of its voxel"; an exclusive popcount scan over the bitmap words
 //       (1/32 of the points) turns it into the voxel rank = order of first appearance, without a per-point rank array;
-//   K3  voxels whose per-scene rank >= max_voxels are dropped (:46-47); every surviving point pushes itself onto its
-//       voxel's linked list (one atomicExch on head[voxel]; next[] lives beside the points);
-//   K4  one thread per voxel walks the list, keeps the max_points smallest indices (= the first max_points points in
-//       input order, :51-54) in registers, sums them in that order and divides by the count
+//   K3  voxels whose per-scene rank >= max_voxels are dropped (:46-47); every surviving point registers with its voxel:
+//       the first three arrivals (atomicAdd on the voxel's counter) land in inline slots, later ones are pushed onto
+//       an overflow list (atomicExch on head[voxel]; next[] lives beside the points) -- 1.9 points per voxel on
+//       average, so the reduction rarely has to chase pointers;
+//   K4  one thread per voxel reads the inline slots (and walks the overflow list if there is one), keeps the
+//       max_points smallest indices (= the first max_points points in input order, :51-54) sorted in registers, sums
+//       them in that order and divides by the count
 //       (det3d/models/readers/voxel_encoder.py:20-22), writes features, (b,z,y,x) coordinates (collate.py:199-206)
 //       and num_points.
 // All indices are bit-exact with the reference; no atomics on floats anywhere; the result does not depend on thread
@@ -32,6 +35,7 @@ struct VoxGeom {
 };
 
 constexpr unsigned long long kEmptyWord = ~0ull;   // memset(0xff)
+constexpr int kInline = 3;                         // inline point slots per voxel (the rest goes to the overflow list)
 
 __device__ __forceinline__ int find_scene(const int32_t* s_off, int B, int i) {
   int lo = 0, hi = B;  // offsets[lo] <= i < offsets[hi]
@@ -146,7 +150,8 @@ vox_link_points(int n, const int32_t* __restrict__ boff, int B, VoxGeom g,
                 const unsigned long long* __restrict__ table, const int* __restrict__ pslot,
                 const uint32_t* __restrict__ bits, const int32_t* __restrict__ wordprefix,
                 const int32_t* __restrict__ scene_rank0, const int32_t* __restrict__ out_base,
-                int max_voxels, int* __restrict__ head, int* __restrict__ next, int32_t* __restrict__ coords) {
+                int max_voxels, int* __restrict__ vcnt, int* __restrict__ inl, int* __restrict__ head,
+                int* __restrict__ next, int32_t* __restrict__ coords) {
   extern __shared__ int32_t s_off[];
   int32_t* s_r0 = s_off + (B + 1);
   int32_t* s_base = s_r0 + B;
@@ -170,23 +175,26 @@ vox_link_points(int n, const int32_t* __restrict__ boff, int B, VoxGeom g,
       const int z = (int)(cell / (uint32_t)g.grid[1]);
       reinterpret_cast<int4*>(coords)[vid] = make_int4(b, z, y, x);
     }
-    next[i] = atomicExch(&head[vid], i);          // push onto the voxel's list (order irrelevant: K4 sorts)
+    const int pos = atomicAdd(&vcnt[vid], 1);     // arrival order is irrelevant: K4 sorts by point index
+    if (pos < kInline) inl[(size_t)vid * kInline + pos] = i;
+    else next[i] = atomicExch(&head[vid], i);      // overflow list
   }
 }
 
 // ---- K4 -----------------------------------------------------------------------
 template <int MAXP>
 __global__ void __launch_bounds__(256)
-vox_reduce_mean(const float* __restrict__ pts, int pstride, int num_feat, const int* __restrict__ head,
-                const int* __restrict__ next, int max_points, const int32_t* __restrict__ total,
+vox_reduce_mean(const float* __restrict__ pts, int pstride, int num_feat, const int* __restrict__ vcnt,
+                const int* __restrict__ inl, const int* __restrict__ head, const int* __restrict__ next, int max_points,
+                const int32_t* __restrict__ total,
                 float* __restrict__ feat, int feat_stride, int32_t* __restrict__ npts, float* __restrict__ voxels) {
   const int nv = *total;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     // the max_points smallest point indices of the list, ascending (insertion into a sorted register array)
-    int best[MAXP];
+    int best[MAXP] = {};
     int cnt = 0;
-    for (int idx = head[v]; idx >= 0; idx = next[idx]) {
-      if (cnt == max_points && idx > best[cnt - 1]) continue;
+    auto insert = [&](int idx) {
+      if (cnt == max_points && idx > best[cnt - 1]) return;
       int j = cnt < max_points ? cnt : max_points - 1;
 #pragma unroll
       for (int q = MAXP - 1; q > 0; --q)
@@ -195,7 +203,16 @@ vox_reduce_mean(const float* __restrict__ pts, int pstride, int num_feat, const 
       for (int q = 0; q < MAXP; ++q)
         if (q == j) best[q] = idx;
       if (cnt < max_points) ++cnt;
-    }
+    };
+    const int arrivals = vcnt[v];
+    int in_idx[kInline];
+#pragma unroll
+    for (int q = 0; q < kInline; ++q) in_idx[q] = q < arrivals ? inl[(size_t)v * kInline + q] : -1;
+    const int h = arrivals > kInline ? head[v] : -1;
+#pragma unroll
+    for (int q = 0; q < kInline; ++q)
+      if (in_idx[q] >= 0) insert(in_idx[q]);
+    for (int idx = h; idx >= 0; idx = next[idx]) insert(idx);
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
@@ -233,7 +250,7 @@ vox_reduce_mean(const float* __restrict__ pts, int pstride, int num_feat, const 
 }
 
 struct VoxWorkspace {
-  unsigned long long* table; int* head; int* pslot; int* next; uint32_t* bits; int32_t* wordprefix;
+  unsigned long long* table; int* head; int* vcnt; int* inl; int* pslot; int* next; uint32_t* bits; int32_t* wordprefix;
   int32_t* scene_rank0; int32_t* out_base; int32_t* total_first; void* scan_tmp;
   int64_t cap; size_t bytes;
 };
@@ -252,6 +269,8 @@ static VoxWorkspace carve(void* base, int64_t n, int B, int max_voxels, int max_
   // [table | head] are contiguous and memset to 0xff with one call (empty word / empty list)
   w.table = (unsigned long long*)take(sizeof(unsigned long long) * cap);
   w.head = (int*)take(sizeof(int) * (size_t)B * max_voxels);
+  w.vcnt = (int*)take(sizeof(int) * (size_t)B * max_voxels);                 // memset to 0
+  w.inl = (int*)take(sizeof(int) * (size_t)B * max_voxels * kInline);        // written before read: no memset
   w.pslot = (int*)take(sizeof(int) * (n > 0 ? n : 1));
   w.next = (int*)take(sizeof(int) * (n > 0 ? n : 1));
   w.bits = (uint32_t*)take(sizeof(uint32_t) * words);
@@ -334,7 +353,8 @@ int fd_voxelize_vfe(const float* d_points, int64_t total_points, int point_strid
   FD_REQUIRE((long long)grid3[0] * grid3[1] * grid3[2] < 0x7fffffffLL, "fd_voxelize_vfe: grid of %lld cells does not fit the 32-bit cell key",
              (long long)grid3[0] * grid3[1] * grid3[2]);
   // table and list heads are adjacent in the workspace: one memset covers both
-  FD_CUDA(cudaMemsetAsync(w.table, 0xff, (char*)w.pslot - (char*)w.table, stream));
+  FD_CUDA(cudaMemsetAsync(w.table, 0xff, (char*)w.vcnt - (char*)w.table, stream));
+  FD_CUDA(cudaMemsetAsync(w.vcnt, 0, sizeof(int) * (size_t)B * max_voxels, stream));
   const int threads = 256;
   const int grid_pts = ceil_div(n, threads) > 0 ? ceil_div(n, threads) : 1;   // one block per 256 consecutive points
   const int64_t words = ((int64_t)n + 31) / 32;
@@ -356,15 +376,15 @@ int fd_voxelize_vfe(const float* d_points, int64_t total_points, int point_strid
   if (n > 0) {
     vox_link_points<<<grid_pts, threads, (3 * B + 1) * sizeof(int32_t), stream>>>(
         n, d_batch_offsets, B, g, w.table, w.pslot, w.bits, w.wordprefix, w.scene_rank0, w.out_base,
-        max_voxels, w.head, w.next, d_coords);
+        max_voxels, w.vcnt, w.inl, w.head, w.next, d_coords);
     FD_LAUNCHED();
     const int64_t vcap = (int64_t)B * max_voxels;
     const int grid_vox = ceil_div(vcap < n ? vcap : n, threads);
     if (max_points <= 16)
-      vox_reduce_mean<16><<<grid_vox, threads, 0, stream>>>(d_points, point_stride, num_feat, w.head, w.next, max_points,
+      vox_reduce_mean<16><<<grid_vox, threads, 0, stream>>>(d_points, point_stride, num_feat, w.vcnt, w.inl, w.head, w.next, max_points,
                                                            d_total, d_feat, feat_stride, d_npts, d_voxels);
     else
-      vox_reduce_mean<64><<<grid_vox, threads, 0, stream>>>(d_points, point_stride, num_feat, w.head, w.next, max_points,
+      vox_reduce_mean<64><<<grid_vox, threads, 0, stream>>>(d_points, point_stride, num_feat, w.vcnt, w.inl, w.head, w.next, max_points,
                                                            d_total, d_feat, feat_stride, d_npts, d_voxels);
     FD_LAUNCHED();
   }

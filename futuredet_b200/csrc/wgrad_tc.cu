@@ -17,6 +17,7 @@
 // into its own slot and wgrad_reduce_kernel adds the slots in ascending order (bit-reproducible gradients); without
 // one the chunks add into dW with fp32 atomics (order varies run to run).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "conv_common.cuh"
 
@@ -294,7 +295,8 @@ bool wgrad_tc_supported(const ConvArgs& a) {
 // row chunks (= partial slots) of a launch
 int conv_wgrad_tc_chunks(const ConvArgs& a) {
   const int tiles = a.K * ceil_div(a.cin, 128) * ceil_div(a.cout, 128);
-  int chunks = ceil_div((int64_t)kNumSMs * 4, tiles);
+  static const int waves = getenv("FD_WG_WAVES") ? atoi(getenv("FD_WG_WAVES")) : 4;
+  int chunks = ceil_div((int64_t)kNumSMs * waves, tiles);
   const int max_chunks = ceil_div(a.n_cap, 1024);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -313,13 +315,8 @@ int conv_wgrad_tc(const ConvArgs& a, float* dw, float* partial, cudaStream_t str
   const int tiles_ci = ceil_div(a.cin, 128), tiles_co = ceil_div(a.cout, 128);
   const int tiles = a.K * tiles_ci * tiles_co;
   FD_REQUIRE(tiles <= 65535, "fd_conv_wgrad: K*tiles = %d exceeds the grid limit", tiles);
-  int chunks = ceil_div((int64_t)kNumSMs * 4, tiles);
-  const int max_chunks = ceil_div(a.n_cap, 1024);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  int rows_per_cta = ceil_div(a.n_cap, chunks);
-  rows_per_cta = ceil_div(rows_per_cta, 64) * 64;
-  chunks = ceil_div(a.n_cap, rows_per_cta);
+  const int chunks = conv_wgrad_tc_chunks(a);
+  const int rows_per_cta = ceil_div(ceil_div(a.n_cap, chunks), 64) * 64;
   conv_wgrad_tc_kernel<<<dim3(chunks, tiles), wg::THREADS, wg::SMEM, stream>>>(a, dw, partial, rows_per_cta, tiles_ci, tiles_co);
   FD_LAUNCHED();
   return 0;
