@@ -238,6 +238,31 @@ def conv_profile(model, pts, off):
                 by_kind={k: dict(gflop=v[0] / 1e9, ms=v[1], tflops=v[0] / max(v[1], 1e-9) / 1e9) for k, v in by_kind.items()})
 
 
+def voxelize_spconv_ms(model, pts, off, reps=5):
+    """The second half of BASELINE's metric: voxelize + VFE + sparse backbone (rulebooks included), ms per scene, CUDA
+    events around exactly that prefix of the forward at the benched batch size."""
+    from futuredet_b200 import ops, precision as P
+    c = model.voxel_cfg
+    B = off.numel() - 1
+    grid = ops.grid_size_of(c["range"], c["voxel_size"])
+    fmt = P.act_fmt(model.precision)
+
+    def run():
+        vox = model.voxelize(pts, off)
+        return model.backbone(vox["features"], vox["coords"], B, grid, n_dev=vox["total"], n_cap=vox["coords"].shape[0],
+                              out_fmt=fmt)
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps / B
+
+
 def voxelize_roofline(model, dev, n_scenes=32):
     """HBM roofline of the fused voxelize+VFE family on one batched launch of `n_scenes` scenes (a single 12.5 MB
     scene is below launch latency, SURVEY.md hard part 1): algorithmic bytes 20*N + 40*M over the CUDA-event time."""
@@ -500,6 +525,7 @@ def run_gpu(args, rank, world, local):
         ms_det, _ = timed(step_detect)
         prof = conv_profile(model, *pool_dev[0]) if rank == 0 else None
         vox_roof = voxelize_roofline(model, dev) if rank == 0 else None
+        vs_ms = voxelize_spconv_ms(model, *pool_dev[0]) if rank == 0 else None
         # the reference's own samples_per_gpu = 1: latency-bound single-scene steps, same timing rules
         one = [(p[:int(o[1])].contiguous(), o[:2].contiguous()) for p, o in pool_dev]
         ms_b1, _ = timed(lambda i: (flush.zero_(), model.forward_points(*one[i % n_pool]))[1])
@@ -556,6 +582,7 @@ def run_gpu(args, rank, world, local):
                                  "detections D2H", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(det_bytes[0])),
                 batch1=dict(value=world * args.steps / (ms_b1 / 1e3), unit="scenes/s", ms_per_scene=ms_b1 / args.steps,
                             what="one scene per step per GPU (the reference's samples_per_gpu), points resident"),
+                voxelize_spconv_ms_per_scene=vs_ms,
                 gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_voxelize=vox_roof,
                 cpu_baseline=cpu_baseline)
     if bar is not None:
