@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -67,7 +69,7 @@ def test_bench_reference_arm_contract_two_ranks():
     assert line["higher_is_better"] is True and line["n_gpus"] == 2
 
 
-def _grad_worker(rank, world, port, q):
+def _grad_worker(rank, world, port, q, inline=False):
     from torch import nn
     from futuredet_b200 import train
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -76,7 +78,7 @@ def _grad_worker(rank, world, port, q):
     model = nn.Sequential(nn.Linear(5, 7), nn.BatchNorm1d(7), nn.Linear(7, 3))
     shard.broadcast_parameters(model)                         # ... and leave with rank 0's
     buckets = train.GradBuckets(list(model.parameters()), bucket_bytes=64)      # tiny buckets -> several all-reduces
-    sync = shard.GradSync(buckets)
+    sync = shard.GradSync(buckets, inline=inline)     # inline: the mode captured into the multi-rank CUDA graph
     launched = []
     orig = sync._launch
     sync._launch = lambda i, flat: (launched.append(i), orig(i, flat))[1]
@@ -87,6 +89,8 @@ def _grad_worker(rank, world, port, q):
         buckets.grad(p).fill_(float(rank + 1) * (j + 1))
         buckets.done(p)
     buckets.flush()
+    if inline:
+        assert sync.handles == []                              # nothing left to wait for: already reduced in place
     sync.finish()
     got = [float(p.grad.flatten()[0]) for p in reversed(params)]
     psum = float(sum(p.detach().sum() for p in model.parameters()))
@@ -95,13 +99,15 @@ def _grad_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_gradient_buckets_allreduce_world2():
-    """The training exchange: bucketed all-reduce(sum)/world of the parameter gradients, launched as
-    buckets complete in backward order; parameters broadcast from rank 0 first."""
+@pytest.mark.parametrize("inline", [False, True])
+def test_gradient_buckets_allreduce_world2(inline):
+    """The training exchange: bucketed all-reduce(avg) of the parameter gradients, launched as buckets
+    complete in backward order (asynchronously, or inline on the launching stream = the CUDA-graph mode); parameters
+    broadcast from rank 0 first."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 31500 + (os.getpid() % 2000) + (1000 if inline else 0)
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q, inline)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in procs)
