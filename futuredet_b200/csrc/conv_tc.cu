@@ -260,11 +260,6 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, 
 __device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void* src, uint32_t sz) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
-// same through L1 (.ca): gathered rows stay in the SM's L1 (the part of the 228 KB the CTA does not claim as shared
-// memory), where the neighbouring kernel offsets of the same tile find them again
-__device__ __forceinline__ void cp_async16_sz_ca(uint32_t dst, const void* src, uint32_t sz) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -408,9 +403,6 @@ struct TcArgs {
   int T;                     // M tiles per super-tile (weight reuse factor)
   int split;                 // 1: bf16x3, 0: single-pass bf16
   int dbg;                   // FD_TC_DEBUG ablation bits (perf triage only): 1 no A gather, 2 no MMA, 4 no B copy, 8 no stores
-  int sa;                    // A ring slots in use; fewer slots leave more of the SM's 228 KB to L1
-  int sb;                    // B (weight) ring slots in use
-  int l1;                    // 1: gather through L1 (cp.async.ca)
   int tma;                   // 0: per-thread cp.async gather; 1: TMA gather4 (wide split-bf16 inputs);
                              // 2: dense 2-D stride-1 convs, TMA TILE loads: an M tile is a bw x bh pixel patch and
                              //    every (tap, 64-channel chunk) stage is ONE 4-D box per plane, shifted by the tap,
@@ -461,8 +453,7 @@ template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs t) {
   using Cfg = TcCfg<NT>;
-  const int SB = t.sb;
-  const int SA = t.sa;
+  constexpr int SA = Cfg::SA, SB = Cfg::SB;
   constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, NT);
   constexpr uint32_t IDESC2 = umma_idesc_bf16(TC_BM, Cfg::FUSE_N ? 2 * NT : NT);
   constexpr int ACC = Cfg::ACC_COLS;
@@ -756,22 +747,12 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
           const char* gh = in_b + ch * 2;
           const char* gl = in_lo + ch * 2;
 #pragma unroll
-          if (t.l1) {
 #pragma unroll
-            for (int q = 0; q < PASSES; ++q) {
-              const uint32_t sz = cur[q] >= 0 ? 16u : 0u;
-              const size_t goff = (size_t)(uint32_t)max(cur[q], 0) * row_bytes;
-              cp_async16_sz_ca(dst0 + q * ROWS_PER_PASS * TC_ROWB, gh + goff, sz);
-              cp_async16_sz_ca(dst0 + q * ROWS_PER_PASS * TC_ROWB + TC_A_PLANE, gl + goff, sz);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < PASSES; ++q) {
-              const uint32_t sz = cur[q] >= 0 ? 16u : 0u;
-              const size_t goff = (size_t)(uint32_t)max(cur[q], 0) * row_bytes;
-              cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB, gh + goff, sz);
-              cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB + TC_A_PLANE, gl + goff, sz);
-            }
+          for (int q = 0; q < PASSES; ++q) {
+            const uint32_t sz = cur[q] >= 0 ? 16u : 0u;
+            const size_t goff = (size_t)(uint32_t)max(cur[q], 0) * row_bytes;
+            cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB, gh + goff, sz);
+            cp_async16_sz(dst0 + q * ROWS_PER_PASS * TC_ROWB + TC_A_PLANE, gl + goff, sz);
           }
           cp_async_mbar_arrive_noinc(fbar);
         } else {
@@ -1039,42 +1020,18 @@ static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 
 // perf-triage knobs, settable at run time through fd_debug_set_tc (not part of the documented ABI)
 static int g_dbg = -1;          // FD_TC_DEBUG bits
-static int g_sa_cap[2] = {0, 0};   // A-ring slot cap [sparse, dense] (0: all that fit)
-static int g_l1[2] = {0, 0};       // gather through L1 [sparse, dense]
 static int g_tma = 0;              // TMA gather4 producer where the layer allows it (measured slower than the cp.async
                                    // gather: ~6 cycles per 128-byte row in the copy engine vs ~4 through the LSU)
 static int g_tma_dense = 1;        // TMA tile loads for dense stride-1 2-D convolutions
-static int g_dense_ring[2] = {0, 0};   // A / B ring slots of the TMA tile path (0: the per-NT defaults)
 
 template <int NT>
 static int launch_tc(TcArgs& t, cudaStream_t stream) {
   using Cfg = TcCfg<NT>;
-  static int configured_sa = 0;
-  const int cls = t.c.mode == FD_GATHER_TABLE ? 0 : 1;
-  int sa = Cfg::SA, sb = Cfg::SB;
-  if (g_sa_cap[cls] > 0 && g_sa_cap[cls] < sa) sa = g_sa_cap[cls] < TC_GROUPS ? TC_GROUPS : g_sa_cap[cls];
-  if (t.tma == 2 && g_dense_ring[0] > 0 && g_dense_ring[1] > 0) {
-    // TMA tile producer (one thread, no per-group slots): the ring split between A and B stages is free
-    sa = g_dense_ring[0]; sb = g_dense_ring[1];
-    const size_t budget = (size_t)Cfg::SA * Cfg::A_BYTES + (size_t)Cfg::SB * Cfg::B_BYTES;
-    auto need = [&](int a_, int b_) { return (size_t)a_ * Cfg::A_BYTES + (size_t)b_ * Cfg::B_BYTES + (size_t)(a_ + b_) * 16; };
-    while (sb > 1 && need(sa, sb) > budget) --sb;
-    while (sa > 1 && need(sa, sb) > budget) --sa;
-  }
-  t.sa = sa;
-  t.sb = sb;
-  t.l1 = g_l1[cls];
-  size_t smem = Cfg::SMEM - (size_t)(Cfg::SA - sa) * Cfg::A_BYTES;
-  if (sb != Cfg::SB)
-    smem = Cfg::SMEM - ((size_t)Cfg::SA * Cfg::A_BYTES + (size_t)Cfg::SB * Cfg::B_BYTES) +
-           ((size_t)sa * Cfg::A_BYTES + (size_t)sb * Cfg::B_BYTES + (size_t)(sa + sb) * 16);
-  if (configured_sa != sa * 100 + sb) {
+  static bool configured = false;
+  const size_t smem = Cfg::SMEM;
+  if (!configured) {
     FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    // shared-memory carve-out just large enough for this launch: the rest of the 228 KB is L1
-    int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;
-    if (pct > 100) pct = 100;
-    FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    configured_sa = sa * 100 + sb;
+    configured = true;
   }
   // weight reuse factor: as many M tiles per weight fetch as TMEM allows while keeping >= one unit per SM (a cost model
   // that also counted the wave tail picked smaller T and measured slower: the extra weight traffic outweighs the tail)
@@ -1181,19 +1138,14 @@ int fd_debug_read_tc_trace(long long* out, int role) {
                                    sizeof(long long) * fd::TC_TRACE_N * role, cudaMemcpyDeviceToHost);
 }
 
-/* perf-triage helper (not part of the documented ABI): key 0 = FD_TC_DEBUG bits, 1 / 2 = A-ring slot cap of the
- * sparse / dense launches, 3 / 4 = gather through L1 for sparse / dense launches, 5 = TMA gather4 producer on/off */
+/* perf-triage helper (not part of the documented ABI): key 0 = FD_TC_DEBUG bits, 5 = TMA gather4 producer on/off, 6 = TMA tile loads for dense convs on/off, 7 = mbarrier watchdog
+ * (the ring-size and L1-gather knobs of the round-2 triage were removed again: run-time ring sizes cost the narrow
+ * layers 10 %, gathers through L1 gained nothing) */
 int fd_debug_set_tc(int key, int value) {
   switch (key) {
     case 0: fd::g_dbg = value; return 0;
-    case 1: fd::g_sa_cap[0] = value; return 0;
-    case 2: fd::g_sa_cap[1] = value; return 0;
-    case 3: fd::g_l1[0] = value; return 0;
-    case 4: fd::g_l1[1] = value; return 0;
     case 5: fd::g_tma = value; return 0;
     case 6: fd::g_tma_dense = value; return 0;
-    case 8: fd::g_dense_ring[0] = value; return 0;
-    case 9: fd::g_dense_ring[1] = value; return 0;
     case 7: {                                     // watchdog of the mbarrier waits, in units of 2^30 cycles (0: ~never)
       const long long v = value > 0 ? (long long)value << 30 : (1LL << 62);
       return (int)cudaMemcpyToSymbol(fd::g_tc_timeout, &v, sizeof(v));

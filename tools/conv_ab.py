@@ -20,13 +20,12 @@ pts = torch.from_numpy(np.concatenate(scenes)).to(dev)
 off = torch.tensor(np.r_[0, np.cumsum([len(s) for s in scenes])], dtype=torch.int32, device=dev)
 L = lib.load()
 L.fd_debug_set_tc.argtypes = [C.c_int, C.c_int]
-CONFIGS = [("default", {}), ("dense ring A3 B3", {8: 3, 9: 3}), ("dense ring A2 B4", {8: 2, 9: 4}), ("dense ring A3 B4", {8: 3, 9: 4})]
+CONFIGS = [("default", {})]
 if len(sys.argv) > 2:
     CONFIGS = [(a, eval(a)) for a in sys.argv[2:]]
 with torch.no_grad():
     for name, knobs in CONFIGS:
-        for k in (0, 1, 2, 3, 4, 8, 9):
-            L.fd_debug_set_tc(k, 0)
+        L.fd_debug_set_tc(0, 0)
         L.fd_debug_set_tc(5, 0)
         L.fd_debug_set_tc(6, 1)
         for k, v in knobs.items():
