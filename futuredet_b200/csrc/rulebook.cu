@@ -76,7 +76,8 @@ outset_mark(const int4* __restrict__ coords, const int32_t* __restrict__ d_n, in
           int ox = tx / g.s[2];
           if (ox >= osh.w) continue;
           long long key = lin_key(c.x, oz, oy, ox, osh);
-          atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+          // up to 27 inputs mark the same output cell: look before the atomic (a stale 0 only costs a redundant atomicOr)
+          if (!(__ldcg(&bitmap[key >> 5]) & (1u << (key & 31)))) atomicOr(&bitmap[key >> 5], 1u << (key & 31));
         }
       }
     }
