@@ -43,6 +43,9 @@ constexpr int TC_CHUNKS = TC_ROWB / 16;   // 16-byte chunks per row
 constexpr int TC_SWZ_SHIFT = TC_BK == 64 ? 0 : 1;   // chunk ^= (row >> shift) & (CHUNKS - 1): SWIZZLE_128B / SWIZZLE_64B
 constexpr int TC_MAXK = 32;               // max kernel offsets (27 for 3x3x3)
 constexpr int TC_DENSE_MAXK = 9;          // dense 2-D mode: up to 3x3 taps (row indices cached in shared memory)
+#ifndef FD_TC_SB64
+#define FD_TC_SB64 4                 // weight-ring slots of the 64-column tiles
+#endif
 #ifndef FD_TC_GROUPS
 #define FD_TC_GROUPS 4
 #endif
@@ -414,7 +417,7 @@ struct TcArgs {
 template <int NT> struct TcCfg {
   static constexpr int A_BYTES = 2 * TC_A_PLANE;
   static constexpr int B_BYTES = 2 * NT * TC_ROWB;
-  static constexpr int SB = (TC_BK == 64 && NT >= FD_TC_SB2_MIN_NT) ? 2 : 4;   // B ring slots (weights are requested SB-1 K stages ahead)
+  static constexpr int SB = (TC_BK == 64 && NT >= FD_TC_SB2_MIN_NT) ? 2 : (NT == 64 ? FD_TC_SB64 : 4);   // B ring slots (weights are requested SB-1 K stages ahead)
   // NT <= 64: the split products A_hi*B_hi and A_hi*B_lo are issued as ONE MMA of width 2*NT against the adjacent
   // [B_hi | B_lo] planes (each MMA re-reads its whole A tile from shared memory, which is what bounds narrow tiles),
   // so a tile owns two accumulator column blocks that the epilogue adds.

@@ -62,3 +62,39 @@ def test_graphed_train_step_matches_eager(cuda):
     for k in p_eager:
         err, ref = float((p_graph[k] - p_eager[k]).norm()), float(p_eager[k].norm())
         assert err <= 2e-2 * ref + 1e-4, (k, err, ref)
+
+
+def test_eval_after_training_sees_updated_weights_and_statistics(cuda):
+    """Derived-weight caches (tensor-core packs, d-major first neck conv, folded BatchNorm, fused head convs) must follow
+    the optimizer and the running statistics: inference before training, a few (graph-replayed) training steps, inference
+    again == inference of a FRESH model loaded with the trained state_dict; and frozen parameters do not break the
+    native backward."""
+    from test_gpu_train import build_model
+    from futuredet_b200.synth import synth_targets
+    pts, off = scene_tensors(5, 30000, cuda)
+    ex = synth_targets(1, 180, 180, 3, seed=1)
+    ex = {k: [[t.to(cuda) for t in ts] for ts in v] for k, v in ex.items()}
+    model = build_model(3, cuda).to(cuda).eval()
+    model.configure_voxelizer(VOX)
+    with torch.no_grad():
+        before = {k: v.clone() for k, v in model.forward_points(pts, off)[0].items()}      # fills every cache
+    model.train()
+    for p in model.backbone.conv_input.parameters():
+        p.requires_grad_(False)                                                            # frozen stem
+    tr = train.NativeTrainer(model, precision="bf16x3")
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-2)
+    step = graphs.GraphedTrainStep(tr, max_points=40000, batch_size=1)
+    for _ in range(3):
+        step(ex, pts, off)
+        opt.step()
+    model.eval()
+    with torch.no_grad():
+        after = {k: v.clone() for k, v in model.forward_points(pts, off)[0].items()}
+    fresh = build_model(3, cuda).to(cuda).eval()
+    fresh.load_state_dict(model.state_dict())
+    fresh.configure_voxelizer(VOX)
+    with torch.no_grad():
+        want = fresh.forward_points(pts, off)[0]
+    assert any(float((after[k] - before[k]).abs().max()) > 1e-4 for k in after)            # training changed the outputs
+    for k in want:
+        assert torch.equal(after[k], want[k]), k                                           # no stale derived weights
