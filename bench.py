@@ -532,6 +532,12 @@ def run_gpu(args, rank, world, local):
         # the reference's own samples_per_gpu = 1: latency-bound single-scene steps, same timing rules
         one = [(p[:int(o[1])].contiguous(), o[:2].contiguous()) for p, o in pool_dev]
         ms_b1, _ = timed(lambda i: (flush.zero_(), model.forward_points(*one[i % n_pool]))[1])
+        # the same as ONE CUDA-graph launch per scene (graphs.GraphedForward: static NaN-padded point buffer)
+        from futuredet_b200 import graphs
+        gf = graphs.GraphedForward(model, max_points=max(int(p.shape[0]) for p, _ in one) + 1024, batch_size=1)
+        gf(*one[0])
+        ms_b1g, _ = timed(lambda i: (flush.zero_(), gf(*one[i % n_pool]))[1])
+        del gf
         bar = cudnn_bar(model, dev, min(B, 4)) if rank == 0 and not args.no_cudnn_bar else None
         stress = stress_bench(args, dev) if rank == 0 else None
     train_info = None
@@ -587,7 +593,9 @@ def run_gpu(args, rank, world, local):
                             what="host points -> H2D -> forward -> CenterHead.predict (decode + rotated NMS on device) -> "
                                  "detections D2H", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(det_bytes[0])),
                 batch1=dict(value=world * args.steps / (ms_b1 / 1e3), unit="scenes/s", ms_per_scene=ms_b1 / args.steps,
-                            what="one scene per step per GPU (the reference's samples_per_gpu), points resident"),
+                            graph_value=world * args.steps / (ms_b1g / 1e3), graph_ms_per_scene=ms_b1g / args.steps,
+                            what="one scene per step per GPU (the reference's samples_per_gpu), points resident; "
+                                 "graph_*: the same forward replayed as one CUDA graph (graphs.GraphedForward)"),
                 voxelize_spconv_ms_per_scene=vs_ms,
                 gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_voxelize=vox_roof,
                 cpu_baseline=cpu_baseline)
