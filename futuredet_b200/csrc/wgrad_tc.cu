@@ -104,6 +104,22 @@ __device__ __forceinline__ void store_split8(uint32_t plane_hi, int r, int c16, 
   sts_u128(plane_hi + PLANE_BYTES + off, lo[0], lo[1], lo[2], lo[3]);
 }
 
+// same with the swizzled offset precomputed by the caller
+__device__ __forceinline__ void store_split8_at(uint32_t addr_hi, const float4& v0, const float4& v1) {
+  const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+    hi[e] = *reinterpret_cast<uint32_t*>(&h);
+    lo[e] = *reinterpret_cast<uint32_t*>(&l);
+  }
+  sts_u128(addr_hi, hi[0], hi[1], hi[2], hi[3]);
+  sts_u128(addr_hi + PLANE_BYTES, lo[0], lo[1], lo[2], lo[3]);
+}
+
 }  // namespace wg
 
 __device__ int g_wg_abort = 0;
@@ -160,6 +176,19 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
   const uint32_t idesc = idesc_mn(128, NT);
 
   const int a_chunks = cin_t >> 3, b_chunks = cout_t >> 3;   // 16-byte (8-channel) chunks per gathered row
+  // item -> (row, chunk) of this thread, fixed for the whole launch (power-of-two chunk counts: shifts, no division in
+  // the stage loop -- the loop is instruction-issue bound: ~500 instructions per thread and stage before this)
+  constexpr int ITEMS_PRE = KP * 16 / THREADS;
+  int a_r[ITEMS_PRE], a_c[ITEMS_PRE], b_r[ITEMS_PRE], b_c[ITEMS_PRE];
+  uint32_t a_so[ITEMS_PRE], b_so[ITEMS_PRE];                  // swizzled shared-memory offset of the item inside a plane
+#pragma unroll
+  for (int i = 0; i < ITEMS_PRE; ++i) {
+    const int e = tid + i * THREADS;
+    a_r[i] = e / a_chunks; a_c[i] = e - a_r[i] * a_chunks;
+    b_r[i] = e / b_chunks; b_c[i] = e - b_r[i] * b_chunks;
+    a_so[i] = (uint32_t)(a_c[i] >> 3) * BLOCK_BYTES + (uint32_t)a_r[i] * ROWB + (uint32_t)(((a_c[i] & 7) ^ (a_r[i] & 7)) << 4);
+    b_so[i] = (uint32_t)(b_c[i] >> 3) * BLOCK_BYTES + (uint32_t)b_r[i] * ROWB + (uint32_t)(((b_c[i] & 7) ^ (b_r[i] & 7)) << 4);
+  }
   int q_head = 0, q_cnt = 0, it = 0;
   bool ok = true;
   for (int rbase = row_begin; rbase < row_end || q_cnt > 0; rbase += THREADS) {
@@ -198,7 +227,7 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         const int e = tid + i * THREADS;
-        const int r = e / a_chunks, c16 = e - r * a_chunks;
+        const int r = a_r[i], c16 = a_c[i];
         va[i][0] = va[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < KP * a_chunks && r < take) {
           const float4* p = reinterpret_cast<const float4*>(a.in + (size_t)q_in[(q_head + r) & (QN - 1)] * a.in_stride + ci0 + c16 * 8);
@@ -208,7 +237,7 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         const int e = tid + i * THREADS;
-        const int r = e / b_chunks, c16 = e - r * b_chunks;
+        const int r = b_r[i], c16 = b_c[i];
         vb[i][0] = vb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < KP * b_chunks && r < take) {
           const float4* p = reinterpret_cast<const float4*>(a.out + (size_t)q_out[(q_head + r) & (QN - 1)] * a.out_stride + co0 + c16 * 8);
@@ -218,12 +247,12 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         const int e = tid + i * THREADS;
-        if (e < KP * a_chunks) { const int r = e / a_chunks; store_split8(sA, r, e - r * a_chunks, va[i][0], va[i][1]); }
+        if (e < KP * a_chunks) store_split8_at(sA + a_so[i], va[i][0], va[i][1]);
       }
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         const int e = tid + i * THREADS;
-        if (e < KP * b_chunks) { const int r = e / b_chunks; store_split8(sB, r, e - r * b_chunks, vb[i][0], vb[i][1]); }
+        if (e < KP * b_chunks) store_split8_at(sB + b_so[i], vb[i][0], vb[i][1]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -262,12 +291,17 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
     for (int e = tid; e < cin_t * cout_t; e += THREADS)
       pslot[((size_t)k * a.cin + ci0 + e / cout_t) * a.cout + co0 + e % cout_t] = 0.f;
   }
-  if (it > 0 && ok && warp < 4) {
-    const int ci = warp * 32 + lane;
+  // all 16 warps: warp w may read TMEM lanes (w % 4) * 32 .. + 31 (its ci rows); the four warps of a lane quarter split
+  // the columns
+  if (it > 0 && ok) {
+    const int lq = warp & 3;
+    const int ci = lq * 32 + lane;
+    const int cols_per = (((NT + 15) >> 4) + 3) / 4 * 16;             // 16-column groups per column quarter
+    const int cbeg = (warp >> 2) * cols_per, cend = min(NT, cbeg + cols_per);
     float* dwk = (pslot ? pslot : dw) + ((size_t)k * a.cin + ci0 + ci) * a.cout + co0;
-    for (int c0 = 0; c0 < NT; c0 += 16) {
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
       uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (ci < cin_t) {
 #pragma unroll
