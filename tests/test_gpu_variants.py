@@ -74,3 +74,42 @@ def test_dense_predict_matches_reference_golden(cuda, golden_dir):
         dense, standard, timesteps, target_timesteps, num_classes = True, False, 3, 7, [1, 1, 1]
     ret = P.center_head_predict(H(), {}, [to_head_views(p, cuda) for p in g["preds"]], g["test_cfg"])
     compare(ret, g["ret"], exact_cells=False)
+
+
+@pytest.mark.parametrize("bev", [False, True])
+def test_detector_with_dense_forecast_head_end_to_end(cuda, bev):
+    """VoxelNet built like the n3dtf / n3dtfm configs (dense + forecast_feature [+ bev_map], 7 chained SepHeads):
+    `model(example, return_loss=True)` (eval-mode loss) and `return_loss=False` (dense predict) through the detector."""
+    from oracle.gen_golden import make_targets
+    from test_gpu_train import random_sites
+    from test_gpu_predict import TEST_CFG
+    torch.manual_seed(0)
+    rng = np.random.default_rng(5)
+    cfg = dict(
+        type="VoxelNet", pretrained=None, reader=dict(type="VoxelFeatureExtractorV3", num_input_features=5),
+        backbone=dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8),
+        neck=dict(type="RPN", layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256],
+                  us_layer_strides=[1, 2], us_num_filters=[256, 256], num_input_features=256),
+        bbox_head=dict(type="CenterHead", in_channels=512, tasks=[dict(num_class=1, class_names=["car"])],
+                       dataset="nuscenes", weight=0.25, code_weights=[1.0] * 6 + [0.2, 0.2, 1.0, 1.0],
+                       common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+                       share_conv_channel=64, dcn_head=False, timesteps=7, dense=True, forecast_feature=True,
+                       bev_map=bev, classify=False))
+    model = fb.build_detector(cfg, test_cfg=fb.ConfigDict(TEST_CFG)).to(cuda).eval()
+    assert len(model.bbox_head.tasks) == 7
+    B, grid = 2, [64, 64, 40]
+    c = random_sites(rng, B, [40, 64, 64], 4000)
+    n = len(c)
+    voxels = np.zeros((n, 10, 5), np.float32); voxels[:, 0] = rng.standard_normal((n, 5)).astype(np.float32)
+    example = make_targets(B, 8, 8, 7, torch.Generator().manual_seed(3), max_objs=10)
+    example = {k: [[t.to(cuda) for t in row] for row in v] for k, v in example.items()}
+    example.update(voxels=torch.from_numpy(voxels).to(cuda), num_points=torch.ones(n, dtype=torch.int32, device=cuda),
+                   coordinates=torch.from_numpy(c).to(cuda), num_voxels=torch.tensor([0] * B), shape=[np.array(grid)] * B,
+                   bev_map=[torch.rand((B, 8, 8), device=cuda) for _ in range(6)])
+    with torch.no_grad():
+        losses = model(example, return_loss=True)
+        dets = model(example, return_loss=False)
+    assert len(losses["loss"]) == 7 and all(torch.isfinite(l).all() for l in losses["loss"])
+    assert len(dets) == B and all(set(d) >= {"box3d_lidar", "scores", "label_preds"} for d in dets)
+    assert all(d["box3d_lidar"].shape[1] == 9 for d in dets)
+    assert all(len(d["label_preds"]) == 0 or int(d["label_preds"].max()) <= 6 for d in dets)
