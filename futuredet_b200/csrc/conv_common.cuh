@@ -23,6 +23,7 @@ struct ConvArgs {
   int out_map;
   const int4* out_coords; int bevD, bevH, bevW;
   int up_s, up_dy, up_dx;  // OUTMAP_UPSAMPLE
+  int n_in_cap;            // rows of `in` (weight gradient only; 0 = unknown)
 };
 
 // input row feeding output row `o` through kernel offset `k`, or -1
@@ -103,6 +104,10 @@ int conv_forward_simt(const ConvArgs& a, cudaStream_t stream);
 bool wgrad_tc_supported(const ConvArgs& a);                              // wgrad_tc.cu
 int conv_wgrad_tc_chunks(const ConvArgs& a);                                              // wgrad_tc.cu
 int conv_wgrad_tc(const ConvArgs& a, float* dw, float* partial, cudaStream_t stream);    // wgrad_tc.cu
+bool wgrad_os_supported(const ConvArgs& a);                                           // wgrad_tc.cu (output-stationary kernel)
+int conv_wgrad_os_chunks(const ConvArgs& a);
+size_t conv_wgrad_os_extra_bytes(const ConvArgs& a);
+int conv_wgrad_os(const ConvArgs& a, float* partial, void* extra, cudaStream_t stream);
 int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream);
 
 }  // namespace fd

@@ -241,6 +241,7 @@ static int launch_wgrad_i(const ConvArgs& a, float* dw, float* partial, int* slo
 // Number of partial slots the deterministic path of this launch writes (planning only, nothing is launched).
 static int wgrad_slots(const ConvArgs& a, int precision) {
   if (a.n_cap <= 0) return 0;
+  if (precision == FD_PREC_BF16X3 && wgrad_os_supported(a)) return conv_wgrad_os_chunks(a);
   if (precision == FD_PREC_BF16X3 && wgrad_tc_supported(a)) return conv_wgrad_tc_chunks(a);
   int slots = 0;
   switch (wg_tile(a.cin)) {
@@ -252,6 +253,14 @@ static int wgrad_slots(const ConvArgs& a, int precision) {
   return slots;
 }
 
+// workspace of the deterministic path: the partial slots (+ the split-bf16 copies of x and dy for the output-stationary
+// tcgen05 kernel)
+static size_t wgrad_ws_bytes(const ConvArgs& a, int precision) {
+  size_t b = ((size_t)wgrad_slots(a, precision) * a.K * a.cin * a.cout * sizeof(float) + 255) & ~(size_t)255;
+  if (a.n_cap > 0 && precision == FD_PREC_BF16X3 && wgrad_os_supported(a)) b += conv_wgrad_os_extra_bytes(a);
+  return b;
+}
+
 // ws == nullptr: fp32 atomics into dw; otherwise per-chunk partial tiles in ws + an ordered reduce into dw
 static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream, int precision = FD_PREC_FP32, float* ws = nullptr,
                         size_t ws_bytes = 0) {
@@ -260,11 +269,13 @@ static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream, int p
   int slots = 0;
   if (ws) {
     slots = wgrad_slots(a, precision);
-    FD_REQUIRE((size_t)slots * elems * sizeof(float) <= ws_bytes, "fd_conv_wgrad_det: workspace %zu < required %zu", ws_bytes,
-               (size_t)slots * elems * sizeof(float));
+    FD_REQUIRE(wgrad_ws_bytes(a, precision) <= ws_bytes, "fd_conv_wgrad_det: workspace %zu < required %zu", ws_bytes,
+               wgrad_ws_bytes(a, precision));
   }
   int rc;
-  if (precision == FD_PREC_BF16X3 && wgrad_tc_supported(a)) {
+  if (ws && precision == FD_PREC_BF16X3 && wgrad_os_supported(a)) {
+    rc = conv_wgrad_os(a, ws, (char*)ws + (((size_t)slots * elems * sizeof(float) + 255) & ~(size_t)255), stream);
+  } else if (precision == FD_PREC_BF16X3 && wgrad_tc_supported(a)) {
     rc = conv_wgrad_tc(a, dw, ws, stream);
   } else {
     switch (wg_tile(a.cin)) {
@@ -624,13 +635,15 @@ static int wgrad_entry(const fd_conv_desc* d, float* d_dw, float* ws, size_t ws_
     case FD_GATHER_TABLE:
       FD_REQUIRE(d->d_nbr && d->nbr_stride >= d->n_out_cap, "fd_conv_wgrad: bad neighbour table");
       FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY && d->out_stride >= d->cout, "fd_conv_wgrad: identity out rows only");
-      if (need) { *need = (size_t)wgrad_slots(a, d->precision) * a.K * a.cin * a.cout * sizeof(float); return 0; }
+      a.n_in_cap = d->n_in_cap;
+      if (need) { *need = wgrad_ws_bytes(a, d->precision); return 0; }
       return launch_wgrad(a, d_dw, stream, d->precision, ws, ws_bytes);
     case FD_GATHER_CONV2D:
       FD_REQUIRE(d->K == d->kh * d->kw && d->sh >= 1 && d->sw >= 1, "fd_conv_wgrad: bad conv2d geometry");
       FD_REQUIRE(d->n_out_cap == d->B * d->Hout * d->Wout && !d->d_n_out, "fd_conv_wgrad: conv2d rows must be B*Hout*Wout");
       FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY && d->out_stride >= d->cout, "fd_conv_wgrad: identity out rows only");
-      if (need) { *need = (size_t)wgrad_slots(a, d->precision) * a.K * a.cin * a.cout * sizeof(float); return 0; }
+      a.n_in_cap = d->B * d->Hin * d->Win;
+      if (need) { *need = wgrad_ws_bytes(a, d->precision); return 0; }
       return launch_wgrad(a, d_dw, stream, d->precision, ws, ws_bytes);
     case FD_GATHER_CONVT2D: {
       FD_REQUIRE(d->kh == d->sh && d->kw == d->sw && d->kh == d->kw && d->ph == 0 && d->pw == 0 && d->K == d->kh * d->kw,
@@ -644,7 +657,7 @@ static int wgrad_entry(const fd_conv_desc* d, float* d_dw, float* ws, size_t ws_
         p.Hout = d->Hin; p.Wout = d->Win;
         p.out_map = OUTMAP_UPSAMPLE;
         p.up_s = d->sh; p.up_dy = k / d->kw; p.up_dx = k % d->kw;
-        if (need) { *need = (size_t)wgrad_slots(p, FD_PREC_FP32) * p.cin * p.cout * sizeof(float); return 0; }
+        if (need) { *need = wgrad_ws_bytes(p, FD_PREC_FP32); return 0; }
         int rc = launch_wgrad(p, d_dw + (size_t)k * d->cin * d->cout, stream, FD_PREC_FP32, ws, ws_bytes);
         if (rc) return rc;
       }

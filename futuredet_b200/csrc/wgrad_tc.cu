@@ -23,6 +23,11 @@
 
 namespace fd {
 
+constexpr int WOS_TRACE_N = 4096;
+__device__ long long g_wos_trace[4][WOS_TRACE_N];       // FD_WG_DBG & 32: clock64 timeline of block (0, 0) (perf triage only)
+#define WOS_TRACE(role, i, v) do { if ((pl.dbg & 32) && blockIdx.x == 0 && blockIdx.y == 0 && (i) < WOS_TRACE_N) g_wos_trace[role][i] = (v); } while (0)
+__device__ int g_wg_abort = 0;      // raised by the first mbarrier wait that times out: every later wait gives up at once
+
 namespace wg {
 
 constexpr int THREADS = 512;                // 16 warps: the stage is latency bound (gather -> split -> store), not MMA bound
@@ -42,11 +47,37 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 // bounded wait: a protocol bug must not hang the GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spins = 0; spins < (1u << 24); ++spins) {
+    if ((spins & 1023) == 1023 && *(volatile int*)&g_wg_abort) return false;
     uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+// same, polling with the non-suspending test_wait (a parked try_wait wakes up hundreds of cycles after the phase flips)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+__device__ __forceinline__ bool mbar_spin(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; spins < (1u << 26); ++spins) {
+    if ((spins & 4095) == 4095 && *(volatile int*)&g_wg_abort) return false;
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return true;
@@ -121,8 +152,6 @@ __device__ __forceinline__ void store_split8_at(uint32_t addr_hi, const float4& 
 }
 
 }  // namespace wg
-
-__device__ int g_wg_abort = 0;
 
 __global__ void __launch_bounds__(wg::THREADS, 1)
 conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict__ partial, int rows_per_cta, int tiles_ci,
@@ -320,6 +349,437 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
 }
 
+// =====================================================================================================================
+// Output-stationary weight gradient ("wos", round 2).  The kernel above gives every kernel offset its own CTAs, so dY
+// rows are gathered once per offset (27x), every stage pays gather -> split -> store -> barrier serially, and a layer
+// with Cin < 128 uses a fraction of the 128 accumulator lanes.  Here a CTA owns a chunk of consecutive OUTPUT rows and
+// a "pass" of M groups: per 64-row K stage the dY tile is loaded ONCE (contiguous rows, no gather) and reused by every
+// group of the pass; a group's A operand is 128 accumulator lanes = 128 / Cin kernel offsets side by side (Cin < 128:
+// the gathered rows of 2 / 4 / 8 offsets share the 128-byte MN-major rows, so narrow layers fill the tensor core's M)
+// or one 128-channel slice of one offset; every group has its own NT-column accumulator in TMEM (<= 512 columns per
+// pass: 27 offsets of a 64 -> 64 layer are 2 passes of 7 groups, of a 32 -> 32 layer one pass).  Operands are
+// pre-split bf16 hi / lo rows (split_rows_kernel, one streaming pass over x and dy), so the 8 producer warps are pure
+// cp.async (missing neighbours zero-filled) into a 4-slot A ring / 2-slot dY ring, one thread issues the 12
+// tcgen05.mma of a (group, stage) and commits the slot back, and the accumulators are read once at the end of the
+// chunk (lane = (offset, ci), column = co) into the chunk's slot of the partial buffer (ordered reduce: bit-reproducible).
+namespace wos {
+
+constexpr int KP = 64, ROWB = 128, BLOCK_BYTES = KP * ROWB;        // one 64-channel column block of one plane: 8 KB
+constexpr int A_PLANE = 2 * BLOCK_BYTES, A_BYTES = 2 * A_PLANE;     // 128 lanes x 64 rows, hi + lo: 32 KB
+constexpr int SB = 2;
+constexpr int PRODUCERS = 256, PGROUPS = 4, THREADS = PRODUCERS + 64;      // + MMA warp + loader warp (dY stages, rulebook slices)
+constexpr int IDX_K = 32;                                           // kernel offsets of a staged rulebook slice
+constexpr int IDX_SLOTS = 4;                                        // staged rulebook slices (stages) in flight
+constexpr int IDX_BYTES = IDX_SLOTS * IDX_K * KP * 4;               // [K][64] input-row indices per stage: 32 KB
+// A ring slots: what the dY ring (2 x 32 KB for Cout = 128, 2 x 16 KB below) and the index slices leave of the CTA's
+// shared memory (5 / 4 slots)
+constexpr size_t smem_bytes(int sa, int b_bytes) { return 1024 + (size_t)sa * A_BYTES + (size_t)SB * b_bytes + IDX_BYTES + 256; }
+
+__device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void* src, uint32_t sz) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ uint32_t wg_lds(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wg_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// one lane polls, the warp parks at __syncwarp
+__device__ __forceinline__ bool wait_warp(uint32_t bar, uint32_t parity, bool spin = false) {
+  bool ok = true;
+  if ((threadIdx.x & 31) == 0) ok = spin ? wg::mbar_spin(bar, parity) : wg::mbar_wait(bar, parity);   // spin: test_wait polling
+  return __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+}
+
+struct Plan {
+  int opg;          // kernel offsets per group (Cin < 128) or 1
+  int ci_tiles;     // 128-channel slices per offset (Cin >= 128) or 1
+  int n_groups;     // groups of the whole layer
+  int gpp;          // groups per pass
+  int passes;
+  int NT;           // accumulator columns per group
+  int tmem_cols;
+  int chunks;
+  int b_bytes;      // bytes of one dY ring slot
+  int dbg;          // FD_WG_DBG triage bits: 1 no gathers, 2 no MMAs, 4 no proxy fence
+};
+
+}  // namespace wos
+
+// fp32 rows [n, C] (row stride in floats) -> FD_FMT_SPLIT_BF16 rows [n][C hi | C lo], dense
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ x, int stride, int C, const int32_t* __restrict__ d_n, int n_cap,
+                  unsigned short* __restrict__ out) {
+  const int n = d_n ? min(*d_n, n_cap) : n_cap;
+  const int c8 = C >> 3;
+  const long long total = (long long)n * c8;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / c8), c = (int)(e - (long long)r * c8) * 8;
+    const float4* p = reinterpret_cast<const float4*>(x + (size_t)r * stride + c);
+    const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+    const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      const float2 hf = __bfloat1622float2(h);
+      __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+      hi[i] = *reinterpret_cast<uint32_t*>(&h);
+      lo[i] = *reinterpret_cast<uint32_t*>(&l);
+    }
+    unsigned short* o = out + (size_t)r * 2 * C + c;
+    *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(o + C) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// a.in / a.out: split-bf16 copies of x / dy (dense rows of 2*cin / 2*cout bf16); everything else as the forward conv
+template <int SA>
+__global__ void __launch_bounds__(wos::THREADS, 1)
+conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict__ partial, const wos::Plan pl) {
+  using namespace wos;
+  const int B_BYTES = pl.b_bytes;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_ring = wg::smem_u32(base), b_ring = a_ring + SA * A_BYTES;
+  const uint32_t idx_ring = b_ring + SB * B_BYTES;                     // [IDX_SLOTS][IDX_K][KP] int32 (rulebook-table layers)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + SA * A_BYTES + SB * B_BYTES + IDX_BYTES);
+  uint64_t* a_full = bars, *a_empty = bars + SA, *b_full = bars + 2 * SA, *b_empty = b_full + SB, *done = b_empty + SB;
+  uint64_t* i_full = done + 1, *i_empty = i_full + IDX_SLOTS;          // [IDX_SLOTS] each
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(i_empty + IDX_SLOTS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.d_n ? min(*a.d_n, a.n_cap) : a.n_cap;
+  const int pass = blockIdx.y;
+  const int g0 = pass * pl.gpp, G = min(pl.gpp, pl.n_groups - g0);        // this pass's groups
+  const int rows_per_cta = ((n + (int)gridDim.x - 1) / (int)gridDim.x + KP - 1) & ~(KP - 1);
+  const long long rb = (long long)blockIdx.x * rows_per_cta;
+  const int row_begin = (int)min((long long)n, rb), row_end = (int)min((long long)n, rb + rows_per_cta);
+  const int n_stages = (row_end - row_begin + KP - 1) / KP;
+  const int cin = a.cin, cout = a.cout, NT = pl.NT;
+  float* pslot = partial ? partial + (size_t)blockIdx.x * a.K * cin * cout : nullptr;
+  // (offset, first channel) of lane-slot `ls` of group `grp`
+  auto group_k = [&](int grp, int ls, int& ch) -> int {
+    if (cin >= 128) { ch = (grp % pl.ci_tiles) * 128 + ls; return grp / pl.ci_tiles; }
+    ch = ls % cin;
+    return grp * pl.opg + ls / cin;
+  };
+
+  if (n_stages == 0) {                                   // a chunk without rows still owns (and zeroes) its tiles
+    if (pslot)
+      for (int g = 0; g < G; ++g)
+        for (int e = tid; e < 128 * cout; e += THREADS) {
+          int ch; const int k = group_k(g0 + g, e / cout, ch);
+          if (k < a.K) pslot[((size_t)k * cin + ch) * cout + e % cout] = 0.f;
+        }
+    return;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < SA; ++s) { wg::mbar_init(wg::smem_u32(&a_full[s]), PRODUCERS / PGROUPS); wg::mbar_init(wg::smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < SB; ++s) { wg::mbar_init(wg::smem_u32(&b_full[s]), 32); wg::mbar_init(wg::smem_u32(&b_empty[s]), 1); }
+    wg::mbar_init(wg::smem_u32(done), 1);
+    for (int s = 0; s < IDX_SLOTS; ++s) { wg::mbar_init(wg::smem_u32(&i_full[s]), 32); wg::mbar_init(wg::smem_u32(&i_empty[s]), PRODUCERS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == PRODUCERS / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wg::smem_u32(s_tmem)), "r"(pl.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  bool ok = true;
+
+  if (warp < PRODUCERS / 32) {
+    // ===================================== PRODUCERS =====================================
+    // 4 groups of 64 threads; group p fills items p, p + 4, ... ((stage, group) pairs in MMA order) on its own, so four
+    // items are being issued concurrently: a single gather warp's dependent instruction stream (index reads, address
+    // arithmetic, 32 cp.async, barrier hand-shake) takes ~1500 cycles per item even with nothing to copy (clock64
+    // timeline, tools/wgrad_trace.py).  Thread: 16-byte chunk c of the 128-lane A row, rows r0 + 4 q.
+    // Rulebook-table layers read their source rows from the [K][64] slice of the neighbour table that the loader warp
+    // stages in shared memory; dense 2-D layers compute them arithmetically.  The gather warps issue NOTHING but the A
+    // gathers: cp.async completes in order per thread, so a dY / index load in the same thread's stream would put its
+    // DRAM round trip in front of the next A stage's arrival.
+    const int pgrp = tid >> 6, t64 = tid & 63;
+    const int c = t64 & 15, r0 = t64 >> 4;               // rows r0 + 4 q, q = 0..15
+    // swizzled offsets of (row r0, chunk c) and (row r0 + 4, chunk c): rows 8 apart keep the swizzle phase
+    const uint32_t a_off0 = (uint32_t)(c >> 3) * BLOCK_BYTES + (uint32_t)r0 * ROWB + (uint32_t)(((c & 7) ^ (r0 & 7)) << 4);
+    const uint32_t a_off1 = (uint32_t)(c >> 3) * BLOCK_BYTES + (uint32_t)(r0 + 4) * ROWB + (uint32_t)(((c & 7) ^ ((r0 + 4) & 7)) << 4);
+    const char* xs = reinterpret_cast<const char*>(a.in);
+    const size_t x_row = (size_t)cin * 4;
+    const bool table = a.mode == FD_GATHER_TABLE;
+    const int koff = cin >= 128 ? 0 : (c * 8) / cin;     // this thread's kernel offset inside a group (Cin < 128)
+    const int ch_n = cin >= 128 ? c * 8 : (c * 8) % cin;
+    const int n_items = n_stages * G;
+    int cur_st = 0;                                      // stage whose index slice this warp is reading
+    bool have_idx = false;
+    for (int item = pgrp; item < n_items; item += PGROUPS) {
+      const int st = item / G, g = item - st * G;
+      const uint32_t as = (uint32_t)item % SA, aph = ((uint32_t)item / SA) & 1;
+      int k, ch;
+      if (cin >= 128) { const int grp = g0 + g; k = grp / pl.ci_tiles; ch = (grp - k * pl.ci_tiles) * 128 + ch_n; }
+      else { k = (g0 + g) * pl.opg + koff; ch = ch_n; }
+      const bool kv = k < a.K;
+      if (table) {
+        if (st != cur_st) {                                 // done with the slices of stages cur_st .. st - 1
+          __syncwarp();
+          if (lane == 0) for (int s2 = cur_st; s2 < st; ++s2) wg_mbar_arrive(wg::smem_u32(&i_empty[s2 % IDX_SLOTS]));
+          cur_st = st;
+          have_idx = false;
+        }
+        if (!have_idx) { ok = wait_warp(wg::smem_u32(&i_full[st % IDX_SLOTS]), (uint32_t)((st / IDX_SLOTS) & 1), true) && ok; have_idx = true; }
+      }
+      const int o0 = row_begin + st * KP + r0;
+      const uint32_t ibase = idx_ring + (uint32_t)(st % IDX_SLOTS) * (IDX_K * KP * 4) + (uint32_t)(k * KP + r0) * 4;
+      int src[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int o = o0 + 4 * q;
+        if (!kv || o >= row_end) src[q] = -1;
+        else if (table) src[q] = (int)wg_lds(ibase + (uint32_t)(4 * q) * 4);
+        else src[q] = gather_row(a, o, k);
+      }
+      if (t64 == 0) WOS_TRACE(0, item, clock64());
+      ok = wait_warp(wg::smem_u32(&a_empty[as]), aph ^ 1, true) && ok;
+      if (t64 == 0) WOS_TRACE(1, item, clock64());
+      const uint32_t adst = a_ring + as * A_BYTES;
+      const char* xh = xs + ch * 2;
+      if (!(pl.dbg & 1)) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const uint32_t sz = src[q] >= 0 ? 16u : 0u;
+          const char* sp = xh + (size_t)(uint32_t)max(src[q], 0) * x_row;
+          const uint32_t d = adst + ((q & 1) ? a_off1 : a_off0) + (uint32_t)(q >> 1) * (8 * ROWB);
+          cp_async16_sz(d, sp, sz);
+          cp_async16_sz(d + A_PLANE, sp + cin * 2, sz);
+        }
+      }
+      cp_async_arrive_noinc(wg::smem_u32(&a_full[as]));
+    }
+    if (table) {                                           // release the slices of the remaining stages
+      __syncwarp();
+      if (lane == 0) for (int s2 = cur_st; s2 < n_stages; ++s2) wg_mbar_arrive(wg::smem_u32(&i_empty[s2 % IDX_SLOTS]));
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == PRODUCERS / 32 + 1) {
+    // ===================================== LOADER =====================================
+    // per stage: the dY tile (64 consecutive output rows, loaded once for all groups of the pass) and, for rulebook
+    // layers, the [K][64] slice of the neighbour table -- up to two stages ahead of the gather warps
+    const char* ys = reinterpret_cast<const char*>(a.out);
+    const size_t y_row = (size_t)cout * 4;
+    const int bchunks = cout >> 3, b_items = KP * bchunks;
+    const uint32_t b_plane = (uint32_t)((cout + 63) >> 6) * BLOCK_BYTES;
+    const bool table = a.mode == FD_GATHER_TABLE;
+    const bool idx_vec = table && (a.nbr_stride & 3) == 0 && (((uintptr_t)a.nbr) & 15) == 0 && (row_begin & 3) == 0;
+    // index slice of stage si into ring slot si % IDX_SLOTS (after every gather warp has released its previous occupant)
+    auto load_indices = [&](int si) {
+      const int buf = si % IDX_SLOTS, o0 = row_begin + si * KP;
+      if (si >= IDX_SLOTS) ok = wait_warp(wg::smem_u32(&i_empty[buf]), (uint32_t)((si / IDX_SLOTS - 1) & 1)) && ok;
+      const uint32_t dst = idx_ring + (uint32_t)buf * (IDX_K * KP * 4);
+      if (idx_vec) {
+        // 16-byte copies (4 rows); rows past the chunk's end are zero-filled and never read
+        for (int e = lane; e < a.K * (KP / 4); e += 32) {
+          const int k = e >> 4, r = (e & 15) * 4;
+          const int valid = min(max(row_end - (o0 + r), 0), 4);
+          const int32_t* src = a.nbr + (size_t)k * a.nbr_stride + min(o0 + r, (row_end - 1) & ~3);
+          cp_async16_sz(dst + (uint32_t)(k * KP + r) * 4, src, (uint32_t)valid * 4);
+        }
+      } else {
+        for (int e = lane; e < a.K * KP; e += 32) {
+          const int k = e >> 6, r = e & (KP - 1);
+          const int o = min(o0 + r, row_end - 1);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)e * 4), "l"(a.nbr + (size_t)k * a.nbr_stride + o) : "memory");
+        }
+      }
+      cp_async_arrive_noinc(wg::smem_u32(&i_full[buf]));
+    };
+    // the slices run IDX_SLOTS - 2 stages ahead of the dY tiles (which are gated by the MMAs of two stages ago): the
+    // gather warps are up to a ring of items ahead of the MMA and must never wait for a slice's DRAM round trip
+    constexpr int AHEAD = IDX_SLOTS - 2;
+    if (table) for (int si = 0; si < AHEAD && si < n_stages; ++si) load_indices(si);
+    uint32_t bs = 0, bph = 0;
+    for (int st = 0; st < n_stages; ++st) {
+      const int o0 = row_begin + st * KP;
+      if (table && st + AHEAD < n_stages) load_indices(st + AHEAD);
+      ok = wait_warp(wg::smem_u32(&b_empty[bs]), bph ^ 1) && ok;
+      const uint32_t bdst = b_ring + bs * B_BYTES;
+      for (int e = lane; e < b_items; e += 32) {
+        const int r = e / bchunks, cc = e - r * bchunks;
+        const uint32_t sz = o0 + r < row_end ? 16u : 0u;
+        const char* src = ys + (size_t)min(o0 + r, row_end - 1) * y_row + cc * 16;
+        const uint32_t d = bdst + (uint32_t)(cc >> 3) * BLOCK_BYTES + (uint32_t)r * ROWB + (uint32_t)(((cc & 7) ^ (r & 7)) << 4);
+        cp_async16_sz(d, src, sz);
+        cp_async16_sz(d + b_plane, src + cout * 2, sz);
+      }
+      cp_async_arrive_noinc(wg::smem_u32(&b_full[bs]));
+      if (++bs == SB) { bs = 0; bph ^= 1; }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (lane == 0) {
+    // ===================================== MMA ISSUER =====================================
+    const uint32_t idesc = wg::idesc_mn(128, NT);
+    const uint32_t b_plane = (uint32_t)((cout + 63) >> 6) * BLOCK_BYTES;
+    // The barrier of the NEXT item (and, at a stage's last group, of the next dY stage) is probed with a non-blocking
+    // test_wait issued BEFORE the current item's MMAs, so that its latency overlaps their issue (which blocks on
+    // execution); a blocking wait only follows when the probe said "not yet".
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+    uint32_t a_ready = 0, b_ready = 0;
+    for (int st = 0; st < n_stages && ok; ++st) {
+      if (!b_ready) ok = wg::mbar_wait(wg::smem_u32(&b_full[bs]), bph) && ok;
+      const uint32_t sB = b_ring + bs * B_BYTES;
+      const uint64_t dBh = wg::desc_mn_sw128(sB), dBl = wg::desc_mn_sw128(sB + b_plane);
+      const uint32_t nbs = bs + 1 == SB ? 0 : bs + 1, nbph = bs + 1 == SB ? bph ^ 1 : bph;
+      for (int g = 0; g < G && ok; ++g) {
+        if (!a_ready) ok = wg::mbar_wait(wg::smem_u32(&a_full[as]), aph) && ok;
+        WOS_TRACE(2, st * G + g, clock64());
+        if (!(pl.dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t nas = as + 1 == SA ? 0 : as + 1, naph = as + 1 == SA ? aph ^ 1 : aph;
+        a_ready = wg::mbar_test(wg::smem_u32(&a_full[nas]), naph);
+        if (g == G - 1) b_ready = wg::mbar_test(wg::smem_u32(&b_full[nbs]), nbph);
+        const uint32_t sA = a_ring + as * A_BYTES;
+        const uint64_t dAh = wg::desc_mn_sw128(sA), dAl = wg::desc_mn_sw128(sA + A_PLANE);
+        const uint32_t td = tmem_base + (uint32_t)(g * NT);
+        if (!(pl.dbg & 2)) {
+#pragma unroll
+          for (int ks = 0; ks < KP / 16; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 16 * ROWB) >> 4);
+            wg::umma(td, dAh + adv, dBh + adv, idesc, (st > 0 || ks > 0) ? 1u : 0u);
+            wg::umma(td, dAh + adv, dBl + adv, idesc, 1u);
+            wg::umma(td, dAl + adv, dBh + adv, idesc, 1u);
+          }
+        }
+        wg::umma_commit(wg::smem_u32(&a_empty[as]));
+        WOS_TRACE(3, st * G + g, clock64());
+        as = nas; aph = naph;
+      }
+      wg::umma_commit(wg::smem_u32(&b_empty[bs]));
+      bs = nbs; bph = nbph;
+    }
+    wg::umma_commit(wg::smem_u32(done));
+  }
+  // ===================================== EPILOGUE =====================================
+  __syncwarp();
+  if (warp < PRODUCERS / 32) {
+    ok = wait_warp(wg::smem_u32(done), 0) && ok;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (ok) {
+      const int lq = warp & 3, half = warp >> 2;           // TMEM lane quarter; the two warps of a quarter alternate groups
+      const int ls = lq * 32 + lane;
+      for (int g = half; g < G; g += 2) {
+        int ch; const int k = group_k(g0 + g, ls, ch);
+        float* dst = (pslot ? pslot : dw) + ((size_t)k * cin + ch) * cout;
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t v[16];
+          wg::tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(g * NT + c0), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (k < a.K) {
+            if (pslot) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (v[j] != 0u) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!ok && lane == 0) atomicAdd(&g_wg_abort, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == PRODUCERS / 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols));
+}
+
+static bool wos_plan(const ConvArgs& a, wos::Plan* out) {
+  const int cin = a.cin, cout = a.cout;
+  const bool cin_ok = cin == 16 || cin == 32 || cin == 64 || (cin >= 128 && cin % 128 == 0);
+  const bool cout_ok = cout == 16 || cout == 32 || cout == 64 || cout == 128;
+  if (!cin_ok || !cout_ok || a.out_map != FD_OUTMAP_IDENTITY) return false;
+  wos::Plan p{};
+  p.opg = cin >= 128 ? 1 : 128 / cin;
+  p.ci_tiles = cin >= 128 ? cin / 128 : 1;
+  p.n_groups = cin >= 128 ? a.K * p.ci_tiles : ceil_div(a.K, p.opg);
+  p.NT = cout;
+  const int max_gpp = 512 / p.NT;
+  p.passes = ceil_div(p.n_groups, max_gpp);
+  p.gpp = ceil_div(p.n_groups, p.passes);
+  p.passes = ceil_div(p.n_groups, p.gpp);
+  int cols = 32;
+  while (cols < p.gpp * p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  int chunks = kNumSMs / p.passes;
+  const int max_chunks = ceil_div(a.n_cap, 4 * wos::KP);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  p.chunks = chunks;
+  // rulebook layers: a gather warp may run SA <= 5 items ahead of another; the two index-slice buffers stay consistent
+  // as long as that is less than two stages
+  if (a.mode == FD_GATHER_TABLE && p.n_groups - (p.passes - 1) * p.gpp < 3) return false;
+  p.b_bytes = 2 * ((cout + 63) / 64) * wos::BLOCK_BYTES;
+  static const int dbg = getenv("FD_WG_DBG") ? atoi(getenv("FD_WG_DBG")) : 0;
+  p.dbg = dbg;
+  *out = p;
+  return true;
+}
+
+// eligibility of the output-stationary kernel (needs the row capacity of d_in to pre-split it, and a workspace)
+bool wgrad_os_supported(const ConvArgs& a) {
+  wos::Plan p;
+  static const int off = getenv("FD_WG_OS_OFF") ? atoi(getenv("FD_WG_OS_OFF")) : 0;
+  return !off && a.n_in_cap > 0 && a.in_fmt == FD_FMT_FP32 && a.out_fmt == FD_FMT_FP32 && a.in_stride % 4 == 0 &&
+         a.out_stride % 4 == 0 && ((((uintptr_t)a.in) | ((uintptr_t)a.out)) & 15) == 0 && a.K <= wos::IDX_K && wos_plan(a, &p);
+}
+int conv_wgrad_os_chunks(const ConvArgs& a) {
+  wos::Plan p;
+  return wos_plan(a, &p) ? p.chunks : 0;
+}
+static size_t wos_align(size_t x) { return (x + 255) & ~(size_t)255; }
+// bytes of the split copies of x and dy that follow the partial slots in the workspace
+size_t conv_wgrad_os_extra_bytes(const ConvArgs& a) {
+  return wos_align((size_t)a.n_in_cap * a.cin * 4) + wos_align((size_t)a.n_cap * a.cout * 4) + 512;
+}
+// `partial`: chunks x [K, Cin, Cout] slots (ordered reduce by the caller); `extra`: conv_wgrad_os_extra_bytes(a) bytes
+int conv_wgrad_os(const ConvArgs& a, float* partial, void* extra, cudaStream_t stream) {
+  if (a.n_cap <= 0) return 0;
+  wos::Plan p;
+  FD_REQUIRE(wos_plan(a, &p), "fd_conv_wgrad: unsupported shape for the output-stationary kernel");
+  static bool configured = false;
+  if (!configured) {
+    FD_CUDA(cudaFuncSetAttribute(conv_wgrad_os_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wos::smem_bytes(4, 32768)));
+    FD_CUDA(cudaFuncSetAttribute(conv_wgrad_os_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wos::smem_bytes(5, 16384)));
+    configured = true;
+  }
+  char* e = (char*)(((uintptr_t)extra + 255) & ~(uintptr_t)255);
+  unsigned short* xs = (unsigned short*)e;
+  unsigned short* ys = (unsigned short*)(e + wos_align((size_t)a.n_in_cap * a.cin * 4));
+  split_rows_kernel<<<persistent_grid(ceil_div((int64_t)a.n_in_cap * (a.cin / 8), 256), 8), 256, 0, stream>>>(
+      a.in, a.in_stride, a.cin, nullptr, a.n_in_cap, xs);
+  FD_LAUNCHED();
+  split_rows_kernel<<<persistent_grid(ceil_div((int64_t)a.n_cap * (a.cout / 8), 256), 8), 256, 0, stream>>>(
+      a.out, a.out_stride, a.cout, a.d_n, a.n_cap, ys);
+  FD_LAUNCHED();
+  ConvArgs s = a;
+  s.in = reinterpret_cast<const float*>(xs); s.in_stride = a.cin; s.in_ctot = a.cin; s.in_fmt = FD_FMT_SPLIT_BF16;
+  s.out = reinterpret_cast<float*>(ys); s.out_stride = a.cout; s.out_ctot = a.cout; s.out_fmt = FD_FMT_SPLIT_BF16;
+  const dim3 grid(p.chunks, p.passes);
+  if (p.b_bytes <= 16384) conv_wgrad_os_kernel<5><<<grid, wos::THREADS, wos::smem_bytes(5, p.b_bytes), stream>>>(s, nullptr, partial, p);
+  else conv_wgrad_os_kernel<4><<<grid, wos::THREADS, wos::smem_bytes(4, p.b_bytes), stream>>>(s, nullptr, partial, p);
+  FD_LAUNCHED();
+  return 0;
+}
+
 // eligibility of the tensor-core arm: plain fp32 rows with 16-byte aligned 8-channel groups on both operands
 bool wgrad_tc_supported(const ConvArgs& a) {
   return a.out_map == FD_OUTMAP_IDENTITY && a.cin % 8 == 0 && a.cout % 8 == 0 && a.in_stride % 4 == 0 &&
@@ -357,3 +817,12 @@ int conv_wgrad_tc(const ConvArgs& a, float* dw, float* partial, cudaStream_t str
 }
 
 }  // namespace fd
+
+extern "C" {
+/* perf-triage helper (not part of the documented ABI): copy the FD_WG_DBG&32 timeline of block (0,0) to the host */
+int fd_debug_read_wgrad_trace(long long* out, int role) {
+  if (role < 0 || role >= 4) return -1;
+  return (int)cudaMemcpyFromSymbol(out, fd::g_wos_trace, sizeof(long long) * fd::WOS_TRACE_N,
+                                   sizeof(long long) * fd::WOS_TRACE_N * role, cudaMemcpyDeviceToHost);
+}
+}

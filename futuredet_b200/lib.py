@@ -37,6 +37,7 @@ class ConvDesc(C.Structure):
         ("out_map", C.c_int32),
         ("d_out_coords4", C.c_void_p), ("bevD", C.c_int32), ("bevH", C.c_int32), ("bevW", C.c_int32),
         ("precision", C.c_int32),
+        ("n_in_cap", C.c_int32),
     ]
 
 

@@ -104,6 +104,7 @@ def sparse_conv_wgrad(x, dy, rb, dw, precision="fp32"):
     d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
     d.out_map = L.OUTMAP_IDENTITY
     d.precision = L.PRECISIONS[precision]
+    d.n_in_cap = n_rows(x)
     _run_wgrad(lib, d, dw, "fd_conv_wgrad(sparse)")
     return dw
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 2
+#define FD_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------ */
 int         fd_version(void);
@@ -181,6 +181,9 @@ typedef struct fd_conv_desc {
   int32_t        out_map;     /* FD_OUTMAP_* */
   const int32_t* d_out_coords4; int32_t bevD, bevH, bevW;  /* FD_OUTMAP_BEV */
   int32_t        precision;   /* FD_PREC_* */
+  int32_t        n_in_cap;    /* fd_conv_wgrad* with FD_GATHER_TABLE: rows of d_in (lets the tcgen05 arm pre-split
+                               * the layer input once); 0 = unknown (the per-offset tcgen05 kernel is used).  Ignored
+                               * by fd_conv_forward.                                                              */
 } fd_conv_desc;
 
 enum { FD_GATHER_TABLE = 0, FD_GATHER_CONV2D = 1, FD_GATHER_CONVT2D = 2,
