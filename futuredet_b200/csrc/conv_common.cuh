@@ -24,6 +24,8 @@ struct ConvArgs {
   const int4* out_coords; int bevD, bevH, bevW;
   int up_s, up_dy, up_dx;  // OUTMAP_UPSAMPLE
   int n_in_cap;            // rows of `in` (weight gradient only; 0 = unknown)
+  const void* in_split;    // weight gradient only: dense FD_FMT_SPLIT_BF16 copies of `in` / dL/dy ([rows][C hi | C lo]) when
+  const void* out_split;   // the caller already has them (NULL: the tcgen05 arm splits into its workspace)
 };
 
 // input row feeding output row `o` through kernel offset `k`, or -1

@@ -424,7 +424,8 @@ static size_t red_partial_bytes(int C) { return sizeof(double) * (size_t)RED_MAX
 __global__ void __launch_bounds__(256)
 affine_act_kernel(const float* __restrict__ x, int xs, int C, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ res, int rs, int relu,
-                  float* __restrict__ y, int ys, const int32_t* __restrict__ d_n, long long n_cap) {
+                  float* __restrict__ y, int ys, unsigned short* __restrict__ ysplit, int split_ctot,
+                  const int32_t* __restrict__ d_n, long long n_cap) {
   const long long n = d_n ? min((long long)*d_n, n_cap) : n_cap;
   const long long total = n * C;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -436,6 +437,12 @@ affine_act_kernel(const float* __restrict__ x, int xs, int C, const float* __res
     if (res) v += res[(size_t)r * rs + c];
     if (relu) v = fmaxf(v, 0.f);
     y[(size_t)r * ys + c] = v;
+    if (ysplit) {          // FD_FMT_SPLIT_BF16 copy for the tensor-core consumers (next conv, its weight gradient)
+      const unsigned short hi = bf16_bits_rn(v);
+      unsigned short* o = ysplit + (size_t)r * 2 * split_ctot + c;
+      o[0] = hi;
+      o[split_ctot] = bf16_bits_rn(v - __uint_as_float((unsigned)hi << 16));
+    }
   }
 }
 
@@ -444,7 +451,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int dys, const float* __restri
                     const float* __restrict__ x, int xs, int C, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ c1,
                     const float* __restrict__ c2, float* __restrict__ dx, int dxs, float* __restrict__ dres, int drs,
-                    const int32_t* __restrict__ d_n, long long n_cap) {
+                    unsigned short* __restrict__ dxsplit, const int32_t* __restrict__ d_n, long long n_cap) {
   const long long n = d_n ? min((long long)*d_n, n_cap) : n_cap;
   const long long total = n * C;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -456,7 +463,14 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int dys, const float* __restri
     const float is = invstd[c];
     const float xh = (x[(size_t)r * xs + c] - mean[c]) * is;
     const float g = gamma ? gamma[c] : 1.f;
-    dx[(size_t)r * dxs + c] = g * is * (dz - c1[c] - xh * c2[c]);
+    const float d = g * is * (dz - c1[c] - xh * c2[c]);
+    dx[(size_t)r * dxs + c] = d;
+    if (dxsplit) {         // dense FD_FMT_SPLIT_BF16 copy [rows][C hi | C lo] for the data- / weight-gradient convolutions
+      const unsigned short hi = bf16_bits_rn(d);
+      unsigned short* o = dxsplit + (size_t)r * 2 * C + c;
+      o[0] = hi;
+      o[C] = bf16_bits_rn(d - __uint_as_float((unsigned)hi << 16));
+    }
     if (dres) dres[(size_t)r * drs + c] = dz;
   }
 }
@@ -636,6 +650,7 @@ static int wgrad_entry(const fd_conv_desc* d, float* d_dw, float* ws, size_t ws_
       FD_REQUIRE(d->d_nbr && d->nbr_stride >= d->n_out_cap, "fd_conv_wgrad: bad neighbour table");
       FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY && d->out_stride >= d->cout, "fd_conv_wgrad: identity out rows only");
       a.n_in_cap = d->n_in_cap;
+      a.in_split = d->d_in_split; a.out_split = d->d_out_split;
       if (need) { *need = wgrad_ws_bytes(a, d->precision); return 0; }
       return launch_wgrad(a, d_dw, stream, d->precision, ws, ws_bytes);
     case FD_GATHER_CONV2D:
@@ -643,6 +658,7 @@ static int wgrad_entry(const fd_conv_desc* d, float* d_dw, float* ws, size_t ws_
       FD_REQUIRE(d->n_out_cap == d->B * d->Hout * d->Wout && !d->d_n_out, "fd_conv_wgrad: conv2d rows must be B*Hout*Wout");
       FD_REQUIRE(d->out_map == FD_OUTMAP_IDENTITY && d->out_stride >= d->cout, "fd_conv_wgrad: identity out rows only");
       a.n_in_cap = d->B * d->Hin * d->Win;
+      a.in_split = d->d_in_split; a.out_split = d->d_out_split;
       if (need) { *need = wgrad_ws_bytes(a, d->precision); return 0; }
       return launch_wgrad(a, d_dw, stream, d->precision, ws, ws_bytes);
     case FD_GATHER_CONVT2D: {
@@ -698,22 +714,24 @@ int fd_bn_train_stats(const float* d_x, int x_stride, int C, const int32_t* d_n,
 }
 
 int fd_affine_act(const float* d_x, int x_stride, int C, const float* d_scale, const float* d_shift,
-                  const float* d_res, int res_stride, int relu, float* d_y, int y_stride, const int32_t* d_n,
-                  int64_t n_cap, void* stream) {
+                  const float* d_res, int res_stride, int relu, float* d_y, int y_stride, void* d_y_split,
+                  int split_ctot, const int32_t* d_n, int64_t n_cap, void* stream) {
   using namespace fd;
+  FD_REQUIRE(!d_y_split || split_ctot >= C, "fd_affine_act: split_ctot < C");
   FD_REQUIRE(d_x && d_y && C >= 1 && x_stride >= C && y_stride >= C && (!d_res || res_stride >= C) && n_cap >= 0,
              "fd_affine_act: bad argument");
   if (n_cap == 0) return 0;
   affine_act_kernel<<<persistent_grid(ceil_div(n_cap * C, 256), 8), 256, 0, (cudaStream_t)stream>>>(
-      d_x, x_stride, C, d_scale, d_shift, d_res, res_stride, relu, d_y, y_stride, d_n, n_cap);
+      d_x, x_stride, C, d_scale, d_shift, d_res, res_stride, relu, d_y, y_stride, (unsigned short*)d_y_split, split_ctot, d_n,
+      n_cap);
   FD_LAUNCHED();
   return 0;
 }
 
 int fd_bn_backward(const float* d_dy, int dy_stride, const float* d_y, int y_stride, int relu, const float* d_x,
                    int x_stride, int C, const int32_t* d_n, int64_t n_cap, const float* d_mean,
-                   const float* d_invstd, const float* d_gamma, float* d_dx, int dx_stride, float* d_dres,
-                   int dres_stride, float* d_dgamma, float* d_dbeta, void* d_workspace, void* stream_) {
+                   const float* d_invstd, const float* d_gamma, float* d_dx, int dx_stride, void* d_dx_split,
+                   float* d_dres, int dres_stride, float* d_dgamma, float* d_dbeta, void* d_workspace, void* stream_) {
   using namespace fd;
   cudaStream_t stream = (cudaStream_t)stream_;
   FD_REQUIRE(d_dy && d_x && d_mean && d_invstd && d_dx && d_workspace && C >= 1 && n_cap >= 1,
@@ -737,7 +755,7 @@ int fd_bn_backward(const float* d_dy, int dy_stride, const float* d_y, int y_str
   FD_LAUNCHED();
   bn_bwd_apply_kernel<<<persistent_grid(ceil_div(n_cap * C, 256), 8), 256, 0, stream>>>(
       d_dy, dy_stride, d_y, y_stride, relu, d_x, x_stride, C, d_mean, d_invstd, d_gamma, c1, c2, d_dx, dx_stride,
-      d_dres, dres_stride, d_n, n_cap);
+      d_dres, dres_stride, (unsigned short*)d_dx_split, d_n, n_cap);
   FD_LAUNCHED();
   return 0;
 }

@@ -764,12 +764,20 @@ int conv_wgrad_os(const ConvArgs& a, float* partial, void* extra, cudaStream_t s
   char* e = (char*)(((uintptr_t)extra + 255) & ~(uintptr_t)255);
   unsigned short* xs = (unsigned short*)e;
   unsigned short* ys = (unsigned short*)(e + wos_align((size_t)a.n_in_cap * a.cin * 4));
-  split_rows_kernel<<<persistent_grid(ceil_div((int64_t)a.n_in_cap * (a.cin / 8), 256), 8), 256, 0, stream>>>(
-      a.in, a.in_stride, a.cin, nullptr, a.n_in_cap, xs);
-  FD_LAUNCHED();
-  split_rows_kernel<<<persistent_grid(ceil_div((int64_t)a.n_cap * (a.cout / 8), 256), 8), 256, 0, stream>>>(
-      a.out, a.out_stride, a.cout, a.d_n, a.n_cap, ys);
-  FD_LAUNCHED();
+  if (a.in_split) {
+    xs = (unsigned short*)a.in_split;
+  } else {
+    split_rows_kernel<<<persistent_grid(ceil_div((int64_t)a.n_in_cap * (a.cin / 8), 256), 8), 256, 0, stream>>>(
+        a.in, a.in_stride, a.cin, nullptr, a.n_in_cap, xs);
+    FD_LAUNCHED();
+  }
+  if (a.out_split) {
+    ys = (unsigned short*)a.out_split;
+  } else {
+    split_rows_kernel<<<persistent_grid(ceil_div((int64_t)a.n_cap * (a.cout / 8), 256), 8), 256, 0, stream>>>(
+        a.out, a.out_stride, a.cout, a.d_n, a.n_cap, ys);
+    FD_LAUNCHED();
+  }
   ConvArgs s = a;
   s.in = reinterpret_cast<const float*>(xs); s.in_stride = a.cin; s.in_ctot = a.cin; s.in_fmt = FD_FMT_SPLIT_BF16;
   s.out = reinterpret_cast<float*>(ys); s.out_stride = a.cout; s.out_ctot = a.cout; s.out_fmt = FD_FMT_SPLIT_BF16;

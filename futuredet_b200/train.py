@@ -29,24 +29,36 @@ from .sparse import SparseConvTensor, SparseSequential, _SparseConvBase
 
 
 # ------------------------------------------------------------------------------------------------ tape
+# Tensor-core arm: the kernels that PRODUCE an activation or a conv-output gradient (fd_affine_act, fd_bn_backward)
+# also write an FD_FMT_SPLIT_BF16 copy of it, and the convolutions that CONSUME it (forward, data gradient, weight
+# gradient) gather those ready-made bf16 planes with cp.async / TMA tiles instead of converting fp32 rows inside their
+# producer warps (the values are the same hi / lo pairs either way: results are bit-identical).  fp32 stays the
+# canonical copy for everything else (BatchNorm statistics and backward, residual sums, the loss).
+SPLIT_COPIES = True
+
+
 class Var:
-    """An activation with a gradient slot."""
+    """An activation with a gradient slot.  `s` / `grad_s`: optional split-bf16 copies of `t` / the gradient (fp32-typed
+    tensors of the same shape), see SPLIT_COPIES."""
 
     def __init__(self, t, needs_grad=True, n_dev=None, n_cap=None):
         self.t, self.needs_grad, self.n_dev, self.n_cap = t, needs_grad, n_dev, n_cap
         self._grad = None
+        self.s = None
+        self.grad_s = None
 
     @property
     def grad(self):
         return self._grad
 
-    def accumulate(self, g):
+    def accumulate(self, g, gs=None):
         if not self.needs_grad:
             return
         if self._grad is None:
-            self._grad = g
+            self._grad, self.grad_s = g, gs
         else:
             T.add_rows_(self._grad, g, self.n_dev, self.n_cap)
+            self.grad_s = None               # the split copy no longer matches the sum
 
 
 class SliceVar:
@@ -57,6 +69,7 @@ class SliceVar:
         self.t = parent.t[..., c0:c0 + c]
         self.needs_grad = True
         self.n_dev = self.n_cap = None
+        self.s = self.grad_s = None          # the split copy lives in parent.s (full width)
 
     @property
     def grad(self):
@@ -165,7 +178,9 @@ def sparse_conv_train(tape, x, conv, xt, grads, prec):
     bias = conv.bias.detach() if conv.bias is not None else None
     xin = x.t[..., :cin] if x.t.shape[-1] != cin else x.t
     p = _prec_for(prec, cin, K, x.t)
-    y_t = ops.sparse_conv(ops.Feat(x.t, "fp32", 0, cin), w, rb, None, bias, None, False, precision=p, out_fmt="fp32")
+    xs = x.s if (p != "fp32" and x.s is not None and x.s.shape[-1] == cin) else None
+    xf = ops.Feat(xs, "split", 0, cin) if xs is not None else ops.Feat(x.t, "fp32", 0, cin)
+    y_t = ops.sparse_conv(xf, w, rb, None, bias, None, False, precision=p, out_fmt="fp32")
     y = Var(y_t, True, rb.n_out_dev, rb.n_out_cap)
     if conv.subm:
         out = xt._like(y_t)
@@ -178,8 +193,10 @@ def sparse_conv_train(tape, x, conv, xt, grads, prec):
         gy = y.grad
         if gy is None:
             return
+        gys = y.grad_s
         if grads.has(conv.weight):
-            T.sparse_conv_wgrad(xin, gy, rb, grads.grad(conv.weight).view(K, cin, cout), precision=prec)
+            T.sparse_conv_wgrad(xin, gy, rb, grads.grad(conv.weight).view(K, cin, cout), precision=prec,
+                                x_split=xs, dy_split=gys)
             grads.done(conv.weight)
         if conv.bias is not None and grads.has(conv.bias):
             T.col_sum(gy, grads.grad(conv.bias), rb.n_out_dev, rb.n_out_cap)
@@ -191,30 +208,42 @@ def sparse_conv_train(tape, x, conv, xt, grads, prec):
             else:
                 table = T.TableView(T.rulebook_transpose(rb, n_in_cap), K, n_in_dev, n_in_cap)
                 wt = w.transpose(1, 2).contiguous()
-            gx = ops.sparse_conv(gy, wt, table, precision=pd, out_fmt="fp32")
+            gin = ops.Feat(gys, "split", 0, cout) if (gys is not None and pd != "fp32") else gy
+            gx = ops.sparse_conv(gin, wt, table, precision=pd, out_fmt="fp32")
             x.accumulate(gx)
 
     tape.add(backward)
     return y, out
 
 
-def bn_train(tape, x, bn, grads, residual=None, relu=True, out=None):
+def bn_train(tape, x, bn, grads, residual=None, relu=True, out=None, prec="fp32"):
     """y = act(batch_norm_train(x) (+ residual)); x.t [rows, C] (rows < n_dev active)."""
     saved = T.bn_train_stats(x.t, bn, x.n_dev, x.n_cap)
+    Cc = x.t.shape[-1]
+    want_split = SPLIT_COPIES and prec != "fp32" and Cc % 8 == 0 and x.t.is_contiguous()
+    split = None
+    if want_split and out is None:
+        split = (torch.empty(x.t.shape, dtype=torch.float32, device=x.t.device), 0)
+    elif want_split and isinstance(out, SliceVar) and out.parent.s is not None:
+        split = (out.parent.s, out.c0)
     y_t = T.affine_act(x.t, saved.scale, saved.shift, residual.t if residual is not None else None, relu,
-                       out.t if out is not None else None, x.n_dev, x.n_cap)
+                       out.t if out is not None else None, x.n_dev, x.n_cap, split=split)
     y = out if out is not None else Var(y_t, True, x.n_dev, x.n_cap)
+    if split is not None and out is None:
+        y.s = split[0]
 
     def backward():
         gy = y.grad
         if gy is None:
             return
         want_res = residual is not None and residual.needs_grad
-        dx, dres = T.bn_backward(gy, y.t, relu, x.t, saved, bn.weight.detach(), grads.scratch(bn.weight),
-                                 grads.scratch(bn.bias), want_res, x.n_dev, x.n_cap)
+        ws = want_split and isinstance(x, Var)
+        r = T.bn_backward(gy, y.t, relu, x.t, saved, bn.weight.detach(), grads.scratch(bn.weight),
+                          grads.scratch(bn.bias), want_res, x.n_dev, x.n_cap, want_split=ws)
+        dx, dres, dxs = r if ws else (r[0], r[1], None)
         grads.done(bn.weight)
         grads.done(bn.bias)
-        x.accumulate(dx)
+        x.accumulate(dx, dxs)
         if want_res:
             residual.accumulate(dres)
 
@@ -232,17 +261,19 @@ def conv2d_train(tape, x, conv, grads, prec, pad=None, out=None):
     ksize, stride = tuple(conv.kernel_size), tuple(conv.stride)
     B, H, W = x.t.shape[0], x.t.shape[1], x.t.shape[2]
     p = _prec_for(prec, cin, 1 if transposed else K, x.t)
-    y_t = ops.conv2d_nhwc(x.t, w, ksize, stride, padding, None, bias, False, out=out.t if out is not None else None,
-                          precision=p, transposed=transposed, out_fmt="fp32")
+    xs = x.s if (p != "fp32" and getattr(x, "s", None) is not None and x.s.shape[-1] == cin) else None
+    y_t = ops.conv2d_nhwc(ops.Feat(xs, "split") if xs is not None else x.t, w, ksize, stride, padding, None, bias, False,
+                          out=out.t if out is not None else None, precision=p, transposed=transposed, out_fmt="fp32")
     y = out if out is not None else Var(y_t)
 
     def backward():
         gy = y.grad
         if gy is None:
             return
+        gys = y.grad_s if isinstance(y, Var) else None
         if grads.has(conv.weight):
             gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=w.device)
-            T.conv2d_wgrad(x.t, gy, gw, ksize, stride, padding, transposed, precision=prec)
+            T.conv2d_wgrad(x.t, gy, gw, ksize, stride, padding, transposed, precision=prec, x_split=xs, dy_split=gys)
             g4 = gw.view(ksize[0], ksize[1], cin, cout)
             # back to the parameter layout: Conv2d [Cout,Cin,kh,kw], ConvTranspose2d [Cin,Cout,kh,kw]
             grads.grad(conv.weight).copy_(g4.permute(2, 3, 0, 1) if transposed else g4.permute(3, 2, 0, 1))
@@ -253,11 +284,12 @@ def conv2d_train(tape, x, conv, grads, prec, pad=None, out=None):
         if x.needs_grad:
             wt = w.transpose(1, 2).contiguous()
             pd = _prec_for(prec, cout, K, gy)
+            gin = ops.Feat(gys, "split") if (gys is not None and pd != "fp32") else gy
             if transposed:   # each input pixel fed k*k output pixels: a k x k stride-k conv over dL/dy
-                gx = ops.conv2d_nhwc(gy, wt, ksize, stride, (0, 0), precision=pd, out_fmt="fp32")
+                gx = ops.conv2d_nhwc(gin, wt, ksize, stride, (0, 0), precision=pd, out_fmt="fp32")
                 gx = gx.t if isinstance(gx, ops.Feat) else gx
             else:
-                gx = T.conv2d_dgrad(gy, wt, (H, W), ksize, stride, padding, precision=pd)
+                gx = T.conv2d_dgrad(gin, wt, (H, W), ksize, stride, padding, precision=pd)
             x.accumulate(gx)
 
     tape.add(backward)
@@ -291,16 +323,16 @@ class NativeTrainer:
                 i += 1
                 if i < len(mods) and isinstance(mods[i], nn.BatchNorm1d):
                     relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
-                    x = bn_train(tape, x, mods[i], self.grads, None, relu)
+                    x = bn_train(tape, x, mods[i], self.grads, None, relu, prec=self.precision)
                     i += 2 if relu else 1
             elif hasattr(m, "conv1") and hasattr(m, "bn2"):        # SparseBasicBlock (scn.py:64-80)
                 if m.downsample is not None:
                     raise NotImplementedError("SparseBasicBlock.downsample is not used by the reference backbone")
                 identity = x
                 o, xt1 = sparse_conv_train(tape, x, m.conv1, xt, self.grads, self.precision)
-                o = bn_train(tape, o, m.bn1, self.grads, None, True)
+                o = bn_train(tape, o, m.bn1, self.grads, None, True, prec=self.precision)
                 o, xt = sparse_conv_train(tape, o, m.conv2, xt1, self.grads, self.precision)
-                x = bn_train(tape, o, m.bn2, self.grads, identity, True)
+                x = bn_train(tape, o, m.bn2, self.grads, identity, True, prec=self.precision)
                 i += 1
             else:
                 raise NotImplementedError("no native training kernel for %s" % type(m).__name__)
@@ -336,10 +368,10 @@ class NativeTrainer:
         for i, block in enumerate(neck.blocks):
             mods = list(block)
             x = conv2d_train(tape, x, mods[1], self.grads, self.precision, pad=(1, 1))     # ZeroPad2d(1) + conv(pad 0)
-            x = bn_train(tape, x, mods[2], self.grads, None, True)
+            x = bn_train(tape, x, mods[2], self.grads, None, True, prec=self.precision)
             for k in range(4, len(mods), 3):
                 x = conv2d_train(tape, x, mods[k], self.grads, self.precision)
-                x = bn_train(tape, x, mods[k + 1], self.grads, None, True)
+                x = bn_train(tape, x, mods[k + 1], self.grads, None, True, prec=self.precision)
             j = i - neck._upsample_start_idx
             if j >= 0:
                 up, bn = neck.deblocks[j][0], neck.deblocks[j][1]
@@ -348,15 +380,17 @@ class NativeTrainer:
                     Ho, Wo = u.t.shape[1], u.t.shape[2]
                     out = Var(torch.empty((B, Ho, Wo, sum(neck._num_upsample_filters)), dtype=torch.float32,
                                           device=u.t.device))
+                    if SPLIT_COPIES and self.precision != "fp32":
+                        out.s = torch.empty_like(out.t)      # split copy of the concatenated map (the deblocks fill slices)
                 c = neck._num_upsample_filters[j]
-                bn_train(tape, u, bn, self.grads, None, True, out=SliceVar(out, col, c))
+                bn_train(tape, u, bn, self.grads, None, True, out=SliceVar(out, col, c), prec=self.precision)
                 col += c
         return out if out is not None else x
 
     # ---- head ----------------------------------------------------------------------------------------
     def _head(self, tape, head, x):
         s = conv2d_train(tape, x, head.shared_conv[0], self.grads, self.precision)
-        s = bn_train(tape, s, head.shared_conv[1], self.grads, None, True)
+        s = bn_train(tape, s, head.shared_conv[1], self.grads, None, True, prec=self.precision)
         B, H, W = s.t.shape[0], s.t.shape[1], s.t.shape[2]
         preds, outs = [], []
         for task in head.tasks:
@@ -377,7 +411,7 @@ class NativeTrainer:
                             raise NotImplementedError("SepHead: final conv followed by BN/ReLU")
                         y = conv2d_train(tape, y, conv, self.grads, self.precision)
                         if bnm is not None:
-                            y = bn_train(tape, y, bnm, self.grads, None, relu)
+                            y = bn_train(tape, y, bnm, self.grads, None, relu, prec=self.precision)
                         elif relu:
                             raise NotImplementedError("SepHead: conv + ReLU without BatchNorm")
                 ret[h] = out.t[..., col:col + c].permute(0, 3, 1, 2)

@@ -87,8 +87,18 @@ def _run_wgrad(lib, d, dw, what):
         L.check(lib.fd_conv_wgrad(C.byref(d), _ptr(dw), _stream()), what)
 
 
-def sparse_conv_wgrad(x, dy, rb, dw, precision="fp32"):
-    """dw [K,Cin,Cout] += sum over rulebook pairs of x[i]^T dy[o] (dw must be zeroed by the caller)."""
+def _split_ptr(t, like):
+    """Pointer of a dense FD_FMT_SPLIT_BF16 copy of `like` (an fp32-typed tensor of the same shape), or None."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.shape != like.shape or not like.is_contiguous():
+        raise RuntimeError("split copy must be a contiguous fp32-typed tensor shaped like its fp32 original")
+    return t.data_ptr()
+
+
+def sparse_conv_wgrad(x, dy, rb, dw, precision="fp32", x_split=None, dy_split=None):
+    """dw [K,Cin,Cout] += sum over rulebook pairs of x[i]^T dy[o] (dw must be zeroed by the caller).
+    x_split / dy_split: optional split-bf16 copies of x / dy (written by affine_act / bn_backward)."""
     lib = L.load()
     x, xs, cin = _rows(x)
     dy, dys, cout = _rows(dy)
@@ -105,11 +115,12 @@ def sparse_conv_wgrad(x, dy, rb, dw, precision="fp32"):
     d.out_map = L.OUTMAP_IDENTITY
     d.precision = L.PRECISIONS[precision]
     d.n_in_cap = n_rows(x)
+    d.d_in_split = _split_ptr(x_split, x); d.d_out_split = _split_ptr(dy_split, dy)
     _run_wgrad(lib, d, dw, "fd_conv_wgrad(sparse)")
     return dw
 
 
-def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False, precision="fp32"):
+def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False, precision="fp32", x_split=None, dy_split=None):
     """Weight gradient of conv2d_nhwc / its ConvTranspose2d(k == s) form.  x [B,H,W,Cin], dy [B,Ho,Wo,Cout] (channel
     slices allowed), dw [kh*kw, Cin, Cout] zeroed by the caller."""
     lib = L.load()
@@ -128,6 +139,8 @@ def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False, precision=
     d.out_map = L.OUTMAP_IDENTITY
     d.n_out_cap = B * H * W if transposed else B * Ho * Wo
     d.precision = L.PRECISIONS[precision]
+    if not transposed:
+        d.d_in_split = _split_ptr(x_split, x); d.d_out_split = _split_ptr(dy_split, dy)
     _run_wgrad(lib, d, dw, "fd_conv_wgrad(conv2d)")
     return dw
 
@@ -136,6 +149,10 @@ def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False, precision=
 def conv2d_dgrad(dy, w_t, in_hw, ksize, stride, padding, precision="fp32"):
     """dL/dx [B,H,W,Cin] of y = conv2d(x, w): gather of dy through FD_GATHER_CONV2D_DGRAD with w_t [K, Cout, Cin]."""
     lib = L.load()
+    fmt = 0
+    if isinstance(dy, ops.Feat):                     # split-bf16 copy of dL/dy (dense rows)
+        fmt = 1 if dy.fmt == "split" else 0
+        dy = dy.t
     dy, dys, cout = _rows(dy)
     B, Ho, Wo = dy.shape[0], dy.shape[1], dy.shape[2]
     H, W = in_hw
@@ -144,7 +161,7 @@ def conv2d_dgrad(dy, w_t, in_hw, ksize, stride, padding, precision="fp32"):
         raise RuntimeError("w_t must be contiguous [K, Cout, Cin]")
     dx = torch.empty((B, H, W, cin), dtype=torch.float32, device=dy.device)
     d = L.ConvDesc()
-    d.d_in = dy.data_ptr(); d.in_stride = dys; d.cin = cout; d.in_format = 0; d.in_ctot = cout
+    d.d_in = dy.data_ptr(); d.in_stride = dys; d.cin = cout; d.in_format = fmt; d.in_ctot = cout
     d.d_w = w_t.data_ptr(); d.cout = cin; d.K = K
     p = L.PRECISIONS[precision]
     if p != L.PREC_FP32:
@@ -190,7 +207,9 @@ def bn_train_stats(x, bn, n_dev=None, n_cap=None):
     return s
 
 
-def affine_act(x, scale, shift, residual=None, relu=False, out=None, n_dev=None, n_cap=None):
+def affine_act(x, scale, shift, residual=None, relu=False, out=None, n_dev=None, n_cap=None, split=None):
+    """split = (fp32-typed tensor [..., Ctot], c0): also write an FD_FMT_SPLIT_BF16 copy of the result into channels
+    [c0, c0 + C) of that buffer (rows of Ctot bf16 hi | Ctot bf16 lo)."""
     lib = L.load()
     x, xs, Cc = _rows(x)
     n_cap = n_rows(x) if n_cap is None else n_cap
@@ -200,14 +219,22 @@ def affine_act(x, scale, shift, residual=None, relu=False, out=None, n_dev=None,
     rs = 0
     if residual is not None:
         residual, rs, _ = _rows(residual)
+    sp, sct = None, 0
+    if split is not None:
+        st, c0 = split
+        if st.dtype != torch.float32 or not st.is_contiguous() or n_rows(st) != n_rows(x):
+            raise RuntimeError("split buffer must be a contiguous fp32-typed tensor with the rows of x")
+        sct = int(st.shape[-1])
+        sp = C.c_void_p(st.data_ptr() + 2 * int(c0))
     rc = lib.fd_affine_act(_ptr(x), xs, Cc, _ptr(scale), _ptr(shift), _ptr(residual), rs, int(bool(relu)), _ptr(out), ys,
-                           _ptr(n_dev), n_cap, _stream())
+                           sp, sct, _ptr(n_dev), n_cap, _stream())
     L.check(rc, "fd_affine_act")
     return out
 
 
-def bn_backward(dy, y, relu, x, saved, gamma, dgamma, dbeta, want_dres=False, n_dev=None, n_cap=None):
-    """-> (dx, dres | None); dgamma / dbeta are written in place."""
+def bn_backward(dy, y, relu, x, saved, gamma, dgamma, dbeta, want_dres=False, n_dev=None, n_cap=None, want_split=False):
+    """-> (dx, dres | None[, dx_split | None]); dgamma / dbeta are written in place.  want_split: also return a dense
+    split-bf16 copy of dx (fp32-typed tensor shaped like dx) for the tensor-core data- / weight-gradient convolutions."""
     lib = L.load()
     dy, dys, Cc = _rows(dy)
     x, xs, _ = _rows(x)
@@ -217,12 +244,15 @@ def bn_backward(dy, y, relu, x, saved, gamma, dgamma, dbeta, want_dres=False, n_
         y, ys, _ = _rows(y)
     dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
     dres = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_dres else None
+    dxs = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_split else None
     ws = _workspace(x.device, lib.fd_bn_workspace_bytes(Cc))
     rc = lib.fd_bn_backward(_ptr(dy), dys, _ptr(y) if relu else None, ys, int(bool(relu)), _ptr(x), xs, Cc, _ptr(n_dev),
-                            n_cap, _ptr(saved.mean), _ptr(saved.invstd), _ptr(gamma), _ptr(dx), dx.stride(-2),
+                            n_cap, _ptr(saved.mean), _ptr(saved.invstd), _ptr(gamma), _ptr(dx), dx.stride(-2), _ptr(dxs),
                             _ptr(dres), dres.stride(-2) if want_dres else 0, _ptr(dgamma), _ptr(dbeta), _ptr(ws),
                             _stream())
     L.check(rc, "fd_bn_backward")
+    if want_split:
+        return dx, dres, dxs
     return dx, dres
 
 

@@ -184,6 +184,9 @@ typedef struct fd_conv_desc {
   int32_t        n_in_cap;    /* fd_conv_wgrad* with FD_GATHER_TABLE: rows of d_in (lets the tcgen05 arm pre-split
                                * the layer input once); 0 = unknown (the per-offset tcgen05 kernel is used).  Ignored
                                * by fd_conv_forward.                                                              */
+  const void*    d_in_split;  /* fd_conv_wgrad_det, optional: dense FD_FMT_SPLIT_BF16 copies ([rows][C hi | C lo]) of   */
+  const void*    d_out_split; /* d_in / dL/dy that the caller already holds (fd_affine_act / fd_bn_backward write    */
+                              /* them); NULL: the tcgen05 arm splits the fp32 rows into its workspace             */
 } fd_conv_desc;
 
 enum { FD_GATHER_TABLE = 0, FD_GATHER_CONV2D = 1, FD_GATHER_CONVT2D = 2,
@@ -277,16 +280,20 @@ int fd_bn_train_stats(const float* d_x, int x_stride, int C, const int32_t* d_n,
                       float momentum, const float* d_gamma, const float* d_beta, float* d_running_mean,
                       float* d_running_var, float* d_mean, float* d_invstd, float* d_scale, float* d_shift,
                       void* d_workspace, void* stream);
-/* y = act(x * scale[c] + shift[c] (+ res)), rows < n; scale/shift/res may be NULL (1 / 0 / none). */
+/* y = act(x * scale[c] + shift[c] (+ res)), rows < n; scale/shift/res may be NULL (1 / 0 / none).  d_y_split
+ * (optional): an FD_FMT_SPLIT_BF16 copy of y is written beside it -- rows of 2*split_ctot bf16, the pointer already
+ * offset to the first channel of the slice -- so that the tensor-core convolutions that consume y (forward, weight
+ * gradient) gather ready-made bf16 planes.                                                                      */
 int fd_affine_act(const float* d_x, int x_stride, int C, const float* d_scale, const float* d_shift,
-                  const float* d_res, int res_stride, int relu, float* d_y, int y_stride, const int32_t* d_n,
-                  int64_t n_cap, void* stream);
+                  const float* d_res, int res_stride, int relu, float* d_y, int y_stride, void* d_y_split,
+                  int split_ctot, const int32_t* d_n, int64_t n_cap, void* stream);
 /* Backward of y = act(bn(x) (+ res)):  dz = dy * [y > 0] (relu) ;  dgamma = sum dz*xhat ; dbeta = sum dz ;
- * dx = gamma*invstd*(dz - dbeta/n - xhat*dgamma/n) ;  dres = dz (d_dres may be NULL).                        */
+ * dx = gamma*invstd*(dz - dbeta/n - xhat*dgamma/n) ;  dres = dz (d_dres may be NULL).  d_dx_split (optional): dense
+ * FD_FMT_SPLIT_BF16 copy of dx ([rows][C hi | C lo]) for the data- / weight-gradient convolutions.             */
 int fd_bn_backward(const float* d_dy, int dy_stride, const float* d_y, int y_stride, int relu, const float* d_x,
                    int x_stride, int C, const int32_t* d_n, int64_t n_cap, const float* d_mean,
-                   const float* d_invstd, const float* d_gamma, float* d_dx, int dx_stride, float* d_dres,
-                   int dres_stride, float* d_dgamma, float* d_dbeta, void* d_workspace, void* stream);
+                   const float* d_invstd, const float* d_gamma, float* d_dx, int dx_stride, void* d_dx_split,
+                   float* d_dres, int dres_stride, float* d_dgamma, float* d_dbeta, void* d_workspace, void* stream);
 /* out[c] = sum_rows x[r, c]  (conv bias gradient). */
 int fd_col_sum(const float* d_x, int x_stride, int C, const int32_t* d_n, int64_t n_cap, float* d_out,
                void* d_workspace, void* stream);

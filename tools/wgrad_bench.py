@@ -22,10 +22,13 @@ with torch.no_grad():
 coords, nd, cap = vox["coords"], vox["total"], int(vox["coords"].shape[0])
 shape = [41, 1440, 1440]
 REP = 5
+ONLY = int(os.environ.get("FD_WG_LEVEL", "0"))      # run one channel width only (ncu captures)
 for lvl, C in enumerate((16, 32, 64, 128)):
     if lvl > 0:
         rbs, _ = ops.rulebook_conv(coords, nd, cap, 1, shape, [3, 3, 3], [2, 2, 2], [1, 1, 1] if lvl < 3 else [0, 1, 1])
         coords, nd, cap, shape = rbs.out_coords, rbs.n_out_dev, rbs.n_out_cap, rbs.out_shape
+    if ONLY and C != ONLY:
+        continue
     rb, _ = ops.rulebook_subm(coords, nd, cap, shape, [3, 3, 3], batch_size=1)
     m = int(nd.item())
     x = torch.randn((cap, C), device=dev)
