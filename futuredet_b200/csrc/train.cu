@@ -187,13 +187,37 @@ conv_wgrad_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict__ 
   }
 }
 
-// dW[e] += sum over slots (ascending) of partial[slot][e]: the ordered reduce of the deterministic weight gradient
+// dW[e] += sum over slots of partial[slot][e]: the ordered reduce of the deterministic weight gradient.  A block is 32
+// consecutive elements x 8 slot lanes (warp w adds slots w, w + 8, ... in ascending order, 4 loads in flight), then
+// the 8 lane sums are added in lane order: a fixed summation tree, so the result is bit-identical run to run.  (One
+// thread per element walking all slots took ~100 us on the small head layers: hundreds of dependent round trips.)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int slots, long long elems, float* __restrict__ dw) {
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += (long long)gridDim.x * blockDim.x) {
+  __shared__ float sh[8][32];
+  const int el = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (long long e0 = (long long)blockIdx.x * 32; e0 < elems; e0 += (long long)gridDim.x * 32) {
+    const long long e = e0 + el;
     float s = 0.f;
-    for (int c = 0; c < slots; ++c) s = __fadd_rn(s, partial[(size_t)c * elems + e]);
-    dw[e] = __fadd_rn(dw[e], s);
+    if (e < elems) {
+      int c = sl;
+      for (; c + 24 < slots; c += 32) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldcs(partial + (size_t)(c + 8 * j) * elems + e);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s = __fadd_rn(s, v[j]);
+      }
+      for (; c < slots; c += 8) s = __fadd_rn(s, __ldcs(partial + (size_t)c * elems + e));
+    }
+    sh[sl][el] = s;
+    __syncthreads();
+    if (sl == 0 && e < elems) {
+      float t = sh[0][el];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) t = __fadd_rn(t, sh[j][el]);
+      dw[e] = __fadd_rn(dw[e], t);
+    }
+    __syncthreads();
   }
 }
 
@@ -286,7 +310,7 @@ static int launch_wgrad(const ConvArgs& a, float* dw, cudaStream_t stream, int p
     }
   }
   if (rc || !ws) return rc;
-  wgrad_reduce_kernel<<<persistent_grid(ceil_div(elems, 256), 8), 256, 0, stream>>>(ws, slots, elems, dw);
+  wgrad_reduce_kernel<<<persistent_grid(ceil_div(elems, 32), 8), 256, 0, stream>>>(ws, slots, elems, dw);
   FD_LAUNCHED();
   return 0;
 }
@@ -412,8 +436,13 @@ static int red_cp(int C) {
   while (cp < C && cp < RED_THREADS) cp <<= 1;
   return cp;
 }
-static int red_blocks(long long n_cap) {
+// blocks of a reduction over [n, C]: by rows for the long sparse levels, by elements for the short, wide BEV maps
+// (8100 x 256 got 32 blocks = a fifth of the GPU and took as long as a 40x larger sparse level)
+static int red_blocks(long long n_cap, int C = 1) {
   long long g = (n_cap + 255) / 256;
+  const long long ge = (n_cap * C + 8191) / 8192;
+  if (ge > g) g = ge;
+  if (g > n_cap) g = n_cap;
   if (g < 1) g = 1;
   if (g > RED_MAX_BLOCKS) g = RED_MAX_BLOCKS;
   return (int)g;
@@ -700,7 +729,7 @@ int fd_bn_train_stats(const float* d_x, int x_stride, int C, const int32_t* d_n,
   RedArgs r{};
   r.mode = RED_STATS; r.x = d_x; r.x_stride = x_stride; r.C = C; r.cp = red_cp(C);
   r.d_n = d_n; r.n_cap = n_cap; r.partial = (double*)d_workspace;
-  const int G = red_blocks(n_cap);
+  const int G = red_blocks(n_cap, C);
   red_partial_kernel<<<G, RED_THREADS, 0, stream>>>(r);
   FD_LAUNCHED();
   FinArgs f{};
@@ -743,7 +772,7 @@ int fd_bn_backward(const float* d_dy, int dy_stride, const float* d_y, int y_str
   r.mode = RED_BN_BWD; r.x = d_x; r.x_stride = x_stride; r.dy = d_dy; r.dy_stride = dy_stride;
   r.y = d_y; r.y_stride = y_stride; r.relu = relu; r.mean = d_mean; r.invstd = d_invstd;
   r.C = C; r.cp = red_cp(C); r.d_n = d_n; r.n_cap = n_cap; r.partial = (double*)d_workspace;
-  const int G = red_blocks(n_cap);
+  const int G = red_blocks(n_cap, C);
   red_partial_kernel<<<G, RED_THREADS, 0, stream>>>(r);
   FD_LAUNCHED();
   float* c1 = (float*)((char*)d_workspace + red_partial_bytes(C));
@@ -768,7 +797,7 @@ int fd_col_sum(const float* d_x, int x_stride, int C, const int32_t* d_n, int64_
   RedArgs r{};
   r.mode = RED_COLSUM; r.x = d_x; r.x_stride = x_stride; r.C = C; r.cp = red_cp(C);
   r.d_n = d_n; r.n_cap = n_cap; r.partial = (double*)d_workspace;
-  const int G = red_blocks(n_cap);
+  const int G = red_blocks(n_cap, C);
   red_partial_kernel<<<G, RED_THREADS, 0, stream>>>(r);
   FD_LAUNCHED();
   FinArgs f{};
