@@ -702,8 +702,12 @@ static int wgrad_entry(const fd_conv_desc* d, float* d_dw, float* ws, size_t ws_
         p.Hout = d->Hin; p.Wout = d->Win;
         p.out_map = OUTMAP_UPSAMPLE;
         p.up_s = d->sh; p.up_dy = k / d->kw; p.up_dx = k % d->kw;
-        if (need) { *need = wgrad_ws_bytes(p, FD_PREC_FP32); return 0; }
-        int rc = launch_wgrad(p, d_dw + (size_t)k * d->cin * d->cout, stream, FD_PREC_FP32, ws, ws_bytes);
+        // the tcgen05 arm handles a phase when the output-stationary kernel does (dY rows = the phase's pixels)
+        p.n_in_cap = d->B * d->Hin * d->Win;
+        p.in_split = d->d_in_split; p.out_split = d->d_out_split;
+        const int pp = (d->precision == FD_PREC_BF16X3 && wgrad_os_supported(p)) ? FD_PREC_BF16X3 : FD_PREC_FP32;
+        if (need) { *need = wgrad_ws_bytes(p, pp); return 0; }
+        int rc = launch_wgrad(p, d_dw + (size_t)k * d->cin * d->cout, stream, pp, ws, ws_bytes);
         if (rc) return rc;
       }
       return 0;

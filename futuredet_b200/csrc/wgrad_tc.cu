@@ -405,6 +405,7 @@ struct Plan {
   int NT;           // accumulator columns per group
   int tmem_cols;
   int chunks;
+  int co_tiles;     // 128-column slices of Cout (grid.z)
   int b_bytes;      // bytes of one dY ring slot
   int dbg;          // FD_WG_DBG triage bits: 1 no gathers, 2 no MMAs, 4 no proxy fence
 };
@@ -456,13 +457,21 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.d_n ? min(*a.d_n, a.n_cap) : a.n_cap;
   const int pass = blockIdx.y;
-  const int g0 = pass * pl.gpp, G = min(pl.gpp, pl.n_groups - g0);        // this pass's groups
+  // this pass's groups: the layer's groups spread evenly over the passes (14 groups in 4 passes: 3, 4, 3, 4)
+  const int g0 = (pass * pl.n_groups) / pl.passes, G = ((pass + 1) * pl.n_groups) / pl.passes - g0;
   const int rows_per_cta = ((n + (int)gridDim.x - 1) / (int)gridDim.x + KP - 1) & ~(KP - 1);
   const long long rb = (long long)blockIdx.x * rows_per_cta;
   const int row_begin = (int)min((long long)n, rb), row_end = (int)min((long long)n, rb + rows_per_cta);
   const int n_stages = (row_end - row_begin + KP - 1) / KP;
   const int cin = a.cin, cout = a.cout, NT = pl.NT;
+  const int co0 = blockIdx.z * 128;                      // this CTA's slice of the output channels (NT columns)
   float* pslot = partial ? partial + (size_t)blockIdx.x * a.K * cin * cout : nullptr;
+  // dY row (of the split copy) of output row o: identity, or the phase pixel of a ConvTranspose2d(k == s)
+  auto dy_row = [&](int o) -> size_t {
+    if (a.out_map == FD_OUTMAP_IDENTITY) return (size_t)o;
+    const int hw = a.Hin * a.Win, b = o / hw, r = o - b * hw, y = r / a.Win, x = r - y * a.Win;
+    return ((size_t)b * a.Hin * a.up_s + (size_t)y * a.up_s + a.up_dy) * (a.Win * a.up_s) + (size_t)x * a.up_s + a.up_dx;
+  };
   // (offset, first channel) of lane-slot `ls` of group `grp`
   auto group_k = [&](int grp, int ls, int& ch) -> int {
     if (cin >= 128) { ch = (grp % pl.ci_tiles) * 128 + ls; return grp / pl.ci_tiles; }
@@ -473,9 +482,9 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
   if (n_stages == 0) {                                   // a chunk without rows still owns (and zeroes) its tiles
     if (pslot)
       for (int g = 0; g < G; ++g)
-        for (int e = tid; e < 128 * cout; e += THREADS) {
-          int ch; const int k = group_k(g0 + g, e / cout, ch);
-          if (k < a.K) pslot[((size_t)k * cin + ch) * cout + e % cout] = 0.f;
+        for (int e = tid; e < 128 * NT; e += THREADS) {
+          int ch; const int k = group_k(g0 + g, e / NT, ch);
+          if (k < a.K) pslot[((size_t)k * cin + ch) * cout + co0 + e % NT] = 0.f;
         }
     return;
   }
@@ -574,8 +583,8 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
     // layers, the [K][64] slice of the neighbour table -- up to two stages ahead of the gather warps
     const char* ys = reinterpret_cast<const char*>(a.out);
     const size_t y_row = (size_t)cout * 4;
-    const int bchunks = cout >> 3, b_items = KP * bchunks;
-    const uint32_t b_plane = (uint32_t)((cout + 63) >> 6) * BLOCK_BYTES;
+    const int bchunks = NT >> 3, b_items = KP * bchunks;
+    const uint32_t b_plane = (uint32_t)((NT + 63) >> 6) * BLOCK_BYTES;
     const bool table = a.mode == FD_GATHER_TABLE;
     const bool idx_vec = table && (a.nbr_stride & 3) == 0 && (((uintptr_t)a.nbr) & 15) == 0 && (row_begin & 3) == 0;
     // index slice of stage si into ring slot si % IDX_SLOTS (after every gather warp has released its previous occupant)
@@ -613,7 +622,7 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
       for (int e = lane; e < b_items; e += 32) {
         const int r = e / bchunks, cc = e - r * bchunks;
         const uint32_t sz = o0 + r < row_end ? 16u : 0u;
-        const char* src = ys + (size_t)min(o0 + r, row_end - 1) * y_row + cc * 16;
+        const char* src = ys + dy_row(min(o0 + r, row_end - 1)) * y_row + co0 * 2 + cc * 16;
         const uint32_t d = bdst + (uint32_t)(cc >> 3) * BLOCK_BYTES + (uint32_t)r * ROWB + (uint32_t)(((cc & 7) ^ (r & 7)) << 4);
         cp_async16_sz(d, src, sz);
         cp_async16_sz(d + b_plane, src + cout * 2, sz);
@@ -625,7 +634,7 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
   } else if (lane == 0) {
     // ===================================== MMA ISSUER =====================================
     const uint32_t idesc = wg::idesc_mn(128, NT);
-    const uint32_t b_plane = (uint32_t)((cout + 63) >> 6) * BLOCK_BYTES;
+    const uint32_t b_plane = (uint32_t)((NT + 63) >> 6) * BLOCK_BYTES;
     // The barrier of the NEXT item (and, at a stage's last group, of the next dY stage) is probed with a non-blocking
     // test_wait issued BEFORE the current item's MMAs, so that its latency overlaps their issue (which blocks on
     // execution); a blocking wait only follows when the probe said "not yet".
@@ -675,7 +684,7 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
       const int ls = lq * 32 + lane;
       for (int g = half; g < G; g += 2) {
         int ch; const int k = group_k(g0 + g, ls, ch);
-        float* dst = (pslot ? pslot : dw) + ((size_t)k * cin + ch) * cout;
+        float* dst = (pslot ? pslot : dw) + ((size_t)k * cin + ch) * cout + co0;
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t v[16];
           wg::tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(g * NT + c0), v);
@@ -705,13 +714,14 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
 static bool wos_plan(const ConvArgs& a, wos::Plan* out) {
   const int cin = a.cin, cout = a.cout;
   const bool cin_ok = cin == 16 || cin == 32 || cin == 64 || (cin >= 128 && cin % 128 == 0);
-  const bool cout_ok = cout == 16 || cout == 32 || cout == 64 || cout == 128;
-  if (!cin_ok || !cout_ok || a.out_map != FD_OUTMAP_IDENTITY) return false;
+  const bool cout_ok = cout == 16 || cout == 32 || cout == 64 || (cout >= 128 && cout % 128 == 0);
+  if (!cin_ok || !cout_ok || (a.out_map != FD_OUTMAP_IDENTITY && a.out_map != OUTMAP_UPSAMPLE)) return false;
   wos::Plan p{};
   p.opg = cin >= 128 ? 1 : 128 / cin;
   p.ci_tiles = cin >= 128 ? cin / 128 : 1;
   p.n_groups = cin >= 128 ? a.K * p.ci_tiles : ceil_div(a.K, p.opg);
-  p.NT = cout;
+  p.NT = cout < 128 ? cout : 128;
+  p.co_tiles = cout < 128 ? 1 : cout / 128;
   const int max_gpp = 512 / p.NT;
   p.passes = ceil_div(p.n_groups, max_gpp);
   p.gpp = ceil_div(p.n_groups, p.passes);
@@ -719,15 +729,12 @@ static bool wos_plan(const ConvArgs& a, wos::Plan* out) {
   int cols = 32;
   while (cols < p.gpp * p.NT) cols <<= 1;
   p.tmem_cols = cols;
-  int chunks = kNumSMs / p.passes;
+  int chunks = kNumSMs / (p.passes * p.co_tiles);
   const int max_chunks = ceil_div(a.n_cap, 4 * wos::KP);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   p.chunks = chunks;
-  // rulebook layers: a gather warp may run SA <= 5 items ahead of another; the two index-slice buffers stay consistent
-  // as long as that is less than two stages
-  if (a.mode == FD_GATHER_TABLE && p.n_groups - (p.passes - 1) * p.gpp < 3) return false;
-  p.b_bytes = 2 * ((cout + 63) / 64) * wos::BLOCK_BYTES;
+  p.b_bytes = 2 * ((p.NT + 63) / 64) * wos::BLOCK_BYTES;
   static const int dbg = getenv("FD_WG_DBG") ? atoi(getenv("FD_WG_DBG")) : 0;
   p.dbg = dbg;
   *out = p;
@@ -747,8 +754,11 @@ int conv_wgrad_os_chunks(const ConvArgs& a) {
 }
 static size_t wos_align(size_t x) { return (x + 255) & ~(size_t)255; }
 // bytes of the split copies of x and dy that follow the partial slots in the workspace
+static size_t wos_dy_rows(const ConvArgs& a) {      // rows of dL/dy: a ConvTranspose2d phase reads every s-th pixel of the full map
+  return a.out_map == OUTMAP_UPSAMPLE ? (size_t)a.n_cap * a.up_s * a.up_s : (size_t)a.n_cap;
+}
 size_t conv_wgrad_os_extra_bytes(const ConvArgs& a) {
-  return wos_align((size_t)a.n_in_cap * a.cin * 4) + wos_align((size_t)a.n_cap * a.cout * 4) + 512;
+  return wos_align((size_t)a.n_in_cap * a.cin * 4) + wos_align(wos_dy_rows(a) * a.cout * 4) + 512;
 }
 // `partial`: chunks x [K, Cin, Cout] slots (ordered reduce by the caller); `extra`: conv_wgrad_os_extra_bytes(a) bytes
 int conv_wgrad_os(const ConvArgs& a, float* partial, void* extra, cudaStream_t stream) {
@@ -774,14 +784,15 @@ int conv_wgrad_os(const ConvArgs& a, float* partial, void* extra, cudaStream_t s
   if (a.out_split) {
     ys = (unsigned short*)a.out_split;
   } else {
-    split_rows_kernel<<<persistent_grid(ceil_div((int64_t)a.n_cap * (a.cout / 8), 256), 8), 256, 0, stream>>>(
-        a.out, a.out_stride, a.cout, a.d_n, a.n_cap, ys);
+    const int64_t dy_rows = (int64_t)wos_dy_rows(a);
+    split_rows_kernel<<<persistent_grid(ceil_div(dy_rows * (a.cout / 8), 256), 8), 256, 0, stream>>>(
+        a.out, a.out_stride, a.cout, a.out_map == FD_OUTMAP_IDENTITY ? a.d_n : nullptr, dy_rows, ys);
     FD_LAUNCHED();
   }
   ConvArgs s = a;
   s.in = reinterpret_cast<const float*>(xs); s.in_stride = a.cin; s.in_ctot = a.cin; s.in_fmt = FD_FMT_SPLIT_BF16;
   s.out = reinterpret_cast<float*>(ys); s.out_stride = a.cout; s.out_ctot = a.cout; s.out_fmt = FD_FMT_SPLIT_BF16;
-  const dim3 grid(p.chunks, p.passes);
+  const dim3 grid(p.chunks, p.passes, p.co_tiles);
   if (p.b_bytes <= 16384) conv_wgrad_os_kernel<5><<<grid, wos::THREADS, wos::smem_bytes(5, p.b_bytes), stream>>>(s, nullptr, partial, p);
   else conv_wgrad_os_kernel<4><<<grid, wos::THREADS, wos::smem_bytes(4, p.b_bytes), stream>>>(s, nullptr, partial, p);
   FD_LAUNCHED();

@@ -139,8 +139,7 @@ def conv2d_wgrad(x, dy, dw, ksize, stride, padding, transposed=False, precision=
     d.out_map = L.OUTMAP_IDENTITY
     d.n_out_cap = B * H * W if transposed else B * Ho * Wo
     d.precision = L.PRECISIONS[precision]
-    if not transposed:
-        d.d_in_split = _split_ptr(x_split, x); d.d_out_split = _split_ptr(dy_split, dy)
+    d.d_in_split = _split_ptr(x_split, x); d.d_out_split = _split_ptr(dy_split, dy)
     _run_wgrad(lib, d, dw, "fd_conv_wgrad(conv2d)")
     return dw
 
