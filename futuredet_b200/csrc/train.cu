@@ -374,6 +374,80 @@ red_partial_kernel(const RedArgs a) {
   }
 }
 
+// 4 channels per thread (128-bit loads): the scalar kernel above moved ~3 TB/s on the large levels.  Same partial layout,
+// same fixed summation order within a block (row lanes added in ascending order), so results are deterministic.
+__global__ void __launch_bounds__(RED_THREADS)
+red_partial_vec4_kernel(const RedArgs a) {
+  __shared__ double sh[8][RED_THREADS];
+  const long long n = a.d_n ? min((long long)*a.d_n, a.n_cap) : a.n_cap;
+  const int tid = threadIdx.x;
+  const int cq = a.cp >> 2;                          // thread columns (4 channels each), power of two <= 64
+  const int chq = tid & (cq - 1), rl = tid / cq, RL = RED_THREADS / cq;
+  const long long chunk = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * chunk;
+  const long long r1 = min(n, r0 + chunk);
+  for (int c0 = 0; c0 < a.C; c0 += a.cp) {
+    const int c = c0 + 4 * chq;
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+    if (c < a.C) {
+      float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu;
+      if (a.mode == RED_BN_BWD) { mu = *reinterpret_cast<const float4*>(a.mean + c); is = *reinterpret_cast<const float4*>(a.invstd + c); }
+      const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, i4[4] = {is.x, is.y, is.z, is.w};
+      for (long long r = r0 + rl; r < r1; r += RL) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)r * a.x_stride + c));
+        const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (a.mode == RED_STATS) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { s1[j] += (double)x4[j]; s2[j] += (double)x4[j] * (double)x4[j]; }
+        } else if (a.mode == RED_BN_BWD) {
+          const float4 dv = __ldg(reinterpret_cast<const float4*>(a.dy + (size_t)r * a.dy_stride + c));
+          float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+          if (a.relu) {
+            const float4 yv = __ldg(reinterpret_cast<const float4*>(a.y + (size_t)r * a.y_stride + c));
+            const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (!(y4[j] > 0.f)) d4[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xh = (x4[j] - m4[j]) * i4[j];
+            s1[j] += (double)d4[j];
+            s2[j] += (double)d4[j] * (double)xh;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s1[j] += (double)x4[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sh[j][tid] = s1[j]; sh[4 + j][tid] = s2[j]; }
+    __syncthreads();
+    if (rl == 0 && c < a.C) {
+      for (int q = 1; q < RL; ++q) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s1[j] += sh[j][q * cq + chq]; s2[j] += sh[4 + j][q * cq + chq]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a.partial[((size_t)blockIdx.x * 2 + 0) * a.C + c + j] = s1[j];
+        a.partial[((size_t)blockIdx.x * 2 + 1) * a.C + c + j] = s2[j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static bool red_vec4_ok(const RedArgs& a) {
+  auto al = [](const void* p, int stride) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && stride % 4 == 0); };
+  return a.C % 4 == 0 && a.cp >= 4 && al(a.x, a.x_stride) && al(a.dy, a.dy_stride) && (!a.relu || al(a.y, a.y_stride)) &&
+         al(a.mean, 4) && al(a.invstd, 4);
+}
+static void launch_red_partial(const RedArgs& r, int G, cudaStream_t stream) {
+  if (red_vec4_ok(r)) red_partial_vec4_kernel<<<G, RED_THREADS, 0, stream>>>(r);
+  else red_partial_kernel<<<G, RED_THREADS, 0, stream>>>(r);
+}
+
 struct FinArgs {
   int mode; int C; int G;
   const double* partial;
@@ -503,6 +577,86 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int dys, const float* __restri
     if (dres) dres[(size_t)r * drs + c] = dz;
   }
 }
+
+// ---- 4 channels per thread (128-bit loads / stores) for 16-byte aligned rows with C % 4 == 0
+__device__ __forceinline__ void split4_store(unsigned short* o, int ctot, const float v[4]) {
+  unsigned short hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = bf16_bits_rn(v[j]);
+    lo[j] = bf16_bits_rn(v[j] - __uint_as_float((unsigned)hi[j] << 16));
+  }
+  *reinterpret_cast<uint2*>(o) = make_uint2((unsigned)hi[0] | ((unsigned)hi[1] << 16), (unsigned)hi[2] | ((unsigned)hi[3] << 16));
+  *reinterpret_cast<uint2*>(o + ctot) = make_uint2((unsigned)lo[0] | ((unsigned)lo[1] << 16), (unsigned)lo[2] | ((unsigned)lo[3] << 16));
+}
+
+__global__ void __launch_bounds__(256)
+affine_act_vec4_kernel(const float* __restrict__ x, int xs, int C, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ res, int rs, int relu,
+                       float* __restrict__ y, int ys, unsigned short* __restrict__ ysplit, int split_ctot,
+                       const int32_t* __restrict__ d_n, long long n_cap) {
+  const long long n = d_n ? min((long long)*d_n, n_cap) : n_cap;
+  const int cq = C >> 2;
+  const long long total = n * cq;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / cq;
+    const int c = (int)(e - r * cq) * 4;
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * xs + c));
+    const float4 sc = scale ? __ldg(reinterpret_cast<const float4*>(scale + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 sh = shift ? __ldg(reinterpret_cast<const float4*>(shift + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float v[4] = {fmaf(xv.x, sc.x, sh.x), fmaf(xv.y, sc.y, sh.y), fmaf(xv.z, sc.z, sh.z), fmaf(xv.w, sc.w, sh.w)};
+    if (res) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(res + (size_t)r * rs + c));
+      v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    *reinterpret_cast<float4*>(y + (size_t)r * ys + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (ysplit) split4_store(ysplit + (size_t)r * 2 * split_ctot + c, split_ctot, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec4_kernel(const float* __restrict__ dy, int dys, const float* __restrict__ y, int ys, int relu,
+                         const float* __restrict__ x, int xs, int C, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ c1,
+                         const float* __restrict__ c2, float* __restrict__ dx, int dxs, float* __restrict__ dres, int drs,
+                         unsigned short* __restrict__ dxsplit, const int32_t* __restrict__ d_n, long long n_cap) {
+  const long long n = d_n ? min((long long)*d_n, n_cap) : n_cap;
+  const int cq = C >> 2;
+  const long long total = n * cq;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / cq;
+    const int c = (int)(e - r * cq) * 4;
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(dy + (size_t)r * dys + c));
+    float dz[4] = {dv.x, dv.y, dv.z, dv.w};
+    if (relu) {
+      const float4 yv = __ldg(reinterpret_cast<const float4*>(y + (size_t)r * ys + c));
+      const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (!(y4[j] > 0.f)) dz[j] = 0.f;
+    }
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * xs + c));
+    const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+    float d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float is = invstd[c + j];
+      const float xh = (x4[j] - mean[c + j]) * is;
+      const float g = gamma ? gamma[c + j] : 1.f;
+      d[j] = g * is * (dz[j] - c1[c + j] - xh * c2[c + j]);
+    }
+    *reinterpret_cast<float4*>(dx + (size_t)r * dxs + c) = make_float4(d[0], d[1], d[2], d[3]);
+    if (dxsplit) split4_store(dxsplit + (size_t)r * 2 * C + c, C, d);
+    if (dres) *reinterpret_cast<float4*>(dres + (size_t)r * drs + c) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+  }
+}
+
+static bool rows_vec4(const void* p, int stride) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && stride % 4 == 0); }
 
 __global__ void __launch_bounds__(256)
 add_rows_kernel(float* __restrict__ dst, int ds, const float* __restrict__ src, int ss, int C,
@@ -734,7 +888,7 @@ int fd_bn_train_stats(const float* d_x, int x_stride, int C, const int32_t* d_n,
   r.mode = RED_STATS; r.x = d_x; r.x_stride = x_stride; r.C = C; r.cp = red_cp(C);
   r.d_n = d_n; r.n_cap = n_cap; r.partial = (double*)d_workspace;
   const int G = red_blocks(n_cap, C);
-  red_partial_kernel<<<G, RED_THREADS, 0, stream>>>(r);
+  launch_red_partial(r, G, stream);
   FD_LAUNCHED();
   FinArgs f{};
   f.mode = RED_STATS; f.C = C; f.G = G; f.partial = r.partial; f.d_n = d_n; f.n_cap = n_cap;
@@ -754,9 +908,15 @@ int fd_affine_act(const float* d_x, int x_stride, int C, const float* d_scale, c
   FD_REQUIRE(d_x && d_y && C >= 1 && x_stride >= C && y_stride >= C && (!d_res || res_stride >= C) && n_cap >= 0,
              "fd_affine_act: bad argument");
   if (n_cap == 0) return 0;
-  affine_act_kernel<<<persistent_grid(ceil_div(n_cap * C, 256), 8), 256, 0, (cudaStream_t)stream>>>(
-      d_x, x_stride, C, d_scale, d_shift, d_res, res_stride, relu, d_y, y_stride, (unsigned short*)d_y_split, split_ctot, d_n,
-      n_cap);
+  if (C % 4 == 0 && rows_vec4(d_x, x_stride) && rows_vec4(d_y, y_stride) && rows_vec4(d_res, res_stride) &&
+      rows_vec4(d_scale, 4) && rows_vec4(d_shift, 4) && (!d_y_split || ((((uintptr_t)d_y_split) & 7) == 0 && split_ctot % 4 == 0)))
+    affine_act_vec4_kernel<<<persistent_grid(ceil_div(n_cap * (C / 4), 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        d_x, x_stride, C, d_scale, d_shift, d_res, res_stride, relu, d_y, y_stride, (unsigned short*)d_y_split, split_ctot,
+        d_n, n_cap);
+  else
+    affine_act_kernel<<<persistent_grid(ceil_div(n_cap * C, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        d_x, x_stride, C, d_scale, d_shift, d_res, res_stride, relu, d_y, y_stride, (unsigned short*)d_y_split, split_ctot,
+        d_n, n_cap);
   FD_LAUNCHED();
   return 0;
 }
@@ -777,7 +937,7 @@ int fd_bn_backward(const float* d_dy, int dy_stride, const float* d_y, int y_str
   r.y = d_y; r.y_stride = y_stride; r.relu = relu; r.mean = d_mean; r.invstd = d_invstd;
   r.C = C; r.cp = red_cp(C); r.d_n = d_n; r.n_cap = n_cap; r.partial = (double*)d_workspace;
   const int G = red_blocks(n_cap, C);
-  red_partial_kernel<<<G, RED_THREADS, 0, stream>>>(r);
+  launch_red_partial(r, G, stream);
   FD_LAUNCHED();
   float* c1 = (float*)((char*)d_workspace + red_partial_bytes(C));
   float* c2 = c1 + C;
@@ -786,9 +946,15 @@ int fd_bn_backward(const float* d_dy, int dy_stride, const float* d_y, int y_str
   f.dgamma = d_dgamma; f.dbeta = d_dbeta; f.c1 = c1; f.c2 = c2;
   red_finalize_kernel<<<ceil_div((int64_t)C * 32, RED_THREADS), RED_THREADS, 0, stream>>>(f);
   FD_LAUNCHED();
-  bn_bwd_apply_kernel<<<persistent_grid(ceil_div(n_cap * C, 256), 8), 256, 0, stream>>>(
-      d_dy, dy_stride, d_y, y_stride, relu, d_x, x_stride, C, d_mean, d_invstd, d_gamma, c1, c2, d_dx, dx_stride,
-      d_dres, dres_stride, (unsigned short*)d_dx_split, d_n, n_cap);
+  if (C % 4 == 0 && rows_vec4(d_dy, dy_stride) && (!relu || rows_vec4(d_y, y_stride)) && rows_vec4(d_x, x_stride) &&
+      rows_vec4(d_dx, dx_stride) && rows_vec4(d_dres, dres_stride) && (((uintptr_t)d_dx_split) & 7) == 0)
+    bn_bwd_apply_vec4_kernel<<<persistent_grid(ceil_div(n_cap * (C / 4), 256), 8), 256, 0, stream>>>(
+        d_dy, dy_stride, d_y, y_stride, relu, d_x, x_stride, C, d_mean, d_invstd, d_gamma, c1, c2, d_dx, dx_stride,
+        d_dres, dres_stride, (unsigned short*)d_dx_split, d_n, n_cap);
+  else
+    bn_bwd_apply_kernel<<<persistent_grid(ceil_div(n_cap * C, 256), 8), 256, 0, stream>>>(
+        d_dy, dy_stride, d_y, y_stride, relu, d_x, x_stride, C, d_mean, d_invstd, d_gamma, c1, c2, d_dx, dx_stride,
+        d_dres, dres_stride, (unsigned short*)d_dx_split, d_n, n_cap);
   FD_LAUNCHED();
   return 0;
 }
@@ -802,7 +968,7 @@ int fd_col_sum(const float* d_x, int x_stride, int C, const int32_t* d_n, int64_
   r.mode = RED_COLSUM; r.x = d_x; r.x_stride = x_stride; r.C = C; r.cp = red_cp(C);
   r.d_n = d_n; r.n_cap = n_cap; r.partial = (double*)d_workspace;
   const int G = red_blocks(n_cap, C);
-  red_partial_kernel<<<G, RED_THREADS, 0, stream>>>(r);
+  launch_red_partial(r, G, stream);
   FD_LAUNCHED();
   FinArgs f{};
   f.mode = RED_COLSUM; f.C = C; f.G = G; f.partial = r.partial; f.d_n = d_n; f.n_cap = n_cap; f.out = d_out;
