@@ -227,6 +227,73 @@ def test_conv2d_wgrad_tensor_core_wide(cuda, cin, cout):
     close(dw3, dw32, 2e-4, "wide wgrad")
 
 
+@pytest.mark.parametrize("cin,cout", [(128, 128), (256, 256)])
+def test_conv_transpose_wgrad_tensor_core(cuda, cin, cout):
+    """ConvTranspose2d(k == s == 2) weight gradient (the RPN deblocks): every phase runs the output-stationary tcgen05
+    kernel over the phase's pixels of dL/dy; against the exact CUDA-core arm."""
+    rng = np.random.default_rng(cin)
+    B, H, W = 2, 11, 9
+    x = torch.from_numpy(rng.standard_normal((B, H, W, cin)).astype(np.float32)).to(cuda)
+    gy = torch.from_numpy(rng.standard_normal((B, 2 * H, 2 * W, cout)).astype(np.float32)).to(cuda)
+    dw32 = torch.zeros((4, cin, cout), device=cuda)
+    dw3 = torch.zeros((4, cin, cout), device=cuda)
+    T.conv2d_wgrad(x, gy, dw32, (2, 2), (2, 2), (0, 0), transposed=True)
+    T.conv2d_wgrad(x, gy, dw3, (2, 2), (2, 2), (0, 0), transposed=True, precision="bf16x3")
+    close(dw3, dw32, 2e-4, "convT wgrad")
+    again = torch.zeros((4, cin, cout), device=cuda)
+    T.conv2d_wgrad(x, gy, again, (2, 2), (2, 2), (0, 0), transposed=True, precision="bf16x3")
+    assert torch.equal(again, dw3)
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (64, 128), (128, 64), (16, 16)])
+def test_sparse_wgrad_output_stationary_shapes(cuda, cin, cout):
+    """The output-stationary tcgen05 weight gradient (2 / 4 / 8 kernel offsets stacked in the accumulator lanes, several
+    passes, a chunk tail that is not a multiple of 64 rows) against the exact CUDA-core arm; the caller-provided split
+    copies (fd_affine_act / fd_bn_backward outputs in training) must give the same bits as the internal pre-pass."""
+    from futuredet_b200 import lib as L
+    rng = np.random.default_rng(cin * 3 + cout)
+    shape, B = [9, 24, 24], 2
+    c = random_sites(rng, B, shape, 3300)
+    n = len(c)
+    cap = n + 41
+    ct = torch.zeros((cap, 4), dtype=torch.int32, device=cuda); ct[:n] = torch.from_numpy(c).to(cuda)
+    nd = torch.tensor([n], dtype=torch.int32, device=cuda)
+    rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3], batch_size=B)
+    x = torch.zeros((cap, cin), device=cuda); x[:n] = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32)).to(cuda)
+    gy = torch.zeros((cap, cout), device=cuda); gy[:n] = torch.from_numpy(rng.standard_normal((n, cout)).astype(np.float32)).to(cuda)
+    dw32 = torch.zeros((27, cin, cout), device=cuda)
+    dw3 = torch.zeros((27, cin, cout), device=cuda)
+    T.sparse_conv_wgrad(x, gy, rb, dw32)
+    T.sparse_conv_wgrad(x, gy, rb, dw3, precision="bf16x3")
+    close(dw3, dw32, 3e-4, "output-stationary wgrad")
+    # split copies made by the conversion entry point == what the kernel's own pre-pass makes
+    lib = L.load()
+    xs, gs = torch.empty_like(x), torch.empty_like(gy)
+    for src, dst, C_ in ((x, xs, cin), (gy, gs, cout)):
+        rc = lib.fd_convert_rows(ops._ptr(src), 0, C_, C_, ops._ptr(dst), 1, C_, C_, C_, None, cap, ops._stream())
+        L.check(rc, "fd_convert_rows")
+    dws = torch.zeros((27, cin, cout), device=cuda)
+    T.sparse_conv_wgrad(x, gy, rb, dws, precision="bf16x3", x_split=xs, dy_split=gs)
+    assert torch.equal(dws, dw3), "caller-provided split copies change the weight gradient"
+
+
+def test_split_copies_leave_training_bit_identical(cuda, golden_dir):
+    """train.SPLIT_COPIES (activations / conv-output gradients also written as split-bf16 rows by their producers and
+    gathered by the tensor-core convolutions) is a data-movement change only: same losses, same gradients, bit for bit."""
+    g = torch.load(os.path.join(golden_dir, "neck_head_train.pt"), weights_only=False)
+    assert train.SPLIT_COPIES
+    m_on, x_on, l_on = _neck_head_step(g, cuda, "bf16x3", smooth=True)
+    train.SPLIT_COPIES = False
+    try:
+        m_off, x_off, l_off = _neck_head_step(g, cuda, "bf16x3", smooth=True)
+    finally:
+        train.SPLIT_COPIES = True
+    assert torch.equal(sum(l_on["loss"]), sum(l_off["loss"]))
+    assert torch.equal(x_on.grad, x_off.grad)
+    for (k, p_on), (_, p_off) in zip(m_on.named_parameters(), m_off.named_parameters()):
+        assert torch.equal(p_on.grad, p_off.grad), k
+
+
 def test_bev_scatter_gather(cuda):
     rng = np.random.default_rng(3)
     B, D, H, W, Cc = 2, 2, 7, 9, 12
