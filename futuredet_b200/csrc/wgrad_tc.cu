@@ -389,11 +389,18 @@ __device__ __forceinline__ void wg_mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-// one lane polls, the warp parks at __syncwarp
-__device__ __forceinline__ bool wait_warp(uint32_t bar, uint32_t parity, bool spin = false) {
+// Warp-level wait.  Default: every lane waits on the barrier itself (try_wait parks the lanes; this is also the form
+// compute-sanitizer's racecheck can follow -- with one polling lane + a shuffle the other lanes never touch the
+// barrier and the tool reports the ring hand-over as hazards).  `one_lane`: lane 0 polls with test_wait, the warp parks
+// at the shuffle (triage knob FD_WG_DBG & 8).
+__device__ __forceinline__ bool wait_warp(uint32_t bar, uint32_t parity, bool one_lane = false) {
   bool ok = true;
-  if ((threadIdx.x & 31) == 0) ok = spin ? wg::mbar_spin(bar, parity) : wg::mbar_wait(bar, parity);   // spin: test_wait polling
-  return __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+  if (one_lane) {
+    if ((threadIdx.x & 31) == 0) ok = wg::mbar_spin(bar, parity);
+    return __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+  }
+  ok = wg::mbar_wait(bar, parity);
+  return __all_sync(0xffffffffu, ok) != 0;
 }
 
 struct Plan {
@@ -543,7 +550,7 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
           cur_st = st;
           have_idx = false;
         }
-        if (!have_idx) { ok = wait_warp(wg::smem_u32(&i_full[st % IDX_SLOTS]), (uint32_t)((st / IDX_SLOTS) & 1), true) && ok; have_idx = true; }
+        if (!have_idx) { ok = wait_warp(wg::smem_u32(&i_full[st % IDX_SLOTS]), (uint32_t)((st / IDX_SLOTS) & 1), pl.dbg & 8) && ok; have_idx = true; }
       }
       const int o0 = row_begin + st * KP + r0;
       const uint32_t ibase = idx_ring + (uint32_t)(st % IDX_SLOTS) * (IDX_K * KP * 4) + (uint32_t)(k * KP + r0) * 4;
@@ -556,7 +563,7 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
         else src[q] = gather_row(a, o, k);
       }
       if (t64 == 0) WOS_TRACE(0, item, clock64());
-      ok = wait_warp(wg::smem_u32(&a_empty[as]), aph ^ 1, true) && ok;
+      ok = wait_warp(wg::smem_u32(&a_empty[as]), aph ^ 1, pl.dbg & 8) && ok;
       if (t64 == 0) WOS_TRACE(1, item, clock64());
       const uint32_t adst = a_ring + as * A_BYTES;
       const char* xh = xs + ch * 2;

@@ -21,7 +21,7 @@ if os.environ.get("FD_NO_WATCHDOG"):          # the sanitizers slow kernels down
     _L.fd_debug_set_tc.argtypes = [C.c_int, C.c_int]
     torch.zeros(1, device=dev)
     assert _L.fd_debug_set_tc(7, 0) == 0
-which = sys.argv[1:] or ["voxelize", "conv", "dense", "wgrad", "predict", "model"]
+which = sys.argv[1:] or ["voxelize", "conv", "dense", "wgrad", "bn", "predict", "model"]
 
 
 def sites(B, shape, n):
@@ -70,13 +70,38 @@ if "dense" in which:
         print("dense conv %d->%d k%d s%d: max |tc - fp32| %.2e" % (cin, cout, k, s, float((y - ref).abs().max())))
 
 if "wgrad" in which:
-    for cin, cout in ((64, 64), (16, 32)):
+    # bf16x3 = the output-stationary tcgen05 kernel (2 / 4 / 8 offsets per accumulator group, several passes, Cout tiles)
+    for cin, cout in ((64, 64), (16, 32), (32, 32), (128, 128)):
         x = torch.randn((n, cin), device=dev)
         gy = torch.randn((n, cout), device=dev)
+        dws = {}
         for prec in ("fp32", "bf16x3"):
-            dw = torch.zeros((27, cin, cout), device=dev)
-            T.sparse_conv_wgrad(x, gy, rb, dw, precision=prec)
-        print("wgrad %d->%d ok" % (cin, cout))
+            dws[prec] = torch.zeros((27, cin, cout), device=dev)
+            T.sparse_conv_wgrad(x, gy, rb, dws[prec], precision=prec)
+        print("wgrad %d->%d: max |tc - fp32| %.2e" % (cin, cout, float((dws["bf16x3"] - dws["fp32"]).abs().max())))
+    for cin, cout, tr in ((128, 256, False), (256, 128, True)):       # dense 3x3 with two Cout tiles, ConvTranspose2d phases
+        x = torch.randn((2, 10, 12, cin), device=dev)
+        k = 2 if tr else 3
+        gy = torch.randn((2, 20, 24, cout) if tr else (2, 10, 12, cout), device=dev)
+        dws = {}
+        for prec in ("fp32", "bf16x3"):
+            dws[prec] = torch.zeros((k * k, cin, cout), device=dev)
+            T.conv2d_wgrad(x, gy, dws[prec], (k, k), (2, 2) if tr else (1, 1), (0, 0) if tr else (1, 1), transposed=tr, precision=prec)
+        print("dense wgrad %d->%d%s: max |tc - fp32| %.2e" % (cin, cout, " (convT)" if tr else "", float((dws["bf16x3"] - dws["fp32"]).abs().max())))
+
+if "bn" in which:
+    # train-mode BatchNorm kernels (128-bit paths) with the split-bf16 copies of the training step
+    from torch import nn
+    for Cc in (16, 128):
+        bn = nn.BatchNorm1d(Cc).to(dev).train()
+        x = torch.randn((5000, Cc), device=dev)
+        saved = T.bn_train_stats(x, bn)
+        ys = torch.empty_like(x)
+        y = T.affine_act(x, saved.scale, saved.shift, x, True, split=(ys, 0))
+        dg, db = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev)
+        dx, dres, dxs = T.bn_backward(torch.randn_like(x), y, True, x, saved, bn.weight.detach(), dg, db, True, want_split=True)
+        back = ops.Feat(ys, "split").to_fp32()
+        print("bn C=%d: split copy max err %.2e" % (Cc, float((back - y).abs().max())))
 
 if "predict" in which:
     from oracle import predict_ref as PR
