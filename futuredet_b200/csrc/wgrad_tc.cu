@@ -411,6 +411,9 @@ struct Plan {
   int passes;
   int NT;           // accumulator columns per group
   int tmem_cols;
+  int fuse;         // Cout <= 64: A_hi * [B_hi | B_lo] as ONE MMA of width 2 NT (each MMA re-reads its whole 4 KB A slice from
+                    // shared memory -- the port is what bounds an item), two accumulator column blocks per group
+  int gcols;        // accumulator columns per group (NT or 2 NT)
   int chunks;
   int co_tiles;     // 128-column slices of Cout (grid.z)
   int b_bytes;      // bytes of one dY ring slot
@@ -632,7 +635,9 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
         const char* src = ys + dy_row(min(o0 + r, row_end - 1)) * y_row + co0 * 2 + cc * 16;
         const uint32_t d = bdst + (uint32_t)(cc >> 3) * BLOCK_BYTES + (uint32_t)r * ROWB + (uint32_t)(((cc & 7) ^ (r & 7)) << 4);
         cp_async16_sz(d, src, sz);
-        cp_async16_sz(d + b_plane, src + cout * 2, sz);
+        // lo plane: the next 64-channel block, or (fused narrow tiles) the channels right after the hi ones in the same rows
+        const uint32_t dlo = (pl.fuse && NT < 64) ? bdst + (uint32_t)r * ROWB + (uint32_t)((((cc + bchunks) & 7) ^ (r & 7)) << 4) : d + b_plane;
+        cp_async16_sz(dlo, src + cout * 2, sz);
       }
       cp_async_arrive_noinc(wg::smem_u32(&b_full[bs]));
       if (++bs == SB) { bs = 0; bph ^= 1; }
@@ -640,7 +645,7 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (lane == 0) {
     // ===================================== MMA ISSUER =====================================
-    const uint32_t idesc = wg::idesc_mn(128, NT);
+    const uint32_t idesc = wg::idesc_mn(128, NT), idesc2 = wg::idesc_mn(128, 2 * NT);
     const uint32_t b_plane = (uint32_t)((NT + 63) >> 6) * BLOCK_BYTES;
     // The barrier of the NEXT item (and, at a stage's last group, of the next dY stage) is probed with a non-blocking
     // test_wait issued BEFORE the current item's MMAs, so that its latency overlaps their issue (which blocks on
@@ -662,14 +667,20 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
         if (g == G - 1) b_ready = wg::mbar_test(wg::smem_u32(&b_full[nbs]), nbph);
         const uint32_t sA = a_ring + as * A_BYTES;
         const uint64_t dAh = wg::desc_mn_sw128(sA), dAl = wg::desc_mn_sw128(sA + A_PLANE);
-        const uint32_t td = tmem_base + (uint32_t)(g * NT);
+        const uint32_t td = tmem_base + (uint32_t)(g * pl.gcols);
         if (!(pl.dbg & 2)) {
 #pragma unroll
           for (int ks = 0; ks < KP / 16; ++ks) {
             const uint64_t adv = (uint64_t)((ks * 16 * ROWB) >> 4);
-            wg::umma(td, dAh + adv, dBh + adv, idesc, (st > 0 || ks > 0) ? 1u : 0u);
-            wg::umma(td, dAh + adv, dBl + adv, idesc, 1u);
-            wg::umma(td, dAl + adv, dBh + adv, idesc, 1u);
+            const uint32_t acc = (st > 0 || ks > 0) ? 1u : 0u;
+            if (pl.fuse) {                                   // columns [0, NT): A_hi B_hi + A_lo B_hi; [NT, 2 NT): A_hi B_lo
+              wg::umma(td, dAh + adv, dBh + adv, idesc2, acc);
+              wg::umma(td, dAl + adv, dBh + adv, idesc, 1u);
+            } else {
+              wg::umma(td, dAh + adv, dBh + adv, idesc, acc);
+              wg::umma(td, dAh + adv, dBl + adv, idesc, 1u);
+              wg::umma(td, dAl + adv, dBh + adv, idesc, 1u);
+            }
           }
         }
         wg::umma_commit(wg::smem_u32(&a_empty[as]));
@@ -694,7 +705,14 @@ conv_wgrad_os_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
         float* dst = (pslot ? pslot : dw) + ((size_t)k * cin + ch) * cout + co0;
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t v[16];
-          wg::tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(g * NT + c0), v);
+          wg::tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(g * pl.gcols + c0), v);
+          if (pl.fuse) {
+            uint32_t v2[16];
+            wg::tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(g * pl.gcols + NT + c0), v2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (k < a.K) {
             if (pslot) {
@@ -729,12 +747,15 @@ static bool wos_plan(const ConvArgs& a, wos::Plan* out) {
   p.n_groups = cin >= 128 ? a.K * p.ci_tiles : ceil_div(a.K, p.opg);
   p.NT = cout < 128 ? cout : 128;
   p.co_tiles = cout < 128 ? 1 : cout / 128;
-  const int max_gpp = 512 / p.NT;
+  static const int nofuse = getenv("FD_WG_NOFUSE") ? atoi(getenv("FD_WG_NOFUSE")) : 0;
+  p.fuse = (cout <= 64 && !nofuse) ? 1 : 0;
+  p.gcols = p.fuse ? 2 * p.NT : p.NT;
+  const int max_gpp = 512 / p.gcols;
   p.passes = ceil_div(p.n_groups, max_gpp);
   p.gpp = ceil_div(p.n_groups, p.passes);
   p.passes = ceil_div(p.n_groups, p.gpp);
   int cols = 32;
-  while (cols < p.gpp * p.NT) cols <<= 1;
+  while (cols < p.gpp * p.gcols) cols <<= 1;
   p.tmem_cols = cols;
   int chunks = kNumSMs / (p.passes * p.co_tiles);
   const int max_chunks = ceil_div(a.n_cap, 4 * wos::KP);
