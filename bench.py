@@ -562,6 +562,28 @@ def run_gpu(args, rank, world, local):
         tj = json.load(open(tpath))
         if tj.get("batch_per_gpu") == B and tj.get("precision") == args.precision:
             traffic = tj.get("conv_family_dram_bytes_per_step")
+    # L2 -> SM side of the same family: the gather roofline is measured live (a kernel that only issues the producers'
+    # access pattern, csrc/probe.cu); the family's bytes through L2 come from an ncu capture of THIS batch size
+    l2 = None
+    if rank == 0:
+        import ctypes as _C
+        from futuredet_b200 import lib as _lib
+        _L = _lib.load()
+        _L.fd_debug_l2_gather_probe.argtypes = [_C.c_int, _C.POINTER(_C.c_double), _C.c_void_p]
+        bps = _C.c_double(0.0)
+        if _L.fd_debug_l2_gather_probe(212740, _C.byref(bps), None) == 0:
+            l2_bytes = None
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                if tj.get("batch_per_gpu") == B and tj.get("precision") == args.precision:
+                    l2_bytes = tj.get("conv_family_l2_bytes_per_step")
+            l2 = dict(gather_peak_tbs=bps.value / 1e12,
+                      peak_what="measured in this run: 16-byte cp.async gathers of 2 x 128-byte row pieces at neighbour-like "
+                                "indices of a 54 MB buffer into a 4 x 32 KB shared-memory ring, nothing else running",
+                      bytes_per_step=l2_bytes,
+                      bytes_what="lts__t_bytes of the family per step, ncu capture of this batch size (null otherwise)",
+                      achieved_tbs=(l2_bytes / (prof["ms"] * 1e-3) / 1e12) if l2_bytes else None,
+                      frac=(l2_bytes / (prof["ms"] * 1e-3) / bps.value) if l2_bytes else None)
     roofline = dict(bound="tensor", kernel="gather->implicit-GEMM conv family (%s), %d launches/step" %
                     (args.precision, prof["launches"]), achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s",
                     frac=achieved / pk["tf_sustained"], traffic=traffic,
@@ -569,7 +591,8 @@ def run_gpu(args, rank, world, local):
                     mma_tflops=3.0 * achieved if args.precision == "bf16x3" else achieved,
                     note="bf16x3 executes 3 tensor-core MMAs per algorithmic product: frac <= 1/3 by construction",
                     peak_source=pk["src"] + " bf16 dense, sustained",
-                    algorithmic_gflop_per_step=prof["flop"] / 1e9, kernel_ms_per_step=prof["ms"], by_kind=prof["by_kind"])
+                    algorithmic_gflop_per_step=prof["flop"] / 1e9, kernel_ms_per_step=prof["ms"], by_kind=prof["by_kind"],
+                    l2=l2)
     cpu_baseline = None
     if world == 1:                                                       # reported at N = 1 only (the contract)
         cores = use_all_host_threads()
