@@ -29,6 +29,8 @@
 extern "C" {
 #endif
 
+/* 3: fd_conv_desc gained n_in_cap / d_in_split / d_out_split (weight gradient), fd_affine_act and fd_bn_backward gained
+ *    the optional split-bf16 copy outputs (round 2, training step).  2: first published layout.                    */
 #define FD_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------ */
