@@ -314,6 +314,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+
 // UMMA shared-memory descriptor, K-major, one swizzle atom per row (SWIZZLE_128B for 64-element stages, SWIZZLE_64B
 // for 32): 8-row groups 8*TC_ROWB bytes apart (SBO), version 1, layout type 2 (128B) / 4 (64B).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -735,7 +736,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
         const int ch = ch_n;
         if (p + G < n_emit) fetch(p + G);                  // prefetch the next owned stage's indices (in flight during the wait)
         if (tid == 0) TC_TRACE(1, 4 * ptrace_i, clock64());
-        if (t.dbg & 128) mbar_spin(smem_u32(&a_empty[slot]), phase ^ 1, 2); else mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1, 2);
+        // every producer thread parks in try_wait.  Measured alternatives, all slower: every thread polling test_wait, one
+        // polling lane per warp + __syncwarp (256 / 8 threads hammering the mbarrier words), and a manager warp that watches
+        // the barrier and releases the group through a named barrier (c64 3.6 vs 3.4 ms).  The group observes a flip
+        // ~1000 cycles late either way: its wait queues behind the 64 cp.async the warp has just issued (LSU, in order).
+        mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1, 2);
         if (tid == 0) { TC_TRACE(1, 4 * ptrace_i + 1, clock64()); TC_TRACE(1, 4 * ptrace_i + 3, (long long)(c_base + p)); }
         const uint32_t fbar = smem_u32(&a_full[slot]);
         const uint32_t dst0 = a_ring_u32 + slot * Cfg::A_BYTES + a_off0;
@@ -816,14 +821,16 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
       tc_fence_after();
       uint32_t accumulate = 0;
       for (int ia = 0; ia < n_act; ++ia) {
-        if (!b_ready) { if (t.dbg & 128) mbar_spin(smem_u32(&b_full[b_slot]), b_phase, 4); else mbar_wait(smem_u32(&b_full[b_slot]), b_phase, 4); }
+        // the single-thread roles (MMA issuer, weight loader) poll with the non-suspending test_wait: a parked try_wait wakes
+        // up ~1000 cycles after the flip, which lands on the critical path of every stage (FD_TC_DEBUG & 128: park instead)
+        if (!b_ready) { if (!(t.dbg & 128)) mbar_spin(smem_u32(&b_full[b_slot]), b_phase, 4); else mbar_wait(smem_u32(&b_full[b_slot]), b_phase, 4); }
         const uint32_t sB_hi = b_ring_u32 + b_slot * Cfg::B_BYTES, sB_lo = sB_hi + NT * TC_ROWB;
         const uint64_t dB_hi = umma_desc_sw128(sB_hi), dB_lo = umma_desc_sw128(sB_lo);
         const uint32_t nb_slot = b_slot + 1 == SB ? 0 : b_slot + 1, nb_phase = b_slot + 1 == SB ? b_phase ^ 1 : b_phase;
         b_ready = mbar_test(smem_u32(&b_full[nb_slot]), nb_phase);   // consumed at the next K stage
         for (int ti = 0; ti < live; ++ti) {
           if (lane == 0) TC_TRACE(3, 4 * trace_i + 2, clock64());
-          if (!a_ready) { if (t.dbg & 128) mbar_spin(smem_u32(&a_full[a_slot]), a_phase, 5); else mbar_wait(smem_u32(&a_full[a_slot]), a_phase, 5); }
+          if (!a_ready) { if (!(t.dbg & 128)) mbar_spin(smem_u32(&a_full[a_slot]), a_phase, 5); else mbar_wait(smem_u32(&a_full[a_slot]), a_phase, 5); }
           if (lane == 0) TC_TRACE(0, 2 * trace_i, clock64());
           tc_fence_after();
           if (lane == 0) TC_TRACE(3, 4 * trace_i + 3, clock64());
@@ -844,6 +851,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
             a_ready = umma_stage<2>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, na_phase, cbar);
           }
           if (lane == 0) TC_TRACE(0, 2 * trace_i + 1, clock64());
+          if (t.dbg & 512) {                                   // triage: how long after its issue does the commit arrive?
+            mbar_spin(cbar, a_phase, 9);
+            if (lane == 0) TC_TRACE(3, 4 * trace_i, clock64());
+          }
           ++trace_i;
           a_slot = na_slot; a_phase = na_phase;
         }
@@ -854,9 +865,20 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
       umma_commit_elect(smem_u32(&t_full[acc]));
     }
     __syncwarp();
+    if ((t.dbg & 1024) && lane == 0) *(volatile uint32_t*)s_tmem = 0xffffffffu;      // (tmem_base was read by everyone long ago)
   } else if (warp == TC_B_WARP) {
     // ===================================== WEIGHT LOADER =====================================
     // one lane: per (unit, active K stage) one TMA bulk copy of the pre-swizzled weight stage, shared by the T tiles
+    if (lane == 1 && (t.dbg & 1024) && blockIdx.x == 0) {
+      // triage monitor: when does the a_empty barrier of emitted stage g actually flip? (trace role 3, word 4 g + 1)
+      for (int g = 0; g < TC_TRACE_N / 4; ++g) {
+        bool stop = false;
+        while (!mbar_test(smem_u32(&a_empty[g % SA]), (uint32_t)((g / SA) & 1)))
+          if (*(volatile uint32_t*)s_tmem == 0xffffffffu) { stop = true; break; }      // the MMA warp is done
+        if (stop) break;
+        g_tc_trace[3][4 * g + 1] = clock64();
+      }
+    }
     if (lane == 0) {
       uint32_t b_slot = 0, b_phase = 0;
       const uint32_t b_ring_u32 = smem_u32(b_ring);
@@ -870,7 +892,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
           const int ks = (__ffs((int)rem) - 1) * spg + sub;
           if (++sub == spg) { sub = 0; rem &= rem - 1; }
           const uint32_t bbar = smem_u32(&b_full[b_slot]);
-          if (t.dbg & 128) mbar_spin(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1); else mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1);
+          if (!(t.dbg & 128)) mbar_spin(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1); else mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1);
           if (!(t.dbg & 4)) {
             mbar_expect_tx(bbar, Cfg::B_BYTES);
             bulk_g2s(b_ring_u32 + b_slot * Cfg::B_BYTES, wtile + (size_t)ks * Cfg::B_BYTES, Cfg::B_BYTES, bbar);
