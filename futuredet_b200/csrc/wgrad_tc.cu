@@ -357,11 +357,15 @@ conv_wgrad_tc_kernel(const ConvArgs a, float* __restrict__ dw, float* __restrict
 // group of the pass; a group's A operand is 128 accumulator lanes = 128 / Cin kernel offsets side by side (Cin < 128:
 // the gathered rows of 2 / 4 / 8 offsets share the 128-byte MN-major rows, so narrow layers fill the tensor core's M)
 // or one 128-channel slice of one offset; every group has its own NT-column accumulator in TMEM (<= 512 columns per
-// pass: 27 offsets of a 64 -> 64 layer are 2 passes of 7 groups, of a 32 -> 32 layer one pass).  Operands are
-// pre-split bf16 hi / lo rows (split_rows_kernel, one streaming pass over x and dy), so the 8 producer warps are pure
-// cp.async (missing neighbours zero-filled) into a 4-slot A ring / 2-slot dY ring, one thread issues the 12
-// tcgen05.mma of a (group, stage) and commits the slot back, and the accumulators are read once at the end of the
-// chunk (lane = (offset, ci), column = co) into the chunk's slot of the partial buffer (ordered reduce: bit-reproducible).
+// pass: 27 offsets of a 64 -> 64 layer are 4 passes of 3-4 groups with the fused split products below, of a 32 -> 32 layer
+// one pass).  Operands are split-bf16 hi / lo rows -- the copies the training step's fd_affine_act / fd_bn_backward
+// already wrote, else split_rows_kernel makes them (one streaming pass over x and dy) -- so the 8 gather warps (4 groups
+// filling 4 items concurrently) are pure cp.async (missing neighbours zero-filled) into a 4-5 slot A ring; a loader
+// warp owns the dY ring (2 slots) and a 4-deep ring of [K][64] rulebook slices; one thread issues the 8-12 tcgen05.mma
+// of a (group, stage) item, probing the next item's barrier first, and commits the slot back; the accumulators are
+// read once at the end of the chunk (lane = (offset, ci), column = co) into the chunk's slot of the partial buffer
+// (fixed-tree ordered reduce afterwards: bit-reproducible).  Cout > 128 runs as 128-column slices (grid.z); a
+// ConvTranspose2d(k == s) phase maps its output rows to the phase's pixels of dL/dy.
 namespace wos {
 
 constexpr int KP = 64, ROWB = 128, BLOCK_BYTES = KP * ROWB;        // one 64-channel column block of one plane: 8 KB
@@ -417,7 +421,8 @@ struct Plan {
   int chunks;
   int co_tiles;     // 128-column slices of Cout (grid.z)
   int b_bytes;      // bytes of one dY ring slot
-  int dbg;          // FD_WG_DBG triage bits: 1 no gathers, 2 no MMAs, 4 no proxy fence
+  int dbg;          // FD_WG_DBG triage bits: 1 no gathers, 2 no MMAs, 4 no proxy fence, 8 one polling lane per gather warp,
+                    // 32 clock64 timeline of block (0,0) (tools/wgrad_trace.py)
 };
 
 }  // namespace wos
