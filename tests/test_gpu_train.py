@@ -277,6 +277,43 @@ def test_sparse_wgrad_output_stationary_shapes(cuda, cin, cout):
     assert torch.equal(dws, dw3), "caller-provided split copies change the weight gradient"
 
 
+@pytest.mark.parametrize("case", ["empty", "tiny", "strided", "wide_cin", "k1"])
+def test_sparse_wgrad_output_stationary_edges(cuda, case):
+    """Edge cases of the output-stationary weight gradient: no active rows (device count 0 under a large capacity), fewer
+    rows than one 64-row stage, a strided rulebook (input and output row sets differ), Cin = 256 (two 128-channel slices
+    per offset) and a single kernel offset."""
+    rng = np.random.default_rng(len(case))
+    shape, B = [9, 24, 24], 2
+    n_sites = {"empty": 200, "tiny": 37}.get(case, 2100)
+    cin, cout = {"wide_cin": (256, 64), "k1": (64, 32)}.get(case, (64, 64))
+    c = random_sites(rng, B, shape, n_sites)
+    n = len(c)
+    cap = n + 300
+    ct = torch.zeros((cap, 4), dtype=torch.int32, device=cuda); ct[:n] = torch.from_numpy(c).to(cuda)
+    nd = torch.tensor([0 if case == "empty" else n], dtype=torch.int32, device=cuda)
+    if case == "strided":
+        rb, _ = ops.rulebook_conv(ct, nd, cap, B, shape, [3, 3, 3], [2, 2, 2], [1, 1, 1])
+    elif case == "k1":
+        rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [1, 1, 1], batch_size=B)
+    else:
+        rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3], batch_size=B)
+    K = rb.K
+    x = torch.from_numpy(rng.standard_normal((cap, cin)).astype(np.float32)).to(cuda)
+    gy = torch.from_numpy(rng.standard_normal((rb.n_out_cap, cout)).astype(np.float32)).to(cuda)
+    dw32 = torch.zeros((K, cin, cout), device=cuda)
+    dw3 = torch.zeros((K, cin, cout), device=cuda)
+    T.sparse_conv_wgrad(x, gy, rb, dw32)
+    T.sparse_conv_wgrad(x, gy, rb, dw3, precision="bf16x3")
+    if case == "empty":
+        assert float(dw3.abs().max()) == 0.0 and float(dw32.abs().max()) == 0.0
+    else:
+        assert float(dw32.abs().max()) > 0
+        close(dw3, dw32, 3e-4, "wgrad " + case)
+    again = torch.zeros((K, cin, cout), device=cuda)
+    T.sparse_conv_wgrad(x, gy, rb, again, precision="bf16x3")
+    assert torch.equal(again, dw3)
+
+
 def test_split_copies_leave_training_bit_identical(cuda, golden_dir):
     """train.SPLIT_COPIES (activations / conv-output gradients also written as split-bf16 rows by their producers and
     gathered by the tensor-core convolutions) is a data-movement change only: same losses, same gradients, bit for bit."""
