@@ -57,6 +57,8 @@ constexpr int TC_B_WARP = TC_PRODUCER_WARPS + 5;       // warp 13 (warps 9-12: e
 constexpr int TC_THREADS = TC_PRODUCERS + 32 + 128 + 32;
 constexpr int TC_SS_MAX = 512;                         // folded BN scale / shift cached in shared memory up to this Cout
 constexpr int TC_A_PLANE = TC_BM * TC_ROWB;   // bytes of one A plane (hi or lo) per stage
+constexpr int TC_EPI_WARP_BYTES = 2048;       // per epilogue warp: 32 rows x 64 bytes of staging for coalesced row I/O
+constexpr int TC_EPI_BYTES = 4 * TC_EPI_WARP_BYTES;
 
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -428,12 +430,12 @@ template <int NT> struct TcCfg {
   static constexpr int TMEM_COLS = 2 * TMAX * ACC_COLS < 32 ? 32 : 2 * TMAX * ACC_COLS;
   static constexpr int IDX_BYTES = TMAX * TC_DENSE_MAXK * TC_BM * 4;   // dense-mode row index cache
   // the A ring takes every byte that is left of the 227 KB a CTA may own
-  static constexpr int FIXED = 1024 + SB * B_BYTES + IDX_BYTES + 2 * TC_SS_MAX * 4 + (2 * 16 + 2 * SB + 4) * 8 + 64;
+  static constexpr int FIXED = 1024 + SB * B_BYTES + IDX_BYTES + 2 * TC_SS_MAX * 4 + TC_EPI_BYTES + (2 * 16 + 2 * SB + 4) * 8 + 64;
   static constexpr int SA_FIT = (232448 - FIXED) / A_BYTES;
   static constexpr int SA = SA_FIT > 12 ? 12 : SA_FIT;            // A ring slots
   static_assert(SA >= TC_GROUPS, "every producer group needs a slot of its own");
   static constexpr int NBAR = 2 * SA + 2 * SB + 4;
-  static constexpr size_t SMEM = 1024 + (size_t)SA * A_BYTES + (size_t)SB * B_BYTES + IDX_BYTES + 2 * TC_SS_MAX * 4 + NBAR * 8 + 64;
+  static constexpr size_t SMEM = 1024 + (size_t)SA * A_BYTES + (size_t)SB * B_BYTES + IDX_BYTES + 2 * TC_SS_MAX * 4 + TC_EPI_BYTES + NBAR * 8 + 64;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -469,7 +471,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
   int* s_idx = (int*)(b_ring + SB * Cfg::B_BYTES);                // [TMAX][TC_DENSE_MAXK][128] (dense mode)
   float* s_scale = (float*)((uint8_t*)s_idx + Cfg::IDX_BYTES);    // [TC_SS_MAX] folded BN scale, then shift
   float* s_shift = s_scale + TC_SS_MAX;
-  uint64_t* bars = (uint64_t*)(s_shift + TC_SS_MAX);
+  uint8_t* s_epi = (uint8_t*)(s_shift + TC_SS_MAX);               // [4 epilogue warps][TC_EPI_WARP_BYTES]
+  uint64_t* bars = (uint64_t*)(s_epi + TC_EPI_BYTES);
   uint64_t* a_full = bars;                  // [SA]
   uint64_t* a_empty = a_full + SA;          // [SA]
   uint64_t* b_full = a_empty + SA;          // [SB]
@@ -924,6 +927,15 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
         OutRow orow{nullptr, 0, 1};
         if (live_row) orow = map_out_row(a, o);
         const float* res = (a.residual && live_row) ? a.residual + (size_t)o * a.res_stride : nullptr;
+        // coalesced row I/O: output row this lane serves in store / load instruction k (rows k * RPI + lane / NCH of the warp)
+        constexpr int NCHq = CH / 8, RPIq = 32 / NCHq;
+        int orr_k[NCHq];
+#pragma unroll
+        for (int k = 0; k < NCHq; ++k) {
+          const int rr = k * RPIq + lane / NCHq;
+          const int v = tiled ? tile_row_to_o(st * T + ti, q * 32 + rr) : (st * T + ti) * TC_BM + q * 32 + rr;
+          orr_k[k] = (v >= 0 && v < n) ? v : -1;
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < NT; c0 += CH) {
           const int cbase = col0 + c0;
@@ -932,6 +944,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
           // identity (residual) values first: they do not depend on the accumulator, so their latency overlaps
           // the TMEM load
           float y[CH];
+          // (the residual rows are read one row per lane: a coalesced, shared-memory staged version of these loads measured
+          // slower -- 32 more registers in the hottest part of the epilogue)
           if (work && res) {
             if (a.res_fmt == FD_FMT_SPLIT_BF16 && fullc) {
               const uint4* rh = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(res) + cbase);
@@ -970,7 +984,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
             tc_fence_before();
             mbar_arrive(smem_u32(&t_empty[acc]));
           }
-          if (!work) continue;
+          // Coalesced row output (warp-uniform condition): identity rows in split-bf16 format.  With one row per lane a
+          // warp-level 16-byte store touches 32 different rows = 32 L2 requests; staged through 2 KB of shared memory per
+          // warp, 32 / NCH rows x NCH chunks go out per instruction (8 requests for a 32-column chunk) -- the epilogue's
+          // requests were ~a third of all LSU traffic of a tile and removing its stores gained 16 % (FD_TC_DEBUG & 8).
+          const bool co_out = !(t.dbg & (8 | 8192)) && cbase < a.cout && fullc && a.out_map == FD_OUTMAP_IDENTITY &&
+                              a.out_fmt == FD_FMT_SPLIT_BF16 && (a.out_ctot & 7) == 0 && (a.out_stride & 3) == 0 &&
+                              ((((uintptr_t)a.out) + 2 * (size_t)cbase) & 15) == 0;
+          if (!work && !co_out) continue;
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int c = cbase + i;
@@ -981,7 +1002,46 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
             if (a.relu) v = fmaxf(v, 0.f);
             y[i] = v;
           }
-          if (orow.cstride == 1 && fullc && a.out_fmt == FD_FMT_SPLIT_BF16 &&
+          if (co_out) {
+            constexpr int NCH = CH / 8;                        // 16-byte chunks of a row's CH bf16 columns (per plane)
+            constexpr int RPI = 32 / NCH;                      // rows per store instruction
+            const uint32_t sbuf = smem_u32(s_epi) + (uint32_t)q * TC_EPI_WARP_BYTES;
+#pragma unroll
+            for (int plane = 0; plane < 2; ++plane) {
+#pragma unroll
+              for (int g8 = 0; g8 < NCH; ++g8) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float f0 = y[g8 * 8 + 2 * i], f1 = y[g8 * 8 + 2 * i + 1];
+                  __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                  if (plane == 0) {
+                    w[i] = *reinterpret_cast<uint32_t*>(&h);
+                  } else {
+                    float2 hf = __bfloat1622float2(h);
+                    __nv_bfloat162 l = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
+                    w[i] = *reinterpret_cast<uint32_t*>(&l);
+                  }
+                }
+                sts_u128(sbuf + (uint32_t)lane * (NCH * 16) + (uint32_t)((g8 ^ (lane & (NCH - 1))) << 4), w[0], w[1], w[2], w[3]);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) {
+                const int rr = k * RPI + lane / NCH, jj = lane % NCH;
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                             : "r"(sbuf + (uint32_t)rr * (NCH * 16) + (uint32_t)((jj ^ (rr & (NCH - 1))) << 4)) : "memory");
+                const int orr = orr_k[k];
+                if (orr >= 0) {
+                  unsigned short* ob = reinterpret_cast<unsigned short*>(a.out + (size_t)orr * a.out_stride) + cbase +
+                                       (plane ? a.out_ctot : 0) + jj * 8;
+                  *reinterpret_cast<uint4*>(ob) = make_uint4(w0, w1, w2, w3);
+                }
+              }
+              __syncwarp();
+            }
+          } else if (orow.cstride == 1 && fullc && a.out_fmt == FD_FMT_SPLIT_BF16 &&
               ((((uintptr_t)orow.base) + 2 * (size_t)(orow.coff + cbase)) & 15) == 0 && (a.out_ctot & 7) == 0) {
             // split once here so that every consumer layer gathers ready-made bf16 hi/lo planes
             unsigned short* ob = reinterpret_cast<unsigned short*>(orow.base) + orow.coff + cbase;
