@@ -992,15 +992,30 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
                               a.out_fmt == FD_FMT_SPLIT_BF16 && (a.out_ctot & 7) == 0 && (a.out_stride & 3) == 0 &&
                               ((((uintptr_t)a.out) + 2 * (size_t)cbase) & 15) == 0;
           if (!work && !co_out) continue;
+          if (ss_smem) {
+            // folded scale / shift from shared memory, four channels per load (the epilogue's instruction stream competes with
+            // the producer and MMA warps for issue slots: FD_TC_DEBUG & 8 -- no epilogue math -- is worth 14 %)
 #pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            const int c = cbase + i;
-            float sc, sh;
-            if (ss_smem) { sc = s_scale[c]; sh = s_shift[c]; }
-            else { sc = (a.scale && c < a.cout) ? __ldg(a.scale + c) : 1.f; sh = (a.shift && c < a.cout) ? __ldg(a.shift + c) : 0.f; }
-            float v = fmaf(__uint_as_float(r[i]), sc, sh) + y[i];
-            if (a.relu) v = fmaxf(v, 0.f);
-            y[i] = v;
+            for (int i4 = 0; i4 < CH / 4; ++i4) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + cbase + 4 * i4);
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + cbase + 4 * i4);
+              const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v = fmaf(__uint_as_float(r[4 * i4 + j]), scv[j], shv[j]) + y[4 * i4 + j];
+                if (a.relu) v = fmaxf(v, 0.f);
+                y[4 * i4 + j] = v;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const int c = cbase + i;
+              const float sc = (a.scale && c < a.cout) ? __ldg(a.scale + c) : 1.f, sh = (a.shift && c < a.cout) ? __ldg(a.shift + c) : 0.f;
+              float v = fmaf(__uint_as_float(r[i]), sc, sh) + y[i];
+              if (a.relu) v = fmaxf(v, 0.f);
+              y[i] = v;
+            }
           }
           if (co_out) {
             constexpr int NCH = CH / 8;                        // 16-byte chunks of a row's CH bf16 columns (per plane)
