@@ -66,6 +66,8 @@ int fd_conv_forward(const fd_conv_desc* d, void* stream_) {
   a.mode = d->mode; a.nbr = d->d_nbr; a.nbr_stride = d->nbr_stride; a.tile_mask = d->d_tile_mask;
   a.Hin = d->Hin; a.Win = d->Win; a.Hout = d->Hout; a.Wout = d->Wout;
   a.kh = d->kh; a.kw = d->kw; a.sh = d->sh; a.sw = d->sw; a.ph = d->ph; a.pw = d->pw;
+  a.row_perm = d->d_row_perm;
+  FD_REQUIRE(!d->d_row_perm || d->mode == FD_GATHER_TABLE, "fd_conv_forward: d_row_perm needs FD_GATHER_TABLE");
   a.out_map = d->out_map;
   a.out_coords = (const int4*)d->d_out_coords4; a.bevD = d->bevD; a.bevH = d->bevH; a.bevW = d->bevW;
 

@@ -26,6 +26,7 @@ struct ConvArgs {
   int n_in_cap;            // rows of `in` (weight gradient only; 0 = unknown)
   const void* in_split;    // weight gradient only: dense FD_FMT_SPLIT_BF16 copies of `in` / dL/dy ([rows][C hi | C lo]) when
   const void* out_split;   // the caller already has them (NULL: the tcgen05 arm splits into its workspace)
+  const int32_t* row_perm; // FD_GATHER_TABLE: nbr / tile_mask are sorted tables, tile position j is output row row_perm[j]
 };
 
 // input row feeding output row `o` through kernel offset `k`, or -1

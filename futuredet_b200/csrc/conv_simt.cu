@@ -130,6 +130,7 @@ conv_simt_kernel(const ConvArgs a) {
     for (int i = 0; i < TM; ++i) {
       int o = row0 + ty * TM + i;
       if (o >= n) continue;
+      if (a.row_perm) o = __ldg(a.row_perm + o);          // sorted table: tile position -> output row
       OutRow orow = map_out_row(a, o);
 #pragma unroll
       for (int j = 0; j < TN; ++j) {

@@ -455,6 +455,8 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* v) {
   }
 }
 
+// (128 registers is the hard limit of 14 warps: an SM sub-partition holds 4 of them in its 16 K registers; __maxnreg__(144)
+// compiles without spills but cannot launch)
 template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs t) {
@@ -917,11 +919,23 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int col0 = tn * NT;
+      // sorted rulebook (fd_rulebook_sort_rows): tile position -> output row.  The lookup is a dependent global load in
+      // front of everything a tile's epilogue does, so it is issued one tile ahead (the first one before the wait for the
+      // accumulators): sorted narrow layers are epilogue bound.
+      auto perm_row = [&](int ti) -> int {
+        const int idx = (st * T + ti) * TC_BM + q * 32 + lane;
+        return idx < n ? __ldg(a.row_perm + idx) : -1;
+      };
+      int o_next = a.row_perm ? perm_row(0) : 0;
       mbar_wait(smem_u32(&t_full[acc]), acc_phase, 6, 64);
       if (threadIdx.x == (TC_MMA_WARP + 1) * 32) TC_TRACE(2, 2 * it, clock64());
       tc_fence_after();
       for (int ti = 0; ti < live; ++ti) {
-        const int o = tiled ? tile_row_to_o(st * T + ti, q * 32 + lane) : (st * T + ti) * TC_BM + q * 32 + lane;
+        int o = tiled ? tile_row_to_o(st * T + ti, q * 32 + lane) : (st * T + ti) * TC_BM + q * 32 + lane;
+        if (a.row_perm) {
+          o = o_next;
+          if (ti + 1 < live) o_next = perm_row(ti + 1);
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + ti) * ACC);
         const bool live_row = o >= 0 && o < n;
         OutRow orow{nullptr, 0, 1};
@@ -933,7 +947,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
 #pragma unroll
         for (int k = 0; k < NCHq; ++k) {
           const int rr = k * RPIq + lane / NCHq;
-          const int v = tiled ? tile_row_to_o(st * T + ti, q * 32 + rr) : (st * T + ti) * TC_BM + q * 32 + rr;
+          const int v = a.row_perm ? __shfl_sync(0xffffffffu, o, rr)
+                        : tiled    ? tile_row_to_o(st * T + ti, q * 32 + rr) : (st * T + ti) * TC_BM + q * 32 + rr;
           orr_k[k] = (v >= 0 && v < n) ? v : -1;
         }
 #pragma unroll 1

@@ -39,6 +39,7 @@ class ConvDesc(C.Structure):
         ("precision", C.c_int32),
         ("n_in_cap", C.c_int32),
         ("d_in_split", C.c_void_p), ("d_out_split", C.c_void_p),
+        ("d_row_perm", C.c_void_p),
     ]
 
 
@@ -66,13 +67,17 @@ SIGNATURES = {
                                           C.c_int, C.c_void_p, C.c_void_p]),
     "fd_rulebook_neighbors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                          c_int_p, c_int_p, c_int_p, c_int_p, C.c_void_p, C.c_int, C.c_void_p,
-                                         C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_rulebook_neighbors_bitmap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, c_int_p,
-                                                c_int_p, c_int_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                                c_int_p, c_int_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]),
     "fd_rulebook_neighbors_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, c_int_p,
                                                  c_int_p, c_int_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                                  C.c_void_p]),
     "fd_rulebook_count_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "fd_rulebook_sort_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "fd_rulebook_sort_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "fd_rulebook_to_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p]),
     "fd_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),

@@ -5,6 +5,7 @@ inside libfuturedet_b200.so.  All functions raise RuntimeError when the library 
 call fails -- there is no fallback path.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -115,14 +116,43 @@ class BitmapIndex:
         self.bitmap, self.prefix, self.shape = bitmap, prefix, [int(s) for s in shape]
 
 
+SORT_TILES = os.environ.get("FD_SORT_TILES", "1") != "0"   # tensor-core inference convs over 3x3x3 rulebooks run on pattern-sorted tiles (Rulebook.sorted_tiles)
+SORT_WINDOW = int(os.environ.get("FD_SORT_WINDOW", 256 * 1024))     # rows per sorting window (a few scenes of a level: the gathered rows stay L2 resident)
+SORT_STRIDED = os.environ.get("FD_SORT_STRIDED", "0") != "0"   # also sort the tables of the strided convs (one launch each:
+                             # the copy costs what the launch gains)
+SORT_MIN_BATCH = int(os.environ.get("FD_SORT_MIN_BATCH", 2))   # scenes per forward from which the sort pays for its launches
+SORT_MIN_ROWS = 4096         # smaller levels are not worth three more launches
+
+
 class Rulebook:
     """Gather-form rulebook: nbr [K, n_out_cap] int32 (input row or -1), pair_num [K]."""
 
     def __init__(self, nbr, pair_num, K, out_coords, n_out_dev, n_out_cap, out_shape, ksize, stride, padding,
                  tile_mask=None):
         self.nbr, self._pair_num, self.K, self.tile_mask = nbr, pair_num, K, tile_mask
+        self._sorted = None
+        self.row_key = None       # [n_out_cap] int16 neighbour-pattern keys left by the neighbour search (sort key)
         self.out_coords, self.n_out_dev, self.n_out_cap = out_coords, n_out_dev, n_out_cap
         self.out_shape, self.ksize, self.stride, self.padding = out_shape, ksize, stride, padding
+
+    def sorted_tiles(self):
+        """(row_perm [n_out_cap], nbr_sorted [K, stride], tile_mask_sorted) of fd_rulebook_sort_rows: the rows of the table
+        regrouped, inside windows of SORT_WINDOW rows, by neighbour pattern, so that the 128-row tiles of the
+        output-stationary convolution skip most kernel offsets.  Built once per rulebook, shared by its convolutions."""
+        if self._sorted is None:
+            lib = L.load()
+            n, dev = self.n_out_cap, self.nbr.device
+            stride = int(self.nbr.stride(0))
+            perm = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+            nbr_s = torch.empty_like(self.nbr)
+            tmask = torch.empty(((max(n, 1) + 127) // 128,), dtype=torch.int32, device=dev)
+            ws_bytes = lib.fd_rulebook_sort_workspace_bytes(n, SORT_WINDOW)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            rc = lib.fd_rulebook_sort_rows(_ptr(self.nbr), stride, self.K, _ptr(self.n_out_dev), n, SORT_WINDOW,
+                                           _ptr(self.row_key), _ptr(perm), _ptr(nbr_s), _ptr(tmask), _ptr(ws), ws_bytes, _stream())
+            L.check(rc, "fd_rulebook_sort_rows")
+            self._sorted = (perm, nbr_s, tmask)
+        return self._sorted
 
     @property
     def pair_num(self):
@@ -151,26 +181,27 @@ class Rulebook:
         return pairs, self.pair_num
 
 
-def _neighbors(out_coords, n_out_dev, n_out_cap, index, ksize, stride, padding):
+def _neighbors(out_coords, n_out_dev, n_out_cap, index, ksize, stride, padding, want_keys=False):
     lib = L.load()
     K = int(ksize[0] * ksize[1] * ksize[2])
     dev = out_coords.device
     nbr = torch.empty((K, max(n_out_cap, 1)), dtype=torch.int32, device=dev)
     pair_num = None          # counted lazily (Rulebook.pair_num)
     tile_mask = torch.empty(((max(n_out_cap, 1) + 127) // 128,), dtype=torch.int32, device=dev) if K <= 32 else None
+    row_key = torch.empty((max(n_out_cap, 1),), dtype=torch.int16, device=dev) if want_keys and K <= 32 else None
     if isinstance(index, BitmapIndex):
         rc = lib.fd_rulebook_neighbors_bitmap(_ptr(out_coords), _ptr(n_out_dev), n_out_cap, _ptr(index.bitmap),
                                               _ptr(index.prefix), L.i32x3(index.shape), L.i32x3(ksize), L.i32x3(stride),
                                               L.i32x3(padding), _ptr(nbr), max(n_out_cap, 1), _ptr(pair_num),
-                                              _ptr(tile_mask), _stream())
+                                              _ptr(tile_mask), _ptr(row_key), _stream())
         L.check(rc, "fd_rulebook_neighbors_bitmap")
-        return nbr, pair_num, K, tile_mask
+        return nbr, pair_num, K, tile_mask, row_key
     rc = lib.fd_rulebook_neighbors(_ptr(out_coords), _ptr(n_out_dev), n_out_cap, _ptr(index.table),
                                    index.cap, L.i32x3(index.shape), L.i32x3(ksize), L.i32x3(stride),
                                    L.i32x3(padding), _ptr(nbr), max(n_out_cap, 1), _ptr(pair_num), _ptr(tile_mask),
-                                   _stream())
+                                   _ptr(row_key), _stream())
     L.check(rc, "fd_rulebook_neighbors")
-    return nbr, pair_num, K, tile_mask
+    return nbr, pair_num, K, tile_mask, row_key
 
 
 def rulebook_subm(coords, n_dev, n_cap, shape, ksize, index=None, batch_size=None):
@@ -180,8 +211,11 @@ def rulebook_subm(coords, n_dev, n_cap, shape, ksize, index=None, batch_size=Non
             raise RuntimeError("rulebook_subm needs batch_size (or a prebuilt CoordIndex)")
         index = CoordIndex(coords, n_dev, n_cap, shape, batch_size)
     pad = [k // 2 for k in ksize]
-    nbr, pair_num, K, tmask = _neighbors(coords, n_dev, n_cap, index, ksize, [1, 1, 1], pad)
-    return Rulebook(nbr, pair_num, K, coords, n_dev, n_cap, list(shape), list(ksize), [1, 1, 1], pad, tmask), index
+    nbr, pair_num, K, tmask, row_key = _neighbors(coords, n_dev, n_cap, index, ksize, [1, 1, 1], pad,
+                                                  want_keys=SORT_TILES and n_cap >= SORT_MIN_ROWS)
+    rb = Rulebook(nbr, pair_num, K, coords, n_dev, n_cap, list(shape), list(ksize), [1, 1, 1], pad, tmask)
+    rb.row_key = row_key
+    return rb, index
 
 
 def conv_out_shape(shape, ksize, stride, padding):
@@ -228,7 +262,7 @@ def rulebook_conv(coords, n_dev, n_cap, batch_size, shape, ksize, stride, paddin
         L.check(rc, "fd_rulebook_neighbors_scatter")
     else:
         index = index or CoordIndex(coords, n_dev, n_cap, shape, batch_size)
-        nbr, pair_num, K, tmask = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
+        nbr, pair_num, K, tmask, _ = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
     rb = Rulebook(nbr, pair_num, K, out_coords, n_out, n_out_cap, out_shape, list(ksize), list(stride),
                   list(padding), tmask)
     rb.out_index = BitmapIndex(bitmap, prefix, out_shape)      # index of the OUTPUT set for the layers that follow
@@ -380,7 +414,7 @@ def _conv_desc(x, cin, w, scale, shift, residual, relu, out, precision, separate
 
 
 def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out=None, precision="fp32",
-                bev=None, out_fmt="fp32", bev_dmajor=False):
+                bev=None, out_fmt="fp32", bev_dmajor=False, sort_tiles=False):
     """out[o] = act((sum_k x[nbr[k,o]] @ w[k]) * scale + shift (+ residual[o])).
 
     x / residual / out: torch fp32 tensors or Feat views (fp32 or split rows); w [K, Cin, Cout] fp32; rb: Rulebook.
@@ -411,8 +445,13 @@ def sparse_conv(x, w, rb, scale=None, shift=None, residual=None, relu=False, out
         d = _conv_desc(x, cin, w, scale, shift, residual, relu, out, precision)
         d.out_map = L.OUTMAP_IDENTITY
     d.mode = L.GATHER_TABLE
-    d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
-    d.d_tile_mask = rb.tile_mask.data_ptr() if rb.tile_mask is not None else None
+    if sort_tiles and SORT_TILES and rb.K == 27 and n_cap >= SORT_MIN_ROWS:
+        perm, nbr_s, tmask_s = rb.sorted_tiles()
+        d.d_nbr = nbr_s.data_ptr(); d.nbr_stride = nbr_s.stride(0)
+        d.d_tile_mask = tmask_s.data_ptr(); d.d_row_perm = perm.data_ptr()
+    else:
+        d.d_nbr = rb.nbr.data_ptr(); d.nbr_stride = rb.nbr.stride(0)
+        d.d_tile_mask = rb.tile_mask.data_ptr() if rb.tile_mask is not None else None
     d.d_n_out = rb.n_out_dev.data_ptr() if rb.n_out_dev is not None else None
     d.n_out_cap = n_cap
     e0 = _prof_begin()

@@ -163,7 +163,9 @@ class _SparseConvBase(SparseModule):
             D, H, W = rb.out_shape
             return ops.sparse_conv(xin, w, rb, scale, shift, None, relu, precision=prec,
                                    bev=(x.batch_size, D, H, W), out_fmt=out_fmt, bev_dmajor=bev_dmajor)
-        y = ops.sparse_conv(xin, w, rb, scale, shift, residual, relu, precision=prec, out_fmt=out_fmt)
+        y = ops.sparse_conv(xin, w, rb, scale, shift, residual, relu, precision=prec, out_fmt=out_fmt,
+                            sort_tiles=prec != "fp32" and (self.subm or ops.SORT_STRIDED) and
+                            x.batch_size >= ops.SORT_MIN_BATCH)
         if self.subm:
             return x._like(y)
         out = x._like(y, rb.out_coords, rb.out_shape, rb.n_out_dev, rb.n_out_cap)

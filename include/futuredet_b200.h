@@ -29,9 +29,11 @@
 extern "C" {
 #endif
 
-/* 3: fd_conv_desc gained n_in_cap / d_in_split / d_out_split (weight gradient), fd_affine_act and fd_bn_backward gained
+/* 4: fd_rulebook_sort_rows + fd_conv_desc.d_row_perm (tiles of rows sorted by neighbour pattern; appended, so ABI 3
+ *    callers that zero the descriptor keep working).
+ * 3: fd_conv_desc gained n_in_cap / d_in_split / d_out_split (weight gradient), fd_affine_act and fd_bn_backward gained
  *    the optional split-bf16 copy outputs (round 2, training step).  2: first published layout.                    */
-#define FD_ABI_VERSION 3
+#define FD_ABI_VERSION 4
 
 /* ---- library ------------------------------------------------------------ */
 int         fd_version(void);
@@ -104,12 +106,14 @@ int fd_rulebook_out_coords(const int32_t* d_in_coords4, const int32_t* d_n_in, i
  * receives the number of pairs per kernel offset (spconv `indice_pair_num`); pass NULL on the hot path and call
  * fd_rulebook_count_pairs() only when the counts are needed (export, flop accounting).
  * d_tile_mask (optional, [ceil(n_out_cap/128)] uint32, K <= 32): bit k of word t is set when some row of
- * the 128-row tile t has a neighbour through offset k; fd_conv_forward skips the other offsets.        */
+ * the 128-row tile t has a neighbour through offset k; fd_conv_forward skips the other offsets.
+ * d_row_key (optional, [n_out_cap] uint16, K <= 32): the 9-bit neighbour-pattern signature of every row, the sort key
+ * of fd_rulebook_sort_rows (the search has the pattern in registers; passing it on saves that call a pass over the table). */
 int fd_rulebook_neighbors(const int32_t* d_out_coords4, const int32_t* d_n_out, int n_out_cap,
                           const uint64_t* d_in_table, int64_t in_cap,
                           const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
                           const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
-                          uint32_t* d_tile_mask, void* stream);
+                          uint32_t* d_tile_mask, uint16_t* d_row_key, void* stream);
 
 int fd_rulebook_count_pairs(const int32_t* d_nbr, int nbr_stride, const int32_t* d_n_out, int n_out_cap, int K,
                             int32_t* d_pair_num, void* stream);
@@ -121,7 +125,7 @@ int fd_rulebook_neighbors_bitmap(const int32_t* d_out_coords4, const int32_t* d_
                                  const uint32_t* d_in_bitmap, const int32_t* d_in_wordprefix,
                                  const int32_t* in_shape3, const int32_t* ksize3, const int32_t* stride3,
                                  const int32_t* pad3, int32_t* d_nbr, int nbr_stride, int32_t* d_pair_num,
-                                 uint32_t* d_tile_mask, void* stream);
+                                 uint32_t* d_tile_mask, uint16_t* d_row_key, void* stream);
 /* Strided (SparseConv3d) rulebooks built from the INPUT side: every active input enumerates the <= prod(ceil(k/s))
  * outputs it reaches, finds their rows through the bitmap + popcount prefix of the OUTPUT set left by
  * fd_rulebook_out_coords, and writes nbr[k][out] = in (the call pre-fills the d_n_out live rows of d_nbr with -1 and
@@ -132,6 +136,21 @@ int fd_rulebook_neighbors_scatter(const int32_t* d_in_coords4, const int32_t* d_
                                   const int32_t* ksize3, const int32_t* stride3, const int32_t* pad3,
                                   const int32_t* d_n_out, int n_out_cap, int32_t* d_nbr, int nbr_stride,
                                   uint32_t* d_tile_mask, void* stream);
+
+/* Tile sorting (inference hot path).  The output-stationary convolution works on tiles of 128 consecutive rows and
+ * skips the kernel offsets no row of a tile uses (d_tile_mask); in voxelizer / raster order nearly every tile of a LiDAR
+ * level uses all 27.  This call reorders the ROWS OF THE TABLE, inside windows of `window` rows (rounded up to a multiple
+ * of 1024; <= 0: 262144), by a 9-bit signature of each row's neighbour pattern, so that rows with the same pattern share
+ * tiles:  d_nbr_sorted[k*nbr_stride + j] = d_nbr[k*nbr_stride + d_row_perm[j]],  d_tile_mask_sorted = masks of the sorted
+ * tiles.  Pass the sorted table + masks + d_row_perm to fd_conv_forward: tile position j is then written to (and takes
+ * its residual from) row d_row_perm[j], so inputs, outputs and their row order are unchanged and the results are
+ * bit-identical to the unsorted call (a skipped offset only ever contributed exact zeros).  The order inside a bucket is
+ * unspecified.  d_row_key: the keys fd_rulebook_neighbors[_bitmap] wrote for this table, or NULL (computed from the table).
+ * Replaces nothing in the reference (spconv 1.x has no counterpart); K <= 32.                          */
+size_t fd_rulebook_sort_workspace_bytes(int n_out_cap, int window);
+int fd_rulebook_sort_rows(const int32_t* d_nbr, int nbr_stride, int K, const int32_t* d_n_out, int n_out_cap, int window,
+                          const uint16_t* d_row_key, int32_t* d_row_perm, int32_t* d_nbr_sorted, uint32_t* d_tile_mask_sorted, void* d_workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* Export to the spconv-1.x layout `indice_pairs [K,2,P_cap]` (pairs of offset k
  * listed in ascending output row), for parity checks and interop.            */
@@ -189,6 +208,9 @@ typedef struct fd_conv_desc {
   const void*    d_in_split;  /* fd_conv_wgrad_det, optional: dense FD_FMT_SPLIT_BF16 copies ([rows][C hi | C lo]) of   */
   const void*    d_out_split; /* d_in / dL/dy that the caller already holds (fd_affine_act / fd_bn_backward write    */
                               /* them); NULL: the tcgen05 arm splits the fp32 rows into its workspace             */
+  const int32_t* d_row_perm;  /* fd_conv_forward with FD_GATHER_TABLE, optional: d_nbr / d_tile_mask are the SORTED table
+                               * of fd_rulebook_sort_rows and tile position j belongs to output row d_row_perm[j]
+                               * (NULL: position j is row j).  Must be NULL for fd_conv_wgrad*.                       */
 } fd_conv_desc;
 
 enum { FD_GATHER_TABLE = 0, FD_GATHER_CONV2D = 1, FD_GATHER_CONVT2D = 2,

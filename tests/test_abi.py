@@ -52,7 +52,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(dll, s), "missing export %s" % s
     assert sorted(lib.SIGNATURES) == syms          # the ctypes table binds exactly the declared ABI
-    assert lib.load().fd_version() == 3
+    assert lib.load().fd_version() == 4
 
 
 def test_conv_desc_layout_matches_header():

@@ -173,3 +173,52 @@ def test_dense_conv_split_format_and_slices(cuda):
     ops.conv2d_nhwc(xs, wk, (3, 3), (1, 1), (1, 1), relu=True, out=wide.slice(32, cout), precision="bf16x3")
     torch.testing.assert_close(wide.slice(32, cout).to_fp32().permute(0, 3, 1, 2).cpu(), want, rtol=3e-4, atol=3e-4)
     assert wide.slice(0, 32).to_fp32().abs().max().item() == 0 and wide.slice(64, 32).to_fp32().abs().max().item() == 0
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 32), (64, 64), (128, 128)])
+def test_sorted_tiles_bit_identical(cuda, cin, cout, monkeypatch):
+    """fd_rulebook_sort_rows: the sorted table is the source table with its rows permuted inside the windows, its masks
+    are those of the sorted tiles, and a convolution over it (row_perm epilogue) is bit-identical to the unsorted call
+    on both arms, residual + ReLU included; the sparse, clustered sites make most tiles skip most kernel offsets."""
+    monkeypatch.setattr(ops, "SORT_WINDOW", 2048)
+    monkeypatch.setattr(ops, "SORT_MIN_ROWS", 0)
+    rng = np.random.default_rng(cin + cout)
+    shape, B = [12, 96, 96], 2
+    c = random_sites(rng, B, shape, 9000)                 # ~4 % occupancy: few neighbours per row
+    n = len(c)
+    cap = n + 517
+    ct = torch.zeros((cap, 4), dtype=torch.int32, device=cuda); ct[:n] = torch.from_numpy(c).to(cuda)
+    nd = torch.tensor([n], dtype=torch.int32, device=cuda)
+    rb, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3], batch_size=B)
+    assert rb.row_key is not None                         # keys handed over by the neighbour search
+    perm, nbr_s, tmask_s = rb.sorted_tiles()
+    keys = rb.row_key[:n].cpu().numpy().astype(np.int64)
+    rb2, _ = ops.rulebook_subm(ct, nd, cap, shape, [3, 3, 3], batch_size=B)
+    rb2.row_key = None                                    # ... or computed from the table: same buckets
+    perm2 = rb2.sorted_tiles()[0][:n].cpu().numpy()
+    p = perm[:n].cpu().numpy()
+    assert np.array_equal(keys[p], keys[perm2])
+    assert all(np.all(np.diff(keys[p][w:w + 2048]) >= 0) for w in range(0, n, 2048))   # ascending keys inside a window
+    assert np.array_equal(np.sort(p), np.arange(n))                                     # a permutation of the live rows
+    win = 2048
+    assert np.array_equal(p // win, np.arange(n) // win)                                # ... inside the windows
+    nbr, ns = rb.nbr.cpu().numpy()[:, :n], nbr_s.cpu().numpy()[:, :n]
+    assert np.array_equal(ns, nbr[:, p])
+    bits = ((ns >= 0).astype(np.uint32) << np.arange(27, dtype=np.uint32)[:, None]).sum(0).astype(np.uint32)
+    want_mask = np.array([np.bitwise_or.reduce(bits[t:t + 128]) for t in range(0, n, 128)], np.uint32)
+    assert np.array_equal(tmask_s.cpu().numpy().view(np.uint32)[:len(want_mask)], want_mask)
+    unsorted_mask = rb.tile_mask.cpu().numpy().view(np.uint32)[:len(want_mask)]
+    popc = lambda m: sum(int(v).bit_count() for v in m)
+    assert popc(want_mask) < 0.8 * popc(unsorted_mask)                                  # the point of sorting
+    x = torch.zeros((cap, cin), device=cuda); x[:n] = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32)).to(cuda)
+    res = torch.zeros((cap, cout), device=cuda); res[:n] = torch.from_numpy(rng.standard_normal((n, cout)).astype(np.float32)).to(cuda)
+    w = torch.from_numpy((rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32)).to(cuda)
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32)).to(cuda)
+    shift = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).to(cuda)
+    for prec in ("fp32", "bf16x3"):
+        for fmt in (("fp32",) if prec == "fp32" else ("fp32", "split")):
+            xin, rin = (ops.to_split(x, nd), ops.to_split(res, nd)) if fmt == "split" else (x, res)
+            ya = ops.sparse_conv(xin, w, rb, scale, shift, rin, True, precision=prec, out_fmt=fmt, sort_tiles=False)
+            yb = ops.sparse_conv(xin, w, rb, scale, shift, rin, True, precision=prec, out_fmt=fmt, sort_tiles=True)
+            ya, yb = (ya.t, yb.t) if fmt == "split" else (ya, yb)
+            assert torch.equal(ya[:n].view(torch.int32), yb[:n].view(torch.int32)), (prec, fmt)
