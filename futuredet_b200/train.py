@@ -180,7 +180,10 @@ def sparse_conv_train(tape, x, conv, xt, grads, prec):
     p = _prec_for(prec, cin, K, x.t)
     xs = x.s if (p != "fp32" and x.s is not None and x.s.shape[-1] == cin) else None
     xf = ops.Feat(xs, "split", 0, cin) if xs is not None else ops.Feat(x.t, "fp32", 0, cin)
-    y_t = ops.sparse_conv(xf, w, rb, None, bias, None, False, precision=p, out_fmt="fp32")
+    # SubM layers of a multi-sample step run on pattern-sorted tiles like the inference path (same table for the data
+    # gradient: it is its own transpose); bit-identical to the unsorted call
+    sort = conv.subm and xt.batch_size >= ops.SORT_MIN_BATCH
+    y_t = ops.sparse_conv(xf, w, rb, None, bias, None, False, precision=p, out_fmt="fp32", sort_tiles=sort and p != "fp32")
     y = Var(y_t, True, rb.n_out_dev, rb.n_out_cap)
     if conv.subm:
         out = xt._like(y_t)
@@ -209,7 +212,8 @@ def sparse_conv_train(tape, x, conv, xt, grads, prec):
                 table = T.TableView(T.rulebook_transpose(rb, n_in_cap), K, n_in_dev, n_in_cap)
                 wt = w.transpose(1, 2).contiguous()
             gin = ops.Feat(gys, "split", 0, cout) if (gys is not None and pd != "fp32") else gy
-            gx = ops.sparse_conv(gin, wt, table, precision=pd, out_fmt="fp32")
+            gx = ops.sparse_conv(gin, wt, table, precision=pd, out_fmt="fp32",
+                                 sort_tiles=sort and pd != "fp32" and table is rb)
             x.accumulate(gx)
 
     tape.add(backward)

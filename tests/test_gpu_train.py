@@ -610,6 +610,31 @@ def test_train_step_on_fused_points_path(cuda):
     assert all(p.grad is not None and p.grad.data_ptr() == tr.grads.grad(p).data_ptr() for p in model.parameters())
 
 
+def test_sorted_tiles_leave_training_bit_identical(cuda, monkeypatch):
+    """Pattern-sorted SubM tiles (forward and data-gradient convolutions of a multi-sample step) only change which tile a
+    row is computed in: same losses and gradients, bit for bit, as the unsorted step."""
+    from futuredet_b200 import ops
+    from futuredet_b200.synth import NUSC_RANGE, NUSC_VOXEL, synth_scene
+    from oracle.gen_golden import make_targets
+    monkeypatch.setattr(ops, "SORT_MIN_ROWS", 0)
+    scenes = [synth_scene(20000, seed=s) for s in (2, 3)]
+    pts = torch.from_numpy(np.concatenate(scenes)).to(cuda)
+    off = torch.tensor(np.r_[0, np.cumsum([len(s) for s in scenes])], dtype=torch.int32, device=cuda)
+    example = make_targets(2, 180, 180, 3, torch.Generator().manual_seed(0), max_objs=50)
+    out = []
+    for min_batch in (1, 100):
+        monkeypatch.setattr(ops, "SORT_MIN_BATCH", min_batch)
+        model = build_model(3, cuda).to(cuda).train()
+        model.configure_voxelizer(dict(range=NUSC_RANGE, voxel_size=NUSC_VOXEL, max_points_in_voxel=10,
+                                       max_voxel_num=[120000, 160000]), training=True)
+        tr = train.NativeTrainer(model, precision="bf16x3")
+        losses = tr.step(example, points=pts, batch_offsets=off)
+        out.append((sum(losses["loss"]).clone(), {k: p.grad.clone() for k, p in model.named_parameters()}))
+    assert torch.equal(out[0][0], out[1][0])
+    for k in out[0][1]:
+        assert torch.equal(out[0][1][k], out[1][1][k]), k
+
+
 def test_reference_trainer_idiom_loss_backward(cuda):
     """`losses = model(example, return_loss=True); sum(losses["loss"]).backward()` (trainer.py:85,317-344) drives the
     native backward through the autograd bridge and fills param.grad with the same gradients as NativeTrainer.step."""

@@ -10,11 +10,15 @@ for l in csv.reader(open(sys.argv[1])):
     if len(l) < 15 or l[0] == "ID":
         continue
     r = rows.setdefault(int(l[0]), {"name": l[4]})
-    r[l[12]] = float(l[14].replace(",", ""))
+    try:
+        r[l[12]] = float(l[14].replace(",", ""))
+    except ValueError:                      # "n/a" (a metric the kernel does not report)
+        pass
 fam = collections.OrderedDict()
 for r in rows.values():
     n = r["name"]
     key = ("conv_tc" if "conv_tc_kernel" in n else "conv_simt" if "conv_simt" in n else "voxelize" if "vox_" in n else
+           "rowsort" if "rowsort" in n else
            "rulebook" if any(k in n for k in ("neighbors", "outset", "coord_index", "nbr_")) else "scan" if "scan" in n else
            "wgrad" if "wgrad" in n else "other")
     f = fam.setdefault(key, collections.Counter())
