@@ -14,6 +14,11 @@
 //     hardware arrives on the stage's mbarrier when the bytes land (cp.async.mbarrier.arrive.noinc);
 //   * kernel offsets that are empty for the whole super-tile are skipped (per-tile masks from the rulebook).
 //
+//   * dense 3x3 stride-1 convolutions (neck, head) run as "tall stages" (TALL instantiation): an M tile is an 8 x 16-pixel
+//     patch, an A stage the TMA box {64 ch, 8 px, 18 lines} of one horizontal tap; the three vertical taps read the same
+//     bytes through descriptors 0 / 1024 / 2048 bytes into the stage (a patch line = 8 rows = one swizzle atom), so a
+//     pixel crosses L2 -> shared memory 3.4 times instead of 9.
+//
 // Warp roles (416 threads):
 //   warps 0-7   producers, split into 4 groups that fill different A stages concurrently (A ring of 4-5 x 32 KB);
 //               the group that opens a K stage also issues the B bulk copy (B ring of 2 slots);
@@ -59,6 +64,14 @@ constexpr int TC_SS_MAX = 512;                         // folded BN scale / shif
 constexpr int TC_A_PLANE = TC_BM * TC_ROWB;   // bytes of one A plane (hi or lo) per stage
 constexpr int TC_EPI_WARP_BYTES = 2048;       // per epilogue warp: 32 rows x 64 bytes of staging for coalesced row I/O
 constexpr int TC_EPI_BYTES = 4 * TC_EPI_WARP_BYTES;
+// dense 3x3 stride-1 "tall" stages (tma == 3): an A stage is an 8-pixel-wide, 16 + 2-line patch of one 64-channel chunk
+// at one horizontal tap; the three vertical taps are the same shared-memory bytes read 8 rows (= 1024 bytes, one swizzle
+// atom) further down, so a pixel is loaded 3 x 18/16 times instead of 9 times
+constexpr int TC_TALL_BW = 8, TC_TALL_BH = 16;
+constexpr int TC_TALL_PLANE = (TC_TALL_BH + 2) * TC_TALL_BW * TC_ROWB;   // 18 KB per plane
+constexpr int TC_TALL_BYTES = 2 * TC_TALL_PLANE;                          // hi + lo
+constexpr int TC_TALL_SLOTS = 4;                                          // two tiles of the current tap column + two of the next
+constexpr int TC_TALL_T = 2;
 
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -437,6 +450,9 @@ template <int NT> struct TcCfg {
   static constexpr int NBAR = 2 * SA + 2 * SB + 4;
   static constexpr size_t SMEM = 1024 + (size_t)SA * A_BYTES + (size_t)SB * B_BYTES + IDX_BYTES + 2 * TC_SS_MAX * 4 + TC_EPI_BYTES + NBAR * 8 + 64;
   static_assert(SMEM <= 232448, "shared memory budget");
+  // tall-stage layout: A ring of TC_TALL_SLOTS x 36 KB, no dense index cache
+  static constexpr size_t SMEM_TALL = 1024 + (size_t)TC_TALL_SLOTS * TC_TALL_BYTES + (size_t)SB * B_BYTES + 2 * TC_SS_MAX * 4 + TC_EPI_BYTES + NBAR * 8 + 64;
+  static_assert(SMEM_TALL <= 232448 && SA >= TC_TALL_SLOTS, "shared memory budget (tall stages)");
 };
 
 template <int N>
@@ -457,7 +473,9 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* v) {
 
 // (128 registers is the hard limit of 14 warps: an SM sub-partition holds 4 of them in its 16 K registers; __maxnreg__(144)
 // compiles without spills but cannot launch)
-template <int NT>
+// TALL: the tall-stage dense 3x3 path (t.tma == 3) is its own instantiation -- the kernel sits at the 128-register ceiling, and
+// any code added to the common one changes what ptxas spills in the gather producers' loop (measured: sparse family +8 %)
+template <int NT, bool TALL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs t) {
   using Cfg = TcCfg<NT>;
@@ -468,10 +486,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms want 1024-B (128B) / 512-B (64B) alignment
+  constexpr bool tall = TALL;
   uint8_t* a_ring = smem;
-  uint8_t* b_ring = a_ring + SA * Cfg::A_BYTES;
+  uint8_t* b_ring = a_ring + (tall ? TC_TALL_SLOTS * TC_TALL_BYTES : SA * Cfg::A_BYTES);
   int* s_idx = (int*)(b_ring + SB * Cfg::B_BYTES);                // [TMAX][TC_DENSE_MAXK][128] (dense mode)
-  float* s_scale = (float*)((uint8_t*)s_idx + Cfg::IDX_BYTES);    // [TC_SS_MAX] folded BN scale, then shift
+  float* s_scale = (float*)((uint8_t*)s_idx + (tall ? 0 : Cfg::IDX_BYTES));    // [TC_SS_MAX] folded BN scale, then shift
   float* s_shift = s_scale + TC_SS_MAX;
   uint8_t* s_epi = (uint8_t*)(s_shift + TC_SS_MAX);               // [4 epilogue warps][TC_EPI_WARP_BYTES]
   uint64_t* bars = (uint64_t*)(s_epi + TC_EPI_BYTES);
@@ -482,12 +501,13 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
   uint64_t* t_full = b_empty + SB;          // [2]
   uint64_t* t_empty = t_full + 2;           // [2]
   uint32_t* s_tmem = (uint32_t*)(t_empty + 2);
+  uint64_t* scratch_bar = (uint64_t*)(s_tmem + 2);   // tall stages: commit target of the taps that do not free their A slot
 
   const ConvArgs& a = t.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.d_n ? min(*a.d_n, a.n_cap) : a.n_cap;
   const int T = t.T;
-  const bool tiled = t.tma == 2;
+  const bool tiled = t.tma >= 2;
   const int tiles_img = t.tiles_x * t.tiles_y;
   const int n_tiles_m = tiled ? (n / (a.Hout * a.Wout)) * tiles_img : (n + TC_BM - 1) / TC_BM;
   // tiled mode: output pixel of accumulator row r of M tile tm (or -1: outside the patch / the image)
@@ -518,6 +538,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
     for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), t.tma ? 1 : GT); mbar_init(smem_u32(&a_empty[s]), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 128); }
+    mbar_init(smem_u32(scratch_bar), 1);
     fence_barrier_init();
   }
   if (ss_smem)
@@ -555,7 +576,36 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
     return gm ? gm : 1u;
   };
 
-  if (warp < TC_PRODUCER_WARPS && tiled) {
+  if (warp < TC_PRODUCER_WARPS && tall) {
+    // ===================================== PRODUCER (dense 3x3, tall TMA stages) =====================================
+    // one elected thread: per (horizontal tap, 64-channel chunk, M tile) two box loads {64 ch, 8 px, 18 lines}
+    if (warp == 0 && lane == 0) {
+      const uint32_t a_ring_u32 = smem_u32(a_ring);
+      const CUtensorMap* tmap = &t.tmap;
+      uint32_t slot = 0, phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int st = unit / t.n_tiles_n;
+        const int live = min(T, n_tiles_m - st * T);
+        for (int kx = 0; kx < 3; ++kx) {
+          for (int sub = 0; sub < spo; ++sub) {
+            for (int ti = 0; ti < live; ++ti) {
+              const int tm = st * T + ti;
+              const int b = tm / tiles_img, rem = tm - b * tiles_img;
+              const int ty = rem / t.tiles_x, tx = rem - ty * t.tiles_x;
+              mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1, 2);
+              const uint32_t fbar = smem_u32(&a_full[slot]);
+              const uint32_t dst = a_ring_u32 + slot * TC_TALL_BYTES;
+              mbar_arrive_expect_tx(fbar, TC_TALL_BYTES);
+              const int x0 = tx * TC_TALL_BW - a.pw + kx, y0 = ty * TC_TALL_BH - a.ph;
+              tma_tile4d(dst, tmap, sub * TC_BK, x0, y0, b, fbar);
+              tma_tile4d(dst + TC_TALL_PLANE, tmap, a.in_ctot + sub * TC_BK, x0, y0, b, fbar);
+              if (++slot == (uint32_t)TC_TALL_SLOTS) { slot = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < TC_PRODUCER_WARPS && tiled) {
     // ===================================== PRODUCER (dense 2-D, TMA tile loads) =====================================
     // one elected thread: per A stage (M tile x tap x 64-channel chunk) two box loads (hi plane, lo plane)
     if (warp == 0 && lane == 0) {
@@ -816,6 +866,57 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
     const uint32_t a_ring_u32 = smem_u32(a_ring), b_ring_u32 = smem_u32(b_ring);
     uint32_t a_ready = 0, b_ready = 0;          // probe results for the upcoming A / B slot (issued one step ahead)
     int it = 0, trace_i = 0;
+    if (tall) {
+      // tall stages: for every (horizontal tap, chunk) the T tiles' A stages are acquired once and read by the three vertical
+      // taps at 0 / 1024 / 2048 bytes; the slot is released by the commit of the last one.  `a_slot` is the next slot to be
+      // acquired; every stage's asm block probes its barrier while the MMAs issue.
+      const uint32_t scratch = smem_u32(scratch_bar);
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+        const int st = unit / t.n_tiles_n;
+        const int live = min(T, n_tiles_m - st * T);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&t_empty[acc]), acc_phase ^ 1, 3);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int kx = 0; kx < 3; ++kx) {
+          for (int sub = 0; sub < spo; ++sub) {
+            const uint32_t g_slot = a_slot;                  // first slot of this tap column's tiles
+            for (int ky = 0; ky < 3; ++ky) {
+              if (!b_ready) mbar_spin(smem_u32(&b_full[b_slot]), b_phase, 4);
+              const uint32_t sB_hi = b_ring_u32 + b_slot * Cfg::B_BYTES, sB_lo = sB_hi + NT * TC_ROWB;
+              const uint64_t dB_hi = umma_desc_sw128(sB_hi), dB_lo = umma_desc_sw128(sB_lo);
+              const uint32_t nb_slot = b_slot + 1 == SB ? 0 : b_slot + 1, nb_phase = b_slot + 1 == SB ? b_phase ^ 1 : b_phase;
+              b_ready = mbar_test(smem_u32(&b_full[nb_slot]), nb_phase);
+              uint32_t sl = g_slot;
+              for (int ti = 0; ti < live; ++ti) {
+                if (ky == 0) {
+                  if (!a_ready) mbar_spin(smem_u32(&a_full[a_slot]), a_phase, 5);
+                  a_ready = 0;
+                  if (++a_slot == (uint32_t)TC_TALL_SLOTS) { a_slot = 0; a_phase ^= 1; }
+                }
+                tc_fence_after();
+                const uint32_t sA_hi = a_ring_u32 + sl * TC_TALL_BYTES + (uint32_t)ky * (TC_TALL_BW * TC_ROWB);
+                const uint64_t dA_hi = umma_desc_sw128(sA_hi), dA_lo = umma_desc_sw128(sA_hi + TC_TALL_PLANE);
+                const uint32_t tmem_d = tmem_base + (uint32_t)((acc * T + ti) * ACC);
+                const uint32_t nbar = smem_u32(&a_full[a_slot]);
+                const uint32_t cbar = ky == 2 ? smem_u32(&a_empty[sl]) : scratch;
+                uint32_t r;
+                if (!t.split) r = umma_stage<0>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, a_phase, cbar);
+                else if (Cfg::FUSE_N) r = umma_stage<1>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, a_phase, cbar);
+                else r = umma_stage<2>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, a_phase, cbar);
+                a_ready |= r;
+                if (++sl == (uint32_t)TC_TALL_SLOTS) sl = 0;
+              }
+              umma_commit_elect(smem_u32(&b_empty[b_slot]));
+              b_slot = nb_slot; b_phase = nb_phase;
+              accumulate = 1;
+            }
+          }
+        }
+        umma_commit_elect(smem_u32(&t_full[acc]));
+      }
+    } else
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const int st = unit / t.n_tiles_n;
       const int live = min(T, n_tiles_m - st * T);
@@ -894,8 +995,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
         uint32_t rem = unit_gmask(st);
         const int n_act = __popc(rem) * spg;
         for (int ia = 0, sub = 0; ia < n_act; ++ia) {
-          const int ks = (__ffs((int)rem) - 1) * spg + sub;
-          if (++sub == spg) { sub = 0; rem &= rem - 1; }
+          int ks;
+          if (tall) {        // order of the tall-stage MMA loop: horizontal tap, chunk, vertical tap
+            const int kx = ia / (3 * spo), r3 = ia - kx * 3 * spo, sb = r3 / 3, ky = r3 - sb * 3;
+            ks = (ky * 3 + kx) * spo + sb;
+          } else {
+            ks = (__ffs((int)rem) - 1) * spg + sub;
+            if (++sub == spg) { sub = 0; rem &= rem - 1; }
+          }
           const uint32_t bbar = smem_u32(&b_full[b_slot]);
           if (!(t.dbg & 128)) mbar_spin(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1); else mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1, 1);
           if (!(t.dbg & 4)) {
@@ -1138,25 +1245,29 @@ static int g_dbg = -1;          // FD_TC_DEBUG bits
 static int g_tma = 0;              // TMA gather4 producer where the layer allows it (measured slower than the cp.async
                                    // gather: ~6 cycles per 128-byte row in the copy engine vs ~4 through the LSU)
 static int g_tma_dense = 1;        // TMA tile loads for dense stride-1 2-D convolutions
+static int g_tall = 1;             // ... as tall stages (one load per horizontal tap feeds the three vertical taps) for 3x3 kernels
 
 template <int NT>
 static int launch_tc(TcArgs& t, cudaStream_t stream) {
   using Cfg = TcCfg<NT>;
   static bool configured = false;
-  const size_t smem = Cfg::SMEM;
+  const size_t smem = t.tma == 3 && Cfg::SMEM_TALL > Cfg::SMEM ? Cfg::SMEM_TALL : Cfg::SMEM;
   if (!configured) {
-    FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    FD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(Cfg::SMEM_TALL > Cfg::SMEM ? Cfg::SMEM_TALL : Cfg::SMEM)));
     configured = true;
   }
   // weight reuse factor: as many M tiles per weight fetch as TMEM allows while keeping >= one unit per SM (a cost model
   // that also counted the wave tail picked smaller T and measured slower: the extra weight traffic outweighs the tail)
-  const int tiles_m = t.tma == 2 ? (t.c.n_cap / (t.c.Hout * t.c.Wout)) * t.tiles_x * t.tiles_y : ceil_div(t.c.n_cap, TC_BM);
-  int T = Cfg::TMAX;
+  const int tiles_m = t.tma >= 2 ? (t.c.n_cap / (t.c.Hout * t.c.Wout)) * t.tiles_x * t.tiles_y : ceil_div(t.c.n_cap, TC_BM);
+  int T = t.tma == 3 && Cfg::TMAX > TC_TALL_T ? TC_TALL_T : Cfg::TMAX;
   while (T > 1 && (int64_t)ceil_div(tiles_m, T) * t.n_tiles_n < kNumSMs) T >>= 1;
   t.T = T;
   const int64_t units = (int64_t)ceil_div(tiles_m, T) * t.n_tiles_n;
   const int grid = units < kNumSMs ? (int)units : kNumSMs;   // persistent: one CTA per SM
-  conv_tc_kernel<NT><<<grid, TC_THREADS, smem, stream>>>(t);
+  if (t.tma == 3) conv_tc_kernel<NT, true><<<grid, TC_THREADS, smem, stream>>>(t);
+  else conv_tc_kernel<NT, false><<<grid, TC_THREADS, smem, stream>>>(t);
   FD_LAUNCHED();
   return 0;
 }
@@ -1181,7 +1292,10 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
   t.ktot_pad = pad_to(a.K * a.cin, TC_BK);
   t.n_tiles_n = t.cout_pad / NT;
   t.split = precision == FD_PREC_BF16X3;
-  if (g_dbg < 0) g_dbg = getenv("FD_TC_DEBUG") ? atoi(getenv("FD_TC_DEBUG")) : 0;
+  if (g_dbg < 0) {
+    g_dbg = getenv("FD_TC_DEBUG") ? atoi(getenv("FD_TC_DEBUG")) : 0;
+    if (getenv("FD_TC_TALL")) g_tall = atoi(getenv("FD_TC_TALL"));
+  }
   t.dbg = g_dbg;
   // TMA gather for the A operand: wide layers (Cin a multiple of the 64-channel stage) reading split-bf16 rows
   t.tma = 0;
@@ -1233,6 +1347,18 @@ int conv_forward_tc(const ConvArgs& a, int precision, cudaStream_t stream) {
     t.tma = 2;
     t.bw = bw; t.bh = bh;
     t.tiles_x = ceil_div(a.Wout, bw); t.tiles_y = ceil_div(a.Hout, bh);
+    if (g_tall && a.kh == 3 && a.kw == 3 && a.Wout >= TC_TALL_BW && a.Hout >= TC_TALL_BH) {
+      // tall stages: 8 x 16-pixel tiles, box {64 ch, 8 px, 18 lines}
+      const cuuint32_t tbox[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_TALL_BW, (cuuint32_t)(TC_TALL_BH + 2), 1};
+      cr = enc(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.in, dims, strides, tbox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS)
+        return set_error((int)cr, "fd_conv_forward: cuTensorMapEncodeTiled (tall box) failed (%d)", (int)cr);
+      t.tma = 3;
+      t.bw = TC_TALL_BW; t.bh = TC_TALL_BH;
+      t.tiles_x = ceil_div(a.Wout, t.bw); t.tiles_y = ceil_div(a.Hout, t.bh);
+    }
   }
   switch (NT) {
     case 128: return launch_tc<128>(t, stream);
@@ -1253,7 +1379,7 @@ int fd_debug_read_tc_trace(long long* out, int role) {
                                    sizeof(long long) * fd::TC_TRACE_N * role, cudaMemcpyDeviceToHost);
 }
 
-/* perf-triage helper (not part of the documented ABI): key 0 = FD_TC_DEBUG bits, 5 = TMA gather4 producer on/off, 6 = TMA tile loads for dense convs on/off, 7 = mbarrier watchdog
+/* perf-triage helper (not part of the documented ABI): key 0 = FD_TC_DEBUG bits, 5 = TMA gather4 producer on/off, 6 = TMA tile loads for dense convs on/off, 7 = mbarrier watchdog, 8 = tall stages for dense 3x3 convs on/off
  * (the ring-size and L1-gather knobs of the round-2 triage were removed again: run-time ring sizes cost the narrow
  * layers 10 %, gathers through L1 gained nothing) */
 int fd_debug_set_tc(int key, int value) {
@@ -1261,6 +1387,7 @@ int fd_debug_set_tc(int key, int value) {
     case 0: fd::g_dbg = value; return 0;
     case 5: fd::g_tma = value; return 0;
     case 6: fd::g_tma_dense = value; return 0;
+    case 8: fd::g_tall = value; return 0;
     case 7: {                                     // watchdog of the mbarrier waits, in units of 2^30 cycles (0: ~never)
       const long long v = value > 0 ? (long long)value << 30 : (1LL << 62);
       return (int)cudaMemcpyToSymbol(fd::g_tc_timeout, &v, sizeof(v));

@@ -255,6 +255,9 @@ def bn_train(tape, x, bn, grads, residual=None, relu=True, out=None, prec="fp32"
     return y
 
 
+DGRAD_AS_CONV = True       # data gradients of stride-1 "same" Conv2d layers through the forward convolution path
+
+
 def conv2d_train(tape, x, conv, grads, prec, pad=None, out=None):
     """Conv2d / ConvTranspose2d(k == s) (+ bias) on channels-last x.t [B,H,W,Cin]."""
     transposed = isinstance(conv, nn.ConvTranspose2d)
@@ -291,6 +294,12 @@ def conv2d_train(tape, x, conv, grads, prec, pad=None, out=None):
             gin = ops.Feat(gys, "split") if (gys is not None and pd != "fp32") else gy
             if transposed:   # each input pixel fed k*k output pixels: a k x k stride-k conv over dL/dy
                 gx = ops.conv2d_nhwc(gin, wt, ksize, stride, (0, 0), precision=pd, out_fmt="fp32")
+                gx = gx.t if isinstance(gx, ops.Feat) else gx
+            elif DGRAD_AS_CONV and stride == (1, 1) and all(2 * p_ == k_ - 1 for p_, k_ in zip(padding, ksize)):
+                # a "same" convolution's data gradient is the same convolution over dL/dy with flipped, transposed taps:
+                # gx[i] = sum_k gy[i - k + p] W[k]^T = sum_k' gy[i + k' - p] W[K-1-k']^T  -- it then takes the forward kernels'
+                # dense fast path (TMA tile loads, tall stages for 3x3) instead of the per-thread gather of the dgrad mode
+                gx = ops.conv2d_nhwc(gin, wt.flip(0).contiguous(), ksize, stride, padding, precision=pd, out_fmt="fp32")
                 gx = gx.t if isinstance(gx, ops.Feat) else gx
             else:
                 gx = T.conv2d_dgrad(gin, wt, (H, W), ksize, stride, padding, precision=pd)

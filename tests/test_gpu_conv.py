@@ -222,3 +222,25 @@ def test_sorted_tiles_bit_identical(cuda, cin, cout, monkeypatch):
             yb = ops.sparse_conv(xin, w, rb, scale, shift, rin, True, precision=prec, out_fmt=fmt, sort_tiles=True)
             ya, yb = (ya.t, yb.t) if fmt == "split" else (ya, yb)
             assert torch.equal(ya[:n].view(torch.int32), yb[:n].view(torch.int32)), (prec, fmt)
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(64, 64, 37, 29), (128, 128, 16, 8), (256, 256, 45, 45), (128, 11, 33, 40),
+                                          (512, 64, 20, 19), (64, 384, 17, 9)])
+def test_dense_3x3_tall_stages(cuda, cin, cout, H, W):
+    """Dense 3x3 stride-1 convolutions on split-bf16 rows take the tall-stage TMA path (8 x 16-pixel tiles, one
+    {64 ch, 8 px, 18 lines} box per horizontal tap feeding the three vertical taps): maps that are not multiples of the
+    tile, image borders (zero padding = out-of-bounds fill), several channel chunks, N tiles and tile widths, residual."""
+    g = torch.Generator().manual_seed(cin + cout + H)
+    B = 3
+    x = torch.randn((B, cin, H, W), generator=g)
+    w = torch.randn((cout, cin, 3, 3), generator=g) / np.sqrt(cin * 9)
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g)
+    res = torch.randn((B, cout, H, W), generator=g)
+    want = F.relu(F.conv2d(x, w, None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None] + res)
+    wk = w.permute(2, 3, 1, 0).reshape(9, cin, cout).contiguous().to(cuda)
+    xs = ops.to_split(x.permute(0, 2, 3, 1).contiguous().to(cuda))
+    rs = res.permute(0, 2, 3, 1).contiguous().to(cuda)
+    y = ops.conv2d_nhwc(xs, wk, (3, 3), (1, 1), (1, 1), scale.to(cuda), shift.to(cuda), True, residual=rs,
+                        precision="bf16x3", out_fmt="split")
+    torch.testing.assert_close(y.to_fp32().permute(0, 3, 1, 2).cpu(), want, rtol=3e-4, atol=3e-4)
