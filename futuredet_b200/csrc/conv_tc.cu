@@ -501,7 +501,6 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
   uint64_t* t_full = b_empty + SB;          // [2]
   uint64_t* t_empty = t_full + 2;           // [2]
   uint32_t* s_tmem = (uint32_t*)(t_empty + 2);
-  uint64_t* scratch_bar = (uint64_t*)(s_tmem + 2);   // tall stages: commit target of the taps that do not free their A slot
 
   const ConvArgs& a = t.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -535,10 +534,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
   if (threadIdx.x == 0) {
     // A stage complete: every thread of the filling group arrives (cp.async path) / one expect_tx arrival + the
     // stage's bytes (TMA path)
-    for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), t.tma ? 1 : GT); mbar_init(smem_u32(&a_empty[s]), 1); }
+    // (tall stages: a slot is free when the commits of all three vertical taps have arrived)
+    for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), t.tma ? 1 : GT); mbar_init(smem_u32(&a_empty[s]), tall ? 3 : 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 128); }
-    mbar_init(smem_u32(scratch_bar), 1);
     fence_barrier_init();
   }
   if (ss_smem)
@@ -868,9 +867,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
     int it = 0, trace_i = 0;
     if (tall) {
       // tall stages: for every (horizontal tap, chunk) the T tiles' A stages are acquired once and read by the three vertical
-      // taps at 0 / 1024 / 2048 bytes; the slot is released by the commit of the last one.  `a_slot` is the next slot to be
+      // taps at 0 / 1024 / 2048 bytes; every tap commits to the slot's empty barrier, which expects three arrivals.  `a_slot` is the next slot to be
       // acquired; every stage's asm block probes its barrier while the MMAs issue.
-      const uint32_t scratch = smem_u32(scratch_bar);
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
         const int st = unit / t.n_tiles_n;
         const int live = min(T, n_tiles_m - st * T);
@@ -900,7 +898,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
                 const uint64_t dA_hi = umma_desc_sw128(sA_hi), dA_lo = umma_desc_sw128(sA_hi + TC_TALL_PLANE);
                 const uint32_t tmem_d = tmem_base + (uint32_t)((acc * T + ti) * ACC);
                 const uint32_t nbar = smem_u32(&a_full[a_slot]);
-                const uint32_t cbar = ky == 2 ? smem_u32(&a_empty[sl]) : scratch;
+                const uint32_t cbar = smem_u32(&a_empty[sl]);       // third arrival (ky == 2) completes the phase
                 uint32_t r;
                 if (!t.split) r = umma_stage<0>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, a_phase, cbar);
                 else if (Cfg::FUSE_N) r = umma_stage<1>(tmem_d, dA_hi, dA_lo, dB_hi, dB_lo, IDESC, IDESC2, accumulate, nbar, a_phase, cbar);

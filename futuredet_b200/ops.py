@@ -118,8 +118,10 @@ class BitmapIndex:
 
 SORT_TILES = os.environ.get("FD_SORT_TILES", "1") != "0"   # tensor-core inference convs over 3x3x3 rulebooks run on pattern-sorted tiles (Rulebook.sorted_tiles)
 SORT_WINDOW = int(os.environ.get("FD_SORT_WINDOW", 256 * 1024))     # rows per sorting window (a few scenes of a level: the gathered rows stay L2 resident)
-SORT_STRIDED = os.environ.get("FD_SORT_STRIDED", "0") != "0"   # also sort the tables of the strided convs (one launch each:
-                             # the copy costs what the launch gains)
+SORT_STRIDED = os.environ.get("FD_SORT_STRIDED", "0") != "0"   # also sort the strided tables that come without keys (the
+                             # input-side scatter build of the first strided conv): one launch per table, and the copy plus
+                             # the key pass cost more than the launch gains.  Strided tables whose search hands the keys over
+                             # (levels 3, 4) are sorted: +0.25 ms per 16 scenes
 SORT_MIN_BATCH = int(os.environ.get("FD_SORT_MIN_BATCH", 2))   # scenes per forward from which the sort pays for its launches
 SORT_MIN_ROWS = 4096         # smaller levels are not worth three more launches
 
@@ -260,11 +262,14 @@ def rulebook_conv(coords, n_dev, n_cap, batch_size, shape, ksize, stride, paddin
                                                L.i32x3(out_shape), L.i32x3(ksize), L.i32x3(stride), L.i32x3(padding),
                                                _ptr(n_out), n_out_cap, _ptr(nbr), stride_n, _ptr(tmask), _stream())
         L.check(rc, "fd_rulebook_neighbors_scatter")
+        row_key = None
     else:
         index = index or CoordIndex(coords, n_dev, n_cap, shape, batch_size)
-        nbr, pair_num, K, tmask, _ = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding)
+        nbr, pair_num, K, tmask, row_key = _neighbors(out_coords, n_out, n_out_cap, index, ksize, stride, padding,
+                                                      want_keys=SORT_TILES and n_out_cap >= SORT_MIN_ROWS)
     rb = Rulebook(nbr, pair_num, K, out_coords, n_out, n_out_cap, out_shape, list(ksize), list(stride),
                   list(padding), tmask)
+    rb.row_key = row_key        # output-side (bitmap / hash) searches hand the sort keys over; the scatter build cannot
     rb.out_index = BitmapIndex(bitmap, prefix, out_shape)      # index of the OUTPUT set for the layers that follow
     return rb, index
 

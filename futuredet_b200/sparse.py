@@ -164,8 +164,8 @@ class _SparseConvBase(SparseModule):
             return ops.sparse_conv(xin, w, rb, scale, shift, None, relu, precision=prec,
                                    bev=(x.batch_size, D, H, W), out_fmt=out_fmt, bev_dmajor=bev_dmajor)
         y = ops.sparse_conv(xin, w, rb, scale, shift, residual, relu, precision=prec, out_fmt=out_fmt,
-                            sort_tiles=prec != "fp32" and (self.subm or ops.SORT_STRIDED) and
-                            x.batch_size >= ops.SORT_MIN_BATCH)
+                            sort_tiles=prec != "fp32" and x.batch_size >= ops.SORT_MIN_BATCH and
+                            (self.subm or ops.SORT_STRIDED or rb.row_key is not None))
         if self.subm:
             return x._like(y)
         out = x._like(y, rb.out_coords, rb.out_shape, rb.n_out_dev, rb.n_out_cap)

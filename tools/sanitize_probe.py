@@ -21,7 +21,7 @@ if os.environ.get("FD_NO_WATCHDOG"):          # the sanitizers slow kernels down
     _L.fd_debug_set_tc.argtypes = [C.c_int, C.c_int]
     torch.zeros(1, device=dev)
     assert _L.fd_debug_set_tc(7, 0) == 0
-which = sys.argv[1:] or ["voxelize", "conv", "dense", "wgrad", "bn", "predict", "model"]
+which = sys.argv[1:] or ["voxelize", "conv", "sort", "dense", "tall", "wgrad", "bn", "predict", "model"]
 
 
 def sites(B, shape, n):
@@ -41,7 +41,7 @@ if "voxelize" in which:
     v = ops.voxelize_vfe(pts, off, NUSC_VOXEL, NUSC_RANGE, 10, 4000, num_feat=5, feat_stride=8)
     print("voxelize: %d voxels" % int(v["total"].item()))
 
-if "conv" in which or "wgrad" in which:
+if "conv" in which or "wgrad" in which or "sort" in which:
     shape, B = [9, 24, 24], 2
     c = sites(B, shape, 3000)
     n = len(c)
@@ -59,6 +59,31 @@ if "conv" in which:
         ref = ops.sparse_conv(x.to_fp32(), w, rb2, relu=True, precision="fp32")
         no = int(rb2.n_out_dev.item())            # rows past the active count are undefined
         print("sparse conv %d->%d: max |tc - fp32| %.2e" % (cin, cout, float((y2[:no] - ref[:no]).abs().max())))
+
+if "sort" in which:
+    # pattern-sorted tiles: the counting sort (keys from the neighbour search and from the table), the row_perm epilogue
+    ops.SORT_MIN_ROWS, ops.SORT_WINDOW = 0, 2048
+    for r in (rb, rb2):
+        r._sorted = None
+    rb_k, _ = ops.rulebook_subm(ct, nd, n, shape, [3, 3, 3], batch_size=B)          # with row keys
+    rb2.row_key = None                                                              # keys computed from the table
+    for cin, cout, table in ((16, 16, rb_k), (64, 64, rb_k), (32, 64, rb2)):
+        x = ops.to_split(torch.randn((n, cin), device=dev))
+        w = torch.randn((27, cin, cout), device=dev) / np.sqrt(27 * cin)
+        res = x if cin == cout else None
+        ya = ops.sparse_conv(x, w, table, residual=res, relu=True, precision="bf16x3", out_fmt="split", sort_tiles=False)
+        yb = ops.sparse_conv(x, w, table, residual=res, relu=True, precision="bf16x3", out_fmt="split", sort_tiles=True)
+        no = int(table.n_out_dev.item())
+        print("sorted conv %d->%d: identical %s" % (cin, cout, bool(torch.equal(ya.t[:no].view(torch.int32), yb.t[:no].view(torch.int32)))))
+
+if "tall" in which:
+    for cin, cout, H, W in ((64, 64, 21, 13), (128, 16, 16, 8), (128, 256, 18, 17)):   # tall TMA stages of the dense 3x3 layers
+        x = torch.randn((2, H, W, cin), device=dev)
+        w = torch.randn((9, cin, cout), device=dev) / np.sqrt(9 * cin)
+        y = ops.conv2d_nhwc(ops.to_split(x), w, (3, 3), (1, 1), (1, 1), relu=True, precision="bf16x3", out_fmt="fp32")
+        ref = ops.conv2d_nhwc(x, w, (3, 3), (1, 1), (1, 1), relu=True, precision="fp32")
+        y = y.t if isinstance(y, ops.Feat) else y
+        print("tall dense conv %d->%d %dx%d: max |tc - fp32| %.2e" % (cin, cout, H, W, float((y - ref).abs().max())))
 
 if "dense" in which:
     for cin, cout, k, s in ((64, 128, 3, 1), (128, 64, 1, 1), (64, 64, 3, 2)):            # TMA tile loads (stride 1) / cp.async
