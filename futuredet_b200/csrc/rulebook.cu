@@ -10,6 +10,8 @@
 //   * the rulebook is stored in gather form nbr[k][o] (input row or -1), which is what
 //     the output-stationary implicit-GEMM kernels consume -- no scatter atomics, so the
 //     convolution is deterministic.  fd_rulebook_to_pairs() exports spconv's layout.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -426,7 +428,7 @@ rowsort_scan_kernel(int32_t* __restrict__ win_hist, int window) {
 // inside the CTA + the row's rank), so that consecutive local positions of one key map to consecutive sorted positions:
 // the columns are then read in source order (coalesced), transposed through shared memory RS_KB columns at a time and
 // written as runs of consecutive table entries instead of one 4-byte store per (row, offset) at a random place.
-constexpr int RS_KB = 9;               // table columns staged per round (3 rounds for 27 offsets)
+template <int RS_KB>                   // table columns staged per round
 __global__ void __launch_bounds__(256)
 rowsort_scatter_kernel(const int32_t* __restrict__ nbr, int nbr_stride, int K, const int32_t* __restrict__ d_n, int n_cap,
                        int window, const uint16_t* __restrict__ keys, const uint16_t* __restrict__ lrank,
@@ -726,15 +728,23 @@ int fd_rulebook_sort_rows(const int32_t* d_nbr, int nbr_stride, int K, const int
   FD_LAUNCHED();
   rowsort_scan_kernel<<<wins, RS_BUCKETS, 0, stream>>>(win_hist, window);
   FD_LAUNCHED();
-  static bool configured = false;
-  constexpr int kStageBytes = RS_KB * RS_ROWS * (int)sizeof(int);
-  if (!configured) {
-    FD_CUDA(cudaFuncSetAttribute(rowsort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
-    configured = true;
+  static int kb = 0;
+  if (!kb) {
+    // columns staged per round: 3 (24 KB, 7 CTAs per SM).  Measured per 16-scene forward (six tables): 9 columns (2 CTAs per SM)
+    // 1.50 ms, 5: 1.22, 3: 1.09, 2: 1.06, 1: 1.06 -- the kernel is occupancy (latency) bound, not bound by the number of rounds
+    kb = getenv("FD_RS_KB") ? atoi(getenv("FD_RS_KB")) : 3;
+    FD_CUDA(cudaFuncSetAttribute(rowsort_scatter_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * RS_ROWS * 4));
+    FD_CUDA(cudaFuncSetAttribute(rowsort_scatter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * RS_ROWS * 4));
+    FD_CUDA(cudaFuncSetAttribute(rowsort_scatter_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * RS_ROWS * 4));
+    FD_CUDA(cudaFuncSetAttribute(rowsort_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RS_ROWS * 4));
+    FD_CUDA(cudaFuncSetAttribute(rowsort_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 * RS_ROWS * 4));
   }
-  rowsort_scatter_kernel<<<blocks, 256, kStageBytes, stream>>>(d_nbr, nbr_stride, K, d_n_out, n_out_cap, window,
-                                                     d_row_key ? d_row_key : keys, lrank, blk_base,
-                                                     win_hist, d_row_perm, d_nbr_sorted, d_tile_mask_sorted);
+#define FD_RS_LAUNCH(KB)                                                                                              \
+  rowsort_scatter_kernel<KB><<<blocks, 256, KB * RS_ROWS * 4, stream>>>(d_nbr, nbr_stride, K, d_n_out, n_out_cap, window, \
+                                                     d_row_key ? d_row_key : keys, lrank, blk_base,                   \
+                                                     win_hist, d_row_perm, d_nbr_sorted, d_tile_mask_sorted)
+  if (kb == 1) FD_RS_LAUNCH(1); else if (kb == 2) FD_RS_LAUNCH(2); else if (kb == 3) FD_RS_LAUNCH(3); else if (kb == 5) FD_RS_LAUNCH(5); else FD_RS_LAUNCH(9);
+#undef FD_RS_LAUNCH
   FD_LAUNCHED();
   return 0;
 }
