@@ -513,7 +513,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
   auto tile_row_to_o = [&](int tm, int r) -> int {
     const int b = tm / tiles_img, rem = tm - b * tiles_img;
     const int ty = rem / t.tiles_x, tx = rem - ty * t.tiles_x;
-    const int h = r / t.bw, w = r - h * t.bw;
+    const int h = TALL ? r / TC_TALL_BW : r / t.bw, w = r - h * (TALL ? TC_TALL_BW : t.bw);
     const int oy = ty * t.bh + h, ox = tx * t.bw + w;
     if (h >= t.bh || oy >= a.Hout || ox >= a.Wout) return -1;
     return (b * a.Hout + oy) * a.Wout + ox;
@@ -1052,7 +1052,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs t) {
 #pragma unroll
         for (int k = 0; k < NCHq; ++k) {
           const int rr = k * RPIq + lane / NCHq;
-          const int v = a.row_perm ? __shfl_sync(0xffffffffu, o, rr)
+          // (the common instantiation keeps its round-2 arithmetic: at the 128-register ceiling any change to this code moves
+          // ptxas's spills into the gather producers -- taking the row from lane rr everywhere cost the sparse family 8 %)
+          const int v = (TALL || a.row_perm) ? __shfl_sync(0xffffffffu, o, rr)
                         : tiled    ? tile_row_to_o(st * T + ti, q * 32 + rr) : (st * T + ti) * TC_BM + q * 32 + rr;
           orr_k[k] = (v >= 0 && v < n) ? v : -1;
         }

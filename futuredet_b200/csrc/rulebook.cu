@@ -55,6 +55,14 @@ __device__ __forceinline__ int coord_index_resolve(const unsigned long long* __r
   }
 }
 
+// t = q * s exactly?  Strides are 1 or 2 in every layer of the backbone: no integer division on those paths.
+__device__ __forceinline__ bool exact_div(int t, int s, int& q) {
+  if (s == 1) { q = t; return true; }
+  if (s == 2) { q = t >> 1; return (t & 1) == 0; }
+  q = t / s;
+  return q * s == t;
+}
+
 // mark every output cell reachable from an active input: out = (in + p - k) / s when divisible
 __global__ void __launch_bounds__(256)
 outset_mark(const int4* __restrict__ coords, const int32_t* __restrict__ d_n, int n_cap, Conv3Geom g,
@@ -64,18 +72,18 @@ outset_mark(const int4* __restrict__ coords, const int32_t* __restrict__ d_n, in
     int4 c = coords[i];
     for (int kz = 0; kz < g.k[0]; ++kz) {
       int tz = c.y + g.p[0] - kz;
-      if (tz < 0 || tz % g.s[0]) continue;
-      int oz = tz / g.s[0];
+      int oz;
+      if (tz < 0 || !exact_div(tz, g.s[0], oz)) continue;
       if (oz >= osh.d) continue;
       for (int ky = 0; ky < g.k[1]; ++ky) {
         int ty = c.z + g.p[1] - ky;
-        if (ty < 0 || ty % g.s[1]) continue;
-        int oy = ty / g.s[1];
+        int oy;
+        if (ty < 0 || !exact_div(ty, g.s[1], oy)) continue;
         if (oy >= osh.h) continue;
         for (int kx = 0; kx < g.k[2]; ++kx) {
           int tx = c.w + g.p[2] - kx;
-          if (tx < 0 || tx % g.s[2]) continue;
-          int ox = tx / g.s[2];
+          int ox;
+          if (tx < 0 || !exact_div(tx, g.s[2], ox)) continue;
           if (ox >= osh.w) continue;
           long long key = lin_key(c.x, oz, oy, ox, osh);
           // up to 27 inputs mark the same output cell: look before the atomic (a stale 0 only costs a redundant atomicOr)
@@ -93,16 +101,23 @@ outset_emit(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ pre
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words;
        w += (int64_t)gridDim.x * blockDim.x) {
     uint32_t bits = bitmap[w];
+    if (!bits) continue;
     int row = prefix[w];
+    // the word's first cell is decoded once with 32-bit divisions (B*D*H*W < 2^32); its bits are consecutive cells
+    uint32_t t = (uint32_t)w * 32u;
+    const int x0 = (int)(t % (uint32_t)osh.w); t /= (uint32_t)osh.w;
+    const int y0 = (int)(t % (uint32_t)osh.h); t /= (uint32_t)osh.h;
+    const int z0 = (int)(t % (uint32_t)osh.d);
+    const int b0 = (int)(t / (uint32_t)osh.d);
     while (bits) {
       int j = __ffs(bits) - 1;
       bits &= bits - 1;
       if (row < n_out_cap) {
-        long long key = w * 32 + j;
-        int x = (int)(key % osh.w); key /= osh.w;
-        int y = (int)(key % osh.h); key /= osh.h;
-        int z = (int)(key % osh.d); key /= osh.d;
-        out_coords[row] = make_int4((int)key, z, y, x);
+        int x = x0 + j, y = y0, z = z0, b = b0;
+        while (x >= osh.w) { x -= osh.w; ++y; }
+        while (y >= osh.h) { y -= osh.h; ++z; }
+        while (z >= osh.d) { z -= osh.d; ++b; }
+        out_coords[row] = make_int4(b, z, y, x);
       }
       ++row;
     }
@@ -256,18 +271,18 @@ neighbors_scatter_kernel(const int4* __restrict__ in_coords, const int32_t* __re
     const int4 c = in_coords[i];
     for (int kz = 0; kz < g.k[0]; ++kz) {
       const int tz = c.y + g.p[0] - kz;
-      if (tz < 0 || tz % g.s[0]) continue;
-      const int oz = tz / g.s[0];
+      int oz;
+      if (tz < 0 || !exact_div(tz, g.s[0], oz)) continue;
       if (oz >= osh.d) continue;
       for (int ky = 0; ky < g.k[1]; ++ky) {
         const int ty = c.z + g.p[1] - ky;
-        if (ty < 0 || ty % g.s[1]) continue;
-        const int oy = ty / g.s[1];
+        int oy;
+        if (ty < 0 || !exact_div(ty, g.s[1], oy)) continue;
         if (oy >= osh.h) continue;
         for (int kx = 0; kx < g.k[2]; ++kx) {
           const int tx = c.w + g.p[2] - kx;
-          if (tx < 0 || tx % g.s[2]) continue;
-          const int ox = tx / g.s[2];
+          int ox;
+          if (tx < 0 || !exact_div(tx, g.s[2], ox)) continue;
           if (ox >= osh.w) continue;
           const long long key = lin_key(c.x, oz, oy, ox, osh);
           const uint32_t bits = __ldg(out_bitmap + (key >> 5));
