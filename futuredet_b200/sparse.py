@@ -155,6 +155,10 @@ class _SparseConvBase(SparseModule):
             if xin.fmt == "fp32" and xin.ctot >= cin_pad and xin.c0 == 0:
                 # e.g. the 5-channel stem fed by the fused voxelizer (rows zero-padded to 8 channels)
                 xin, w = ops.Feat(xin.t, "fp32", 0, cin_pad), self.weight_kio(cin_pad)
+                if ops.STEM_SPLIT and x.batch_size >= ops.SORT_MIN_BATCH:     # (one more launch: not at one scene per forward)
+                    # one small conversion pass, then the stem gathers ready-made bf16 hi/lo rows with cp.async like every
+                    # other layer instead of splitting fp32 rows in its producer warps
+                    xin = ops.to_split(xin, x.n_dev)
             else:
                 prec = "fp32"       # no tensor-core tile shape for this Cin: exact fp32 CUDA-core arm, explicitly
         if out_fmt is None:

@@ -171,6 +171,27 @@ def test_forward_host_matches_forward_points(cuda):
         torch.testing.assert_close(res[0][..., -1:], want, rtol=0, atol=0)
 
 
+def test_batched_inference_paths_are_bit_identical(cuda, monkeypatch):
+    """From ops.SORT_MIN_BATCH scenes per forward the SubM / keyed strided convolutions run on pattern-sorted tiles and
+    the stem gathers pre-split rows; both only move data differently -- every head tensor is bit-identical to the
+    small-batch path (which the oracle tests above pin)."""
+    from futuredet_b200 import ops
+    monkeypatch.setattr(ops, "SORT_MIN_ROWS", 0)
+    m = build_model(3, cuda).to(cuda)
+    m.configure_voxelizer(dict(range=NUSC_RANGE, voxel_size=NUSC_VOXEL, max_points_in_voxel=10,
+                               max_voxel_num=[120000, 160000]))
+    scenes = [synth_scene(30000 + 5000 * i, seed=40 + i) for i in range(3)]
+    pts = torch.from_numpy(np.concatenate(scenes)).to(cuda)
+    off = torch.tensor(np.r_[0, np.cumsum([len(s) for s in scenes])], dtype=torch.int32, device=cuda)
+    outs = []
+    for min_batch in (100, 1):
+        monkeypatch.setattr(ops, "SORT_MIN_BATCH", min_batch)
+        outs.append(m.forward_points(pts, off))
+    for a, b in zip(*outs):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # The BENCHED configuration, end to end (BASELINE configs[1] / [2] / [4]): full 10-sweep scenes, the 160 k-voxel cap
 # hit, the tensor-core arm that bench.py times, every head tensor <= 1e-3 from the fp32 oracle chain.
