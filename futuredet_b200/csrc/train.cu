@@ -817,6 +817,7 @@ static int wgrad_entry(const fd_conv_desc* d, float* d_dw, float* ws, size_t ws_
   FD_REQUIRE(d->cin >= 1 && d->cout >= 1 && d->K >= 1, "fd_conv_wgrad: bad cin/cout/K");
   FD_REQUIRE(d->in_format == FD_FMT_FP32 && d->out_format == FD_FMT_FP32, "fd_conv_wgrad: fp32 rows only");
   FD_REQUIRE(d->in_stride >= d->cin && d->n_out_cap >= 0, "fd_conv_wgrad: bad stride / row count");
+  FD_REQUIRE(d->d_row_perm == nullptr, "fd_conv_wgrad: d_row_perm (sorted tables) is a forward-only option; pass the unsorted table");
   ConvArgs a{};
   a.in = (const float*)d->d_in; a.in_stride = d->in_stride; a.cin = d->cin;
   a.in_fmt = FD_FMT_FP32; a.in_ctot = d->cin; a.out_fmt = FD_FMT_FP32; a.out_ctot = d->cout;
