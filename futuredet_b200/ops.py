@@ -122,7 +122,7 @@ SORT_STRIDED = os.environ.get("FD_SORT_STRIDED", "0") != "0"   # also sort the s
                              # input-side scatter build of the first strided conv): one launch per table, and the copy plus
                              # the key pass cost more than the launch gains.  Strided tables whose search hands the keys over
                              # (levels 3, 4) are sorted: +0.25 ms per 16 scenes
-SORT_MIN_BATCH = int(os.environ.get("FD_SORT_MIN_BATCH", 2))   # scenes per forward from which the sort pays for its launches
+SORT_MIN_BATCH = int(os.environ.get("FD_SORT_MIN_BATCH", 3))   # scenes per forward from which the sort pays for its launches
 STEM_SPLIT = os.environ.get("FD_STEM_SPLIT", "1") != "0"
 SORT_MIN_ROWS = 4096         # smaller levels are not worth three more launches
 
